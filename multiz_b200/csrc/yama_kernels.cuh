@@ -1,0 +1,476 @@
+// yama_kernels.cuh -- sm_100a kernels for the batched yama hot path.
+//
+// What is computed is defined by the reference (multiz mz_yama.c:50-320); HOW is new:
+//
+//  K1 yb_profile_kernel   one CTA per block pair.  Every alignment column is reduced to a count
+//                         vector: 6 character classes (A,C,G,T,other,'-'; mz_scores.c:39-54 only ever
+//                         distinguishes these) and the dash-transition counts between neighbouring
+//                         columns that the quasi-natural gap costs need (mz_scores.c:57-79).  With
+//                         those, each O(K*L) loop of mz_yama.c:124-137/:174-201/:212-225 collapses to
+//                         a 4-term integer dot product of byte counts (dp4a) and the sum-of-pairs
+//                         score (mz_yama.c:199-201) to a 6-term 16x8-bit dot product (dp2a).
+//                         Also produces the per-row traceback offsets and the wavefront schedule.
+//  K2 yb_fill_kernel      one warp per block pair, persistent, pairs pulled from a queue.  Lane l owns
+//                         rows l+1, l+33, ... and walks its row left to right; lane l is always one
+//                         column behind lane l-1, so at every step the warp advances one anti-diagonal
+//                         of the band.  (C,D,I) of the row above arrive through a 2-slot shared-memory
+//                         mailbox per lane; lane 31 -> lane 0 goes through a ring that holds one band
+//                         row.  One traceback byte per cell (mz_yama.c:253) is packed 4 at a time into
+//                         32-bit stores.
+//  K3 yb_traceback_kernel one thread per pair follows the packed pointers (mz_yama.c:257-291) and emits
+//                         the edit script.
+//
+// Exactness: every in-band cell gets exactly the reference's int32 value and traceback byte, including
+// the "predecessor does not exist -> no gap-open charge" guards (mz_yama.c:131-135,180-186,218-223) and
+// the MININT-minus-penalty values on the right fringe (mz_yama.c:93-94).  The guards are carried as data:
+// every mailbox record holds, next to (C,D,I), the multipliers (-gap_open or 0) that a consumer applies
+// to its gap-open counts for the C and I node of that grid point.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace yb {
+
+constexpr int MININT = -1073741824;  // INT_MIN/2, mz_yama.c:29
+constexpr int FLAG_C = 0, FLAG_I = 1, FLAG_D = 2;  // mz_yama.c:24-26
+
+struct ScoreConst {
+    int S6[6][6];   // substitution score per class pair
+    int gap_open;   // GO
+    int gap_ext;    // GE
+};
+__constant__ ScoreConst c_sc;
+
+// ---- per-pair descriptor (device copy) --------------------------------------------------------
+struct PairMeta {
+    int K, M, L, N;
+    unsigned long long offA, offB;     // byte offsets into the input blob
+    unsigned long long offLB, offRB;   // byte offsets into the input blob (int32 arrays, M+1 each)
+    unsigned long long rowBase;        // index of row 0's RowRec in the RowRec pool (M+1 records)
+    unsigned long long colBase;        // index of column 0's ColRec in the ColRec pool (N+1 records)
+    unsigned long long tbBase;         // byte offset of this pair's traceback matrix
+    unsigned long long scriptBase;     // byte offset of this pair's script (M+N bytes)
+    unsigned long long schedBase;      // index into the schedule pool (ceil(M/32) ints)
+    int ringNeed;                      // widest band row + 32 (host computed)
+    int pad;
+};
+
+// Row record, 64 B.  v[] are byte-count vectors matched against the column words (see ColRec).
+struct __align__(16) RowRec {
+    unsigned avXC, avYC, avZC, avXI;   // C-node x,y,z and I-node x coefficient bytes
+    unsigned avXD, avYD, avZD;         // D-node x,y,z coefficient bytes (bytes 2,3 only)
+    int eD;                            // ndA*L*gap_ext  (mz_yama.c:239-242)
+    unsigned w01, w23, w45;            // S6^T * classcount(A row) as int16 pairs (sum-of-pairs weights)
+    int LB, RB, LBp, RBp;              // band of this row and of the row above
+    unsigned rowoff;                   // byte offset of this row inside the pair's traceback matrix
+};
+
+// Column record, 16 B.
+//  w0 = (b01, ndB, dB, b10)           raw transition / dash counts of column c against column c-1
+//  w1 = (n_A, n_C, n_G, n_T)          class counts
+//  w2 = (n_X, n_dash, ndB', dB')      ndB',dB' zeroed for c==0 and c==N  (mz_yama.c:211, end gaps free)
+//  w3 = w0 zeroed for c==1            (mz_yama.c:173, no gap-open at the start)
+struct __align__(16) ColRec { unsigned w0, w1, w2, w3; };
+
+struct PairOut { int m_new, C, D, I, status, pad; };
+
+__device__ __forceinline__ int classify(unsigned ch) {
+    unsigned u = ch | 0x20u;
+    if (ch == '-') return 5;
+    if (u == 'a') return 0;
+    if (u == 'c') return 1;
+    if (u == 'g') return 2;
+    if (u == 't') return 3;
+    return 4;
+}
+
+__device__ __forceinline__ int dp4a_uu(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_su(unsigned a16x2, unsigned b8x4, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(unsigned a16x2, unsigned b8x4, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned pack4(unsigned b0, unsigned b1, unsigned b2, unsigned b3) {
+    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+__device__ __forceinline__ unsigned pack16(int lo, int hi) {
+    return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+}
+
+// =================================================================================================
+// K1: column / row profiles, traceback row offsets, wavefront schedule.  One CTA per pair.
+// =================================================================================================
+constexpr int K1_THREADS = 128;
+
+__global__ void __launch_bounds__(K1_THREADS)
+yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__restrict__ blob,
+                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int *__restrict__ schedPool) {
+    const PairMeta pm = metas[blockIdx.x];
+    const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
+    const unsigned char *A = blob + pm.offA;
+    const unsigned char *B = blob + pm.offB;
+    const int *LB = reinterpret_cast<const int *>(blob + pm.offLB);
+    const int *RB = reinterpret_cast<const int *>(blob + pm.offRB);
+    RowRec *rows = rowPool + pm.rowBase;
+    ColRec *cols = colPool + pm.colBase;
+    const int GE = c_sc.gap_ext;
+
+    // ---- columns of B (c = 0..N) -------------------------------------------------------------
+    for (int c = threadIdx.x; c <= N; c += K1_THREADS) {
+        ColRec cr = {0u, 0u, 0u, 0u};
+        if (c >= 1) {
+            const unsigned char *now = B + (size_t)(c - 1) * L;
+            const unsigned char *left = now - L;   // only dereferenced when c > 1
+            unsigned n[6] = {0, 0, 0, 0, 0, 0};
+            unsigned b01 = 0, b10 = 0;
+            for (int j = 0; j < L; ++j) {
+                unsigned ch = now[j];
+                n[classify(ch)]++;
+                unsigned v = (ch == '-');
+                unsigned t = (c > 1) ? (left[j] == '-') : 0u;   // mz_yama.c:128 (t==0 when col==1)
+                b01 += (!t) & v;
+                b10 += t & (!v);
+            }
+            unsigned dB = n[5], ndB = (unsigned)L - dB;
+            cr.w0 = pack4(b01, ndB, dB, b10);
+            cr.w1 = pack4(n[0], n[1], n[2], n[3]);
+            bool inner = (c < N);                               // mz_yama.c:211
+            cr.w2 = pack4(n[4], n[5], inner ? ndB : 0u, inner ? dB : 0u);
+            cr.w3 = (c > 1) ? cr.w0 : 0u;                       // mz_yama.c:173
+        }
+        cols[c] = cr;
+    }
+
+    // ---- rows of A (r = 0..M) ------------------------------------------------------------------
+    for (int r = threadIdx.x; r <= M; r += K1_THREADS) {
+        RowRec rr;
+        rr.avXC = rr.avYC = rr.avZC = rr.avXI = rr.avXD = rr.avYD = rr.avZD = 0u;
+        rr.eD = 0; rr.w01 = rr.w23 = rr.w45 = 0u;
+        rr.LB = LB[r]; rr.RB = RB[r];
+        rr.LBp = r > 0 ? LB[r - 1] : 0;
+        rr.RBp = r > 0 ? RB[r - 1] : 0;
+        rr.rowoff = 0u;
+        if (r >= 1) {
+            const unsigned char *now = A + (size_t)(r - 1) * K;
+            const unsigned char *up = now - K;    // only dereferenced when r > 1
+            int n[6] = {0, 0, 0, 0, 0, 0};
+            unsigned a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+            for (int i = 0; i < K; ++i) {
+                unsigned ch = now[i];
+                n[classify(ch)]++;
+                unsigned u = (ch == '-');
+                unsigned s = (r > 1) ? (up[i] == '-') : 0u;     // mz_yama.c:175,213
+                a00 += (!s) & (!u); a01 += (!s) & u; a10 += s & (!u); a11 += s & u;
+            }
+            unsigned dA = (unsigned)n[5], ndA = (unsigned)K - dA;
+            // gap-open counts as dot products with the column bytes (b01, ndB, dB, b10):
+            //   C.x: a00*b01 + a01*ndB + a10*dB + a11*b10   C.y: dA*ndB + a10*dB   C.z: ndA*dB + dA*b10
+            //   I.x: ndA*ndB + dA*b10                        (I.y = K*ndB, I.z = K*b10 need no row data)
+            //   D.x: ndA*ndB' + a10*dB'   D.y: a10*(ndB'+dB')   D.z: ndA*(ndB'+dB')   on bytes 2,3 of w2
+            if (r > 1) {                                        // mz_yama.c:180-184, :218-221 (row>1)
+                rr.avXC = pack4(a00, a01, a10, a11);
+                rr.avYC = pack4(0, dA, a10, 0);
+                rr.avXD = pack4(0, 0, ndA, a10);
+                rr.avYD = pack4(0, 0, a10, a10);
+            }
+            rr.avZC = pack4(0, 0, ndA, dA);
+            rr.avZD = pack4(0, 0, ndA, ndA);
+            if (r < M) rr.avXI = pack4(0, ndA, 0, dA);         // mz_yama.c:123 (row<M)
+            rr.eD = (int)ndA * L * GE;
+            int w[6];
+#pragma unroll
+            for (int l = 0; l < 6; ++l) {
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc += n[k] * c_sc.S6[k][l];
+                w[l] = acc;
+            }
+            rr.w01 = pack16(w[0], w[1]); rr.w23 = pack16(w[2], w[3]); rr.w45 = pack16(w[4], w[5]);
+        }
+        rows[r] = rr;
+    }
+    __syncthreads();
+
+    // ---- warp 0: traceback row offsets (rows padded to 4 B) and the wavefront schedule ----------
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned run = 0;
+        for (int base = 0; base <= M; base += 32) {
+            int r = base + lane;
+            unsigned wdt = 0;
+            if (r <= M) wdt = (unsigned)(((RB[r] - LB[r] + 1) + 3) & ~3);
+            unsigned inc = wdt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (r <= M) rows[r].rowoff = run + inc - wdt;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        // schedule: rows 32b+1..32b+32 run with column = step - (sched[b] + lane).  A lane may start
+        // its next row (32 rows further down) only two steps after finishing the current one, and
+        // lane 0 must stay behind lane 31 of the previous block.
+        int *sched = schedPool + pm.schedBase;
+        int off = 0;
+        int nblk = (M + 31) >> 5;
+        for (int b = 0; b < nblk; ++b) {
+            if (lane == 0) sched[b] = off;
+            int r = 32 * b + 1 + lane;
+            int need = 32;
+            if (r + 32 <= M) need = max(need, RB[r] - LB[r + 32] + 2);
+            need = __reduce_max_sync(0xffffffffu, need);
+            off += need;
+        }
+    }
+}
+
+// =================================================================================================
+// K2: banded three-state fill, one warp per pair.
+// =================================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, int a, int b, int c, unsigned d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// reference tie rule (mz_yama.c:138-154): x wins ties, then y only if strictly greater than z
+__device__ __forceinline__ int pick3(int x, int y, int z, int &val) {
+    bool fromC = (x >= y) && (x >= z);
+    bool fromD = (y > z);
+    int yz = fromD ? y : z;
+    int fyz = fromD ? FLAG_D : FLAG_I;
+    val = fromC ? x : yz;
+    return fromC ? FLAG_C : fyz;
+}
+
+// RING: ring entries, power of two, >= widest band row + 32.  WARPS: warps (= pairs in flight) per CTA.
+template <int RING, int WARPS>
+__device__ __forceinline__ void
+fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+               int *__restrict__ queue, const RowRec *__restrict__ rowPool,
+               const ColRec *__restrict__ colPool, const int *__restrict__ schedPool,
+               unsigned char *__restrict__ tbPool, PairOut *__restrict__ outs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [warp][ RING ring records | 32 lanes x 2 mailbox records ] , then one MININT record
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PER_WARP = (RING + 64) * 16;
+    const unsigned ringAddr = smem_u32(smem_raw) + warp * PER_WARP;
+    const unsigned boxAddr = ringAddr + RING * 16;
+    const unsigned minAddr = smem_u32(smem_raw) + WARPS * PER_WARP;
+    const int GO = c_sc.gap_open;
+    const int nGO = -GO;
+    const unsigned E_both = pack16(nGO, nGO);
+
+    if (threadIdx.x == 0) sts128(minAddr, MININT, MININT, MININT, E_both);   // stale dp[] entry, mz_yama.c:93-94
+    __syncthreads();
+
+    // lane l reads what lane l-1 wrote (lane 0 reads the ring), writes its own mailbox (lane 31: ring)
+    const unsigned rdBase = (lane == 0) ? ringAddr : boxAddr + (lane - 1) * 32;
+    const int rdMask = (lane == 0) ? (RING - 1) : 1;
+    const unsigned wrBase = (lane == 31) ? ringAddr : boxAddr + lane * 32;
+    const int wrMask = (lane == 31) ? (RING - 1) : 1;
+
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(queue, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= nPairs) break;
+        const int p = order[slot];
+        const PairMeta pm = metas[p];
+        const int K = pm.K, M = pm.M, N = pm.N;
+        const RowRec *rows = rowPool + pm.rowBase;
+        const ColRec *cols = colPool + pm.colBase;
+        const int *sched = schedPool + pm.schedBase;
+        unsigned char *tb = tbPool + pm.tbBase;
+        const int KGE = K * c_sc.gap_ext;
+
+        // ---- row 0 (mz_yama.c:83-94) into the ring + its traceback bytes ------------------------
+        {
+            const int RB0 = rows[0].RB;
+            int carry = 0;
+            for (int base = 0; base <= RB0; base += 32) {
+                int c = base + lane;
+                int nd = 0;
+                if (c >= 1 && c <= RB0) nd = (int)((cols[c].w0 >> 8) & 0xffu);
+                int inc = nd;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                if (c <= RB0) {
+                    int I0 = -(carry + inc) * KGE;
+                    unsigned a = ringAddr + ((c & (RING - 1)) << 4);
+                    if (c == 0) sts128(a, 0, 0, 0, 0u);                    // (0,0): nothing is ever charged
+                    else sts128(a, MININT, MININT, I0, pack16(0, nGO));    // only the I node exists in row 0
+                    tb[c] = (c == 0) ? 0 : (unsigned char)(FLAG_I << 4);
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        __syncwarp();
+
+        // ---- per-lane row state --------------------------------------------------------------------
+        int r = lane + 1 - 32;
+        int LBr = 0, RBr = -1, LBp = 0, RBp = 0, off = 0, eD = 0;
+        unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avYI = 0, avZI = 0, avXD = 0, avYD = 0, avZD = 0;
+        unsigned w01 = 0, w23 = 0, w45 = 0;
+        unsigned *tbRow = nullptr;
+        unsigned acc = 0;
+        bool done = false;
+        int Cl = MININT, Dl = MININT, Il = MININT, gCl = 0, gIl = 0;     // grid point (r, c-1)
+        int Cd = MININT, Dd = MININT, Id = MININT, gCd = 0, gId = 0;     // grid point (r-1, c-1)
+
+        for (int t = 0;; ++t) {
+            int c = t - off;
+            if (c > RBr) {
+                // ---- this lane finished its row: flush, publish, move 32 rows down -------------------
+                if (r >= 1) {
+                    int kLast = RBr - LBr;
+                    int rem = kLast & 3;
+                    if (rem != 3) tbRow[kLast >> 2] = acc >> (8 * (3 - rem));
+                    if (r == M) {
+                        outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il;
+                    }
+                }
+                r += 32;
+                if (r <= M) {
+                    const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
+                    uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+                    avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
+                    avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
+                    w01 = q2.x; w23 = q2.y; w45 = q2.z; LBr = (int)q2.w;
+                    RBr = (int)q3.x; LBp = (int)q3.y; RBp = (int)q3.z;
+                    tbRow = reinterpret_cast<unsigned *>(tb + q3.w);
+                    bool inner = r < M;                                     // mz_yama.c:123
+                    avYI = inner ? ((unsigned)K << 8) : 0u;                 // K * ndB
+                    avZI = inner ? ((unsigned)K << 24) : 0u;                // K * b10
+                    off = __ldg(sched + ((r - 1) >> 5)) + lane;
+                    c = t - off;
+                } else {
+                    done = true;
+                    r = -1000000;
+                    LBr = 0x7fffffff; RBr = 0x7fffffff;
+                }
+            }
+            __syncwarp();
+            if (__all_sync(0xffffffffu, done)) break;
+
+            const bool active = (c >= LBr);
+            // ---- grid point (r-1, c) ------------------------------------------------------------------
+            const unsigned ra = (c > RBp) ? minAddr : rdBase + ((unsigned)(c & rdMask) << 4);
+            const uint4 up = lds128(ra);
+            const int Cu = (int)up.x, Du = (int)up.y, Iu = (int)up.z;
+            const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
+
+            uint4 cw = make_uint4(0u, 0u, 0u, 0u);
+            if (active) cw = __ldg(reinterpret_cast<const uint4 *>(cols + c));
+
+            // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
+            int vI, fI;
+            {
+                int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
+                int y = Dl + dp4a_uu(cw.x, avYI, 0) * nGO;
+                int z = Il + dp4a_uu(cw.x, avZI, 0) * gIl;
+                fI = pick3(x, y, z, vI);
+                vI -= (int)((cw.x >> 8) & 0xffu) * KGE;
+            }
+            const bool hasI = c > LBr;
+            vI = hasI ? vI : MININT;
+            fI = hasI ? fI : 0;
+            const int gI = hasI ? nGO : 0;
+
+            // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
+            int vC, fC;
+            {
+                int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
+                int y = Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
+                int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
+                fC = pick3(x, y, z, vC);
+                vC = dp2a_lo_su(w01, cw.y, vC);
+                vC = dp2a_hi_su(w23, cw.y, vC);
+                vC = dp2a_lo_su(w45, cw.z, vC);
+            }
+            const bool hasC = c > LBp;
+            vC = hasC ? vC : MININT;
+            fC = hasC ? fC : 0;
+            const int gC = hasC ? nGO : 0;
+
+            // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
+            int vD, fD;
+            {
+                int x = Cu + dp4a_uu(cw.z, avXD, 0) * gCu;
+                int y = Du + dp4a_uu(cw.z, avYD, 0) * nGO;
+                int z = Iu + dp4a_uu(cw.z, avZD, 0) * gIu;
+                fD = pick3(x, y, z, vD);
+                vD -= eD;
+            }
+
+            if (active) {
+                sts128(wrBase + ((unsigned)(c & wrMask) << 4), vC, vD, vI, pack16(gC, gI));
+                unsigned byte = (unsigned)(fC | (fD << 2) | (fI << 4));     // mz_yama.c:253
+                acc = __funnelshift_r(acc, byte, 8);
+                int k = c - LBr;
+                if ((k & 3) == 3) tbRow[k >> 2] = acc;
+            }
+            Cl = vC; Dl = vD; Il = vI; gCl = gC; gIl = gI;
+            Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// K3: traceback (mz_yama.c:257-291), one thread per pair.
+// =================================================================================================
+__global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, int nPairs,
+                                    const RowRec *__restrict__ rowPool,
+                                    const unsigned char *__restrict__ tbPool,
+                                    unsigned char *__restrict__ scriptPool, PairOut *__restrict__ outs) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPairs) return;
+    const PairMeta pm = metas[p];
+    const RowRec *rows = rowPool + pm.rowBase;
+    const unsigned char *tb = tbPool + pm.tbBase;
+    unsigned char *script = scriptPool + pm.scriptBase;
+    PairOut o = outs[p];
+    int node;
+    if (o.C >= o.D && o.C >= o.I) node = FLAG_C;         // mz_yama.c:262-267
+    else if (o.D >= o.I) node = FLAG_D;
+    else node = FLAG_I;
+    int r = pm.M, c = pm.N, n = 0, status = 0;
+    const int limit = pm.M + pm.N;
+    while (r > 0 || c > 0) {
+        if (r < 0 || c < 0 || n >= limit) { status = -5; break; }           // mz_yama.c:274-276
+        int lb = rows[r].LB, rb = rows[r].RB;
+        if (c < lb || c > rb) { status = -5; break; }                       // left the band (reference: undefined)
+        unsigned st = tb[rows[r].rowoff + (unsigned)(c - lb)];
+        script[n++] = (unsigned char)node;
+        if (node == FLAG_I) { c--; node = st >> 4; }
+        else if (node == FLAG_D) { r--; node = (st >> 2) & 3; }
+        else if (node == FLAG_C) { r--; c--; node = st & 3; }
+        else { status = -5; break; }                                        // mz_yama.c:289-290
+    }
+    o.m_new = n;
+    o.status = status;
+    outs[p] = o;
+}
+
+}  // namespace yb
