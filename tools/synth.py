@@ -114,8 +114,22 @@ ALPHABETS = {
 }
 
 
+def _valid_band(LB, RB, M, N):
+    need = min(N, 10)
+    return (LB[0] == 0 and RB[M] == N and np.all(RB - LB >= need) and np.all(np.diff(LB) >= 0)
+            and np.all(np.diff(RB) >= 0))
+
+
 def random_band(rng, M, N, kind):
     """A band that passes mz_yama.c:58-71: LB[0]=0, RB[M]=N, monotone, width >= min(N,10)."""
+    for _ in range(50):
+        LB, RB = _random_band(rng, M, N, kind)
+        if _valid_band(LB.astype(np.int64), RB.astype(np.int64), M, N):
+            return LB, RB
+    return np.zeros(M + 1, np.int32), np.full(M + 1, N, np.int32)
+
+
+def _random_band(rng, M, N, kind):
     need = min(N, 10)
     if kind == "full":
         return np.zeros(M + 1, np.int32), np.full(M + 1, N, np.int32)
