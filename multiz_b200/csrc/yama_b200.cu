@@ -54,7 +54,7 @@ struct PinBuf {
 };
 
 constexpr int NBINS = 4;
-const int kRingOf[NBINS] = {128, 512, 2048, 8192};
+const int kRingOf[NBINS] = {128, 512, 2048, 4096};
 
 struct JobInfo {           // host-side facts about one pair
     int64_t cells = 0;     // tback_size of the reference
@@ -66,7 +66,7 @@ struct JobInfo {           // host-side facts about one pair
 struct Wave {              // everything needed to (re)launch the kernels of one wave
     int64_t first = 0, count = 0;          // job range [first, first+count)
     size_t blobBytes = 0, metaBytes = 0;
-    size_t rowRecs = 0, colRecs = 0, schedInts = 0, tbBytes = 0, scriptBytes = 0;
+    size_t rowRecs = 0, colRecs = 0, tbBytes = 0, scriptBytes = 0;
     std::vector<int> order;                // pair indices (within wave) grouped by bin, big first
     int binStart[NBINS + 1] = {0, 0, 0, 0, 0};
     std::vector<uint64_t> scriptOff;       // per pair, offset in the wave's script pool
@@ -77,7 +77,7 @@ struct Device {
     int sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    DevBuf dIn, dRow, dCol, dSched, dTb, dScript, dOut, dOrder, dQueue;
+    DevBuf dIn, dRow, dCol, dTb, dScript, dOut, dOrder, dQueue;
     PinBuf hIn, hScript, hOut;
     int fillBlocks[NBINS] = {0, 0, 0, 0};
     // accumulated stats of the current call
@@ -153,7 +153,8 @@ int bin_of(int wmax) {
 constexpr int warps_of(int bin) { return bin <= 1 ? 8 : (bin == 2 ? 4 : 1); }
 
 size_t fill_smem(int bin) {
-    return (size_t)warps_of(bin) * (kRingOf[bin] + 64) * 16 + 16;
+    // rings (RING*16-aligned, hence the slack) + 1 KB of mailboxes per warp
+    return (size_t)warps_of(bin) * ((size_t)kRingOf[bin] * 16 + 1024) + (size_t)kRingOf[bin] * 16;
 }
 
 }  // namespace
@@ -164,22 +165,22 @@ template <int RING, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
-                 const ColRec *__restrict__ colPool, const int *__restrict__ schedPool,
-                 unsigned char *__restrict__ tbPool, PairOut *__restrict__ outs) {
-    fill_body<RING, WARPS>(metas, order, nPairs, queue, rowPool, colPool, schedPool, tbPool, outs);
+                 const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
+                 PairOut *__restrict__ outs) {
+    fill_body<RING, WARPS>(metas, order, nPairs, queue, rowPool, colPool, tbPool, outs);
 }
 }  // namespace yb
 
 namespace {
 
-typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *, const ColRec *, const int *,
+typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *, const ColRec *,
                        unsigned char *, PairOut *);
 FillFn fill_fn(int bin) {
     switch (bin) {
         case 0: return yb_fill_kernel_w<128, 8>;
         case 1: return yb_fill_kernel_w<512, 8>;
         case 2: return yb_fill_kernel_w<2048, 4>;
-        default: return yb_fill_kernel_w<8192, 1>;
+        default: return yb_fill_kernel_w<4096, 1>;
     }
 }
 
@@ -219,7 +220,7 @@ int64_t check_band(int M, int N, const int *LB, const int *RB, char *msg, int ms
             return YB_ERR_BAND;
         }
         cells += j + 1;
-        tb += (j + 1 + 3) & ~3;
+        tb += (j + 1 + 6) & ~3;          // row padded to 4 B plus up to 3 B of phase (see K1)
         if (j + 1 > wm) wm = j + 1;
         if (r > 0 && LB[r] < LB[r - 1]) { if (msg) snprintf(msg, msglen, "LB not monotonic"); return YB_ERR_BAND; }
         if (r > 0 && RB[r] < RB[r - 1]) { if (msg) snprintf(msg, msglen, "RB not monotonic"); return YB_ERR_BAND; }
@@ -262,13 +263,12 @@ int analyse_jobs(yb_ctx *ctx, int64_t n, const yb_job *jobs, std::vector<JobInfo
     return rc;
 }
 
-struct Need { size_t blob, rows, cols, sched, tb, script; };
+struct Need { size_t blob, rows, cols, tb, script; };
 inline Need need_of(const yb_job &j, const JobInfo &ji) {
     Need n;
     n.blob = align_up((size_t)j.K * j.M, 16) + align_up((size_t)j.L * j.N, 16) + 2 * align_up((size_t)(j.M + 1) * 4, 16);
     n.rows = (size_t)j.M + 1;
     n.cols = (size_t)j.N + 1;
-    n.sched = (size_t)((j.M + 31) >> 5);
     n.tb = align_up((size_t)ji.tbBytes, 16);
     n.script = align_up((size_t)j.M + j.N, 4);
     return n;
@@ -280,21 +280,20 @@ int wave_upload(yb_ctx *ctx, Device &d, const yb_job *jobs, const std::vector<Jo
     double t0 = now_ms();
     w.first = first; w.count = count;
     w.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
-    size_t blob = w.metaBytes, rows = 0, cols = 0, sched = 0, tb = 0, script = 0;
+    size_t blob = w.metaBytes, rows = 0, cols = 0, tb = 0, script = 0;
     int nvalid = 0;
     for (int64_t i = 0; i < count; ++i) {
         const JobInfo &ji = info[(size_t)(first + i)];
         if (ji.status != YB_OK) continue;
         Need n = need_of(jobs[first + i], ji);
-        blob += n.blob; rows += n.rows; cols += n.cols; sched += n.sched; tb += n.tb; script += n.script;
+        blob += n.blob; rows += n.rows; cols += n.cols; tb += n.tb; script += n.script;
         ++nvalid;
     }
-    w.blobBytes = blob; w.rowRecs = rows; w.colRecs = cols; w.schedInts = sched; w.tbBytes = tb; w.scriptBytes = script;
+    w.blobBytes = blob; w.rowRecs = rows; w.colRecs = cols; w.tbBytes = tb; w.scriptBytes = script;
     CUDA_TRY(d, d.hIn.reserve(blob));
     CUDA_TRY(d, d.dIn.reserve(blob));
     CUDA_TRY(d, d.dRow.reserve(rows * sizeof(RowRec) + 64));
     CUDA_TRY(d, d.dCol.reserve(cols * sizeof(ColRec) + 64));
-    CUDA_TRY(d, d.dSched.reserve(sched * 4 + 64));
     CUDA_TRY(d, d.dTb.reserve(tb + 64));
     CUDA_TRY(d, d.dScript.reserve(script + 64));
     CUDA_TRY(d, d.dOut.reserve((size_t)count * sizeof(PairOut) + 64));
@@ -306,7 +305,7 @@ int wave_upload(yb_ctx *ctx, Device &d, const yb_job *jobs, const std::vector<Jo
     unsigned char *h = static_cast<unsigned char *>(d.hIn.p);
     PairMeta *metas = reinterpret_cast<PairMeta *>(h);
     size_t off = w.metaBytes;
-    size_t rowBase = 0, colBase = 0, schedBase = 0, tbBase = 0, scriptBase = 0;
+    size_t rowBase = 0, colBase = 0, tbBase = 0, scriptBase = 0;
     w.scriptOff.assign((size_t)count, 0);
     std::vector<std::pair<int64_t, int>> binned[NBINS];
     for (int64_t i = 0; i < count; ++i) {
@@ -323,7 +322,6 @@ int wave_upload(yb_ctx *ctx, Device &d, const yb_job *jobs, const std::vector<Jo
         Need n = need_of(j, ji);
         pm.rowBase = rowBase; rowBase += n.rows;
         pm.colBase = colBase; colBase += n.cols;
-        pm.schedBase = schedBase; schedBase += n.sched;
         pm.tbBase = tbBase; tbBase += n.tb;
         pm.scriptBase = scriptBase; w.scriptOff[(size_t)i] = scriptBase; scriptBase += n.script;
         pm.ringNeed = ji.wmax + 32;
@@ -363,7 +361,6 @@ int wave_compute(Device &d, const Wave &w) {
     const unsigned char *blob = static_cast<const unsigned char *>(d.dIn.p);
     RowRec *rows = static_cast<RowRec *>(d.dRow.p);
     ColRec *cols = static_cast<ColRec *>(d.dCol.p);
-    int *sched = static_cast<int *>(d.dSched.p);
     unsigned char *tb = static_cast<unsigned char *>(d.dTb.p);
     unsigned char *script = static_cast<unsigned char *>(d.dScript.p);
     PairOut *outs = static_cast<PairOut *>(d.dOut.p);
@@ -373,7 +370,7 @@ int wave_compute(Device &d, const Wave &w) {
     CUDA_TRY(d, cudaEventRecord(d.ev[2], d.stream));
     CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)w.count * sizeof(PairOut), d.stream));
     CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, d.stream));
-    yb_profile_kernel<<<(unsigned)w.count, K1_THREADS, 0, d.stream>>>(metas, blob, rows, cols, sched);
+    yb_profile_kernel<<<(unsigned)w.count, K1_THREADS, 0, d.stream>>>(metas, blob, rows, cols, outs);
     d.launches++;
     CUDA_TRY(d, cudaEventRecord(d.ev[3], d.stream));
     for (int b = 0; b < NBINS; ++b) {
@@ -381,7 +378,7 @@ int wave_compute(Device &d, const Wave &w) {
         if (n <= 0) continue;
         int wpc = warps_of(b);
         int blocks = std::min((n + wpc - 1) / wpc, d.fillBlocks[b]);
-        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), d.stream>>>(metas, order + w.binStart[b], n, queue + b, rows, cols, sched, tb, outs);
+        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), d.stream>>>(metas, order + w.binStart[b], n, queue + b, rows, cols, tb, outs);
         d.launches++;
     }
     CUDA_TRY(d, cudaEventRecord(d.ev[4], d.stream));
@@ -493,7 +490,7 @@ int run_range(yb_ctx *ctx, Device &d, const yb_job *jobs, const std::vector<JobI
             if (ji.status == YB_OK) {
                 Need n = need_of(jobs[j], ji);
                 b += n.blob;
-                dv += n.blob + n.rows * sizeof(RowRec) + n.cols * sizeof(ColRec) + n.sched * 4 + n.tb + n.script;
+                dv += n.blob + n.rows * sizeof(RowRec) + n.cols * sizeof(ColRec) + n.tb + n.script;
             }
             if (j > i && (blob + b > ctx->stageBytes || dev + dv > ctx->waveBytes || j - i >= (1 << 24))) break;
             blob += b; dev += dv; ++j;
@@ -572,7 +569,7 @@ void yb_destroy(yb_ctx *ctx) {
     if (!ctx) return;
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.id);
-        for (DevBuf *b : {&d.dIn, &d.dRow, &d.dCol, &d.dSched, &d.dTb, &d.dScript, &d.dOut, &d.dOrder, &d.dQueue}) b->release();
+        for (DevBuf *b : {&d.dIn, &d.dRow, &d.dCol, &d.dTb, &d.dScript, &d.dOut, &d.dOrder, &d.dQueue}) b->release();
         for (PinBuf *b : {&d.hIn, &d.hScript, &d.hOut}) b->release();
         for (auto &e : d.ev) if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);

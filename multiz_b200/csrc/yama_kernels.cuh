@@ -50,19 +50,24 @@ struct PairMeta {
     unsigned long long colBase;        // index of column 0's ColRec in the ColRec pool (N+1 records)
     unsigned long long tbBase;         // byte offset of this pair's traceback matrix
     unsigned long long scriptBase;     // byte offset of this pair's script (M+N bytes)
-    unsigned long long schedBase;      // index into the schedule pool (ceil(M/32) ints)
     int ringNeed;                      // widest band row + 32 (host computed)
     int pad;
 };
 
-// Row record, 64 B.  v[] are byte-count vectors matched against the column words (see ColRec).
+// Row record, 80 B (5 x 16 B).  av* are byte-count vectors matched against the column words (see
+// ColRec) with dp4a; everything a lane needs to run one row of the band.
 struct __align__(16) RowRec {
-    unsigned avXC, avYC, avZC, avXI;   // C-node x,y,z and I-node x coefficient bytes
-    unsigned avXD, avYD, avZD;         // D-node x,y,z coefficient bytes (bytes 2,3 only)
-    int eD;                            // ndA*L*gap_ext  (mz_yama.c:239-242)
-    unsigned w01, w23, w45;            // S6^T * classcount(A row) as int16 pairs (sum-of-pairs weights)
-    int LB, RB, LBp, RBp;              // band of this row and of the row above
-    unsigned rowoff;                   // byte offset of this row inside the pair's traceback matrix
+    unsigned avXC, avYC, avZC, avXI;   // q0: C-node x,y,z and I-node x coefficient bytes
+    unsigned avXD, avYD, avZD;         // q1: D-node x,y,z coefficient bytes (bytes 2,3 only)
+    int eD;                            //     ndA*L*gap_ext  (mz_yama.c:239-242)
+    unsigned w01, w23, w45;            // q2: S6^T * classcount(A row) as int16 pairs (sum-of-pairs weights)
+    unsigned avYI;                     //     K<<8  (K*ndB)  or 0 on the last row (mz_yama.c:123)
+    unsigned avZI;                     // q3: K<<24 (K*b10)  or 0 on the last row
+    int LB16, RB16, LBp16;             //     16*LB[r], 16*RB[r], 16*LB[r-1]
+    int off;                           // q4: wavefront schedule: this row computes column (step - off)
+    unsigned tbOff;                    //     byte offset of cell (r, LB[r]) inside the pair's traceback matrix
+    int RBn;                           //     RB[r+1] (RB[r] on the last row): how far the row below reads us
+    unsigned Efirst;                   //     guard multipliers published by the first cell of the row
 };
 
 // Column record, 16 B.
@@ -72,7 +77,7 @@ struct __align__(16) RowRec {
 //  w3 = w0 zeroed for c==1            (mz_yama.c:173, no gap-open at the start)
 struct __align__(16) ColRec { unsigned w0, w1, w2, w3; };
 
-struct PairOut { int m_new, C, D, I, status, pad; };
+struct PairOut { int m_new, C, D, I, status, nSteps; };
 
 __device__ __forceinline__ int classify(unsigned ch) {
     unsigned u = ch | 0x20u;
@@ -113,9 +118,10 @@ constexpr int K1_THREADS = 128;
 
 __global__ void __launch_bounds__(K1_THREADS)
 yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__restrict__ blob,
-                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int *__restrict__ schedPool) {
+                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, PairOut *__restrict__ outs) {
     const PairMeta pm = metas[blockIdx.x];
     const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
+    if (M < 1) return;                                  // invalid pair (rejected on the host)
     const unsigned char *A = blob + pm.offA;
     const unsigned char *B = blob + pm.offB;
     const int *LB = reinterpret_cast<const int *>(blob + pm.offLB);
@@ -123,6 +129,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     RowRec *rows = rowPool + pm.rowBase;
     ColRec *cols = colPool + pm.colBase;
     const int GE = c_sc.gap_ext;
+    const int nGO = -c_sc.gap_open;
 
     // ---- columns of B (c = 0..N) -------------------------------------------------------------
     for (int c = threadIdx.x; c <= N; c += K1_THREADS) {
@@ -153,12 +160,14 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     // ---- rows of A (r = 0..M) ------------------------------------------------------------------
     for (int r = threadIdx.x; r <= M; r += K1_THREADS) {
         RowRec rr;
-        rr.avXC = rr.avYC = rr.avZC = rr.avXI = rr.avXD = rr.avYD = rr.avZD = 0u;
+        rr.avXC = rr.avYC = rr.avZC = rr.avXI = rr.avXD = rr.avYD = rr.avZD = rr.avYI = rr.avZI = 0u;
         rr.eD = 0; rr.w01 = rr.w23 = rr.w45 = 0u;
-        rr.LB = LB[r]; rr.RB = RB[r];
-        rr.LBp = r > 0 ? LB[r - 1] : 0;
-        rr.RBp = r > 0 ? RB[r - 1] : 0;
-        rr.rowoff = 0u;
+        const int lb = LB[r], lbp = r > 0 ? LB[r - 1] : 0;
+        rr.LB16 = lb * 16; rr.RB16 = RB[r] * 16; rr.LBp16 = lbp * 16;
+        rr.off = 0; rr.tbOff = 0u;
+        rr.RBn = r < M ? RB[r + 1] : RB[r];
+        // first cell of the row: its I node never exists, its C node only if the band moved right
+        rr.Efirst = pack16((r > 0 && lb > lbp) ? nGO : 0, 0);
         if (r >= 1) {
             const unsigned char *now = A + (size_t)(r - 1) * K;
             const unsigned char *up = now - K;    // only dereferenced when r > 1
@@ -174,7 +183,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
             unsigned dA = (unsigned)n[5], ndA = (unsigned)K - dA;
             // gap-open counts as dot products with the column bytes (b01, ndB, dB, b10):
             //   C.x: a00*b01 + a01*ndB + a10*dB + a11*b10   C.y: dA*ndB + a10*dB   C.z: ndA*dB + dA*b10
-            //   I.x: ndA*ndB + dA*b10                        (I.y = K*ndB, I.z = K*b10 need no row data)
+            //   I.x: ndA*ndB + dA*b10    I.y: K*ndB    I.z: K*b10
             //   D.x: ndA*ndB' + a10*dB'   D.y: a10*(ndB'+dB')   D.z: ndA*(ndB'+dB')   on bytes 2,3 of w2
             if (r > 1) {                                        // mz_yama.c:180-184, :218-221 (row>1)
                 rr.avXC = pack4(a00, a01, a10, a11);
@@ -184,7 +193,11 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
             }
             rr.avZC = pack4(0, 0, ndA, dA);
             rr.avZD = pack4(0, 0, ndA, ndA);
-            if (r < M) rr.avXI = pack4(0, ndA, 0, dA);         // mz_yama.c:123 (row<M)
+            if (r < M) {                                        // mz_yama.c:123 (row<M)
+                rr.avXI = pack4(0, ndA, 0, dA);
+                rr.avYI = (unsigned)K << 8;
+                rr.avZI = (unsigned)K << 24;
+            }
             rr.eD = (int)ndA * L * GE;
             int w[6];
 #pragma unroll
@@ -200,37 +213,45 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     }
     __syncthreads();
 
-    // ---- warp 0: traceback row offsets (rows padded to 4 B) and the wavefront schedule ----------
+    // ---- warp 0: wavefront schedule, then traceback row offsets -----------------------------------
+    // Rows 32b+1..32b+32 (lanes 0..31) run with column = step - (OFF_b + lane).  OFF grows per block by
+    // at least 32 (lane 0 stays behind lane 31 of the previous block) and by enough that a lane starts
+    // its next row only after the row below its current one has stopped reading it.
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        unsigned run = 0;
-        for (int base = 0; base <= M; base += 32) {
-            int r = base + lane;
-            unsigned wdt = 0;
-            if (r <= M) wdt = (unsigned)(((RB[r] - LB[r] + 1) + 3) & ~3);
+        int off = 0;
+        const int nblk = (M + 31) >> 5;
+        unsigned run = (unsigned)((RB[0] + 1 + 3) & ~3);       // row 0 occupies bytes [0, RB[0]]
+        int lastStart = 0;
+        for (int b = 0; b < nblk; ++b) {
+            int r = 32 * b + 1 + lane;
+            int need = 32;
+            if (r + 32 <= M) need = max(need, RB[r + 1] - LB[r + 32] + 3);
+            need = __reduce_max_sync(0xffffffffu, need);
+            // traceback bytes: cell (r,c) lives at tbOff + (c-LB[r]); tbOff = 4-aligned base + phase so
+            // that the byte position is congruent to the step number mod 4 (uniform 4-step word stores)
+            unsigned wdt = 0, phase = 0;
+            int myoff = off + lane;
+            if (r <= M) {
+                phase = (unsigned)(LB[r] + myoff) & 3u;
+                wdt = (phase + (unsigned)(RB[r] - LB[r] + 1) + 3u) & ~3u;
+            }
             unsigned inc = wdt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += o;
             }
-            if (r <= M) rows[r].rowoff = run + inc - wdt;
+            if (r <= M) {
+                rows[r].off = myoff;
+                rows[r].tbOff = run + inc - wdt + phase;
+                if (r == M) lastStart = myoff + RB[r];
+            }
             run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        // schedule: rows 32b+1..32b+32 run with column = step - (sched[b] + lane).  A lane may start
-        // its next row (32 rows further down) only two steps after finishing the current one, and
-        // lane 0 must stay behind lane 31 of the previous block.
-        int *sched = schedPool + pm.schedBase;
-        int off = 0;
-        int nblk = (M + 31) >> 5;
-        for (int b = 0; b < nblk; ++b) {
-            if (lane == 0) sched[b] = off;
-            int r = 32 * b + 1 + lane;
-            int need = 32;
-            if (r + 32 <= M) need = max(need, RB[r] - LB[r + 32] + 2);
-            need = __reduce_max_sync(0xffffffffu, need);
             off += need;
         }
+        lastStart = __reduce_max_sync(0xffffffffu, lastStart);
+        if (lane == 0) outs[blockIdx.x].nSteps = lastStart + 2;   // last cell at step lastStart, +1 to flush
     }
 }
 
@@ -242,49 +263,64 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) {
 }
 __device__ __forceinline__ uint4 lds128(unsigned addr) {
     uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts128(unsigned addr, int a, int b, int c, unsigned d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// (a & b) ^ c in one LOP3: ring / mailbox slot addressing
+__device__ __forceinline__ unsigned and_xor(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned launder(unsigned x) {
+    asm volatile("" : "+r"(x));
+    return x;
+}
 
-// reference tie rule (mz_yama.c:138-154): x wins ties, then y only if strictly greater than z
-__device__ __forceinline__ int pick3(int x, int y, int z, int &val) {
-    bool fromC = (x >= y) && (x >= z);
-    bool fromD = (y > z);
-    int yz = fromD ? y : z;
-    int fyz = fromD ? FLAG_D : FLAG_I;
-    val = fromC ? x : yz;
-    return fromC ? FLAG_C : fyz;
+// Pre-shifted traceback flags (mz_yama.c:24-26,253): byte = fC | fD<<2 | fI<<4.
+// reference tie rule (mz_yama.c:138-154): x (from C) wins ties, then y (from D) only if strictly
+// greater than z (from I).  SH = bit position of this node's 2-bit field.
+template <int SH>
+__device__ __forceinline__ int pick3(int x, int y, int z, unsigned &flag) {
+    const int m = __vimax3_s32(x, y, z);
+    const bool fromC = (x == m);
+    const bool fromD = (y > z);
+    const unsigned fyz = fromD ? (unsigned)(FLAG_D << SH) : (unsigned)(FLAG_I << SH);
+    flag = fromC ? 0u : fyz;
+    return m;
 }
 
 // RING: ring entries, power of two, >= widest band row + 32.  WARPS: warps (= pairs in flight) per CTA.
 template <int RING, int WARPS>
 __device__ __forceinline__ void
 fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
-               int *__restrict__ queue, const RowRec *__restrict__ rowPool,
-               const ColRec *__restrict__ colPool, const int *__restrict__ schedPool,
-               unsigned char *__restrict__ tbPool, PairOut *__restrict__ outs) {
+          int *__restrict__ queue, const RowRec *__restrict__ rowPool,
+          const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
+          PairOut *__restrict__ outs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [warp][ RING ring records | 32 lanes x 2 mailbox records ] , then one MININT record
+    // layout per warp: [ RING ring records | 32 lanes x 2 mailbox records ]; ring is RING*16-aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int PER_WARP = (RING + 64) * 16;
-    const unsigned ringAddr = smem_u32(smem_raw) + warp * PER_WARP;
-    const unsigned boxAddr = ringAddr + RING * 16;
-    const unsigned minAddr = smem_u32(smem_raw) + WARPS * PER_WARP;
+    constexpr unsigned PER_WARP = (RING + 64) * 16;
+    // dynamic smem base is at least 16-aligned; rings need RING*16 alignment for the (a&b)^c addressing
+    const unsigned smem0 = (smem_u32(smem_raw) + RING * 16 - 1) & ~(unsigned)(RING * 16 - 1);
+    const unsigned ringAddr = smem0 + warp * RING * 16;
+    const unsigned boxAddr = smem0 + WARPS * RING * 16 + warp * 1024;
+    (void)PER_WARP;
     const int GO = c_sc.gap_open;
     const int nGO = -GO;
     const unsigned E_both = pack16(nGO, nGO);
 
-    if (threadIdx.x == 0) sts128(minAddr, MININT, MININT, MININT, E_both);   // stale dp[] entry, mz_yama.c:93-94
-    __syncthreads();
-
-    // lane l reads what lane l-1 wrote (lane 0 reads the ring), writes its own mailbox (lane 31: ring)
-    const unsigned rdBase = (lane == 0) ? ringAddr : boxAddr + (lane - 1) * 32;
-    const int rdMask = (lane == 0) ? (RING - 1) : 1;
-    const unsigned wrBase = (lane == 31) ? ringAddr : boxAddr + lane * 32;
-    const int wrMask = (lane == 31) ? (RING - 1) : 1;
+    // Mailbox of lane l: 32 B at boxAddr + 32*l, two 16-B slots; slot of column c is (c&1) ^ ((l>>2)&1)
+    // (the swizzle keeps 128-bit accesses of a quarter-warp on distinct banks).  Lane l reads what lane
+    // l-1 wrote (lane 0 reads the ring), writes its own mailbox (lane 31 writes the ring).
+    auto boxOf = [&](int l) { return boxAddr + 32u * l + (((unsigned)l >> 2) & 1u) * 16u; };
+    const unsigned rdBase = launder((lane == 0) ? ringAddr : boxOf(lane - 1));
+    const unsigned rdMask = (lane == 0) ? (unsigned)(RING * 16 - 16) : 16u;
+    const unsigned wrBase = launder((lane == 31) ? ringAddr : boxOf(lane));
+    const unsigned wrMask = (lane == 31) ? (unsigned)(RING * 16 - 16) : 16u;
 
     for (;;) {
         int slot = 0;
@@ -293,145 +329,136 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         if (slot >= nPairs) break;
         const int p = order[slot];
         const PairMeta pm = metas[p];
-        const int K = pm.K, M = pm.M, N = pm.N;
+        const int M = pm.M;
         const RowRec *rows = rowPool + pm.rowBase;
         const ColRec *cols = colPool + pm.colBase;
-        const int *sched = schedPool + pm.schedBase;
         unsigned char *tb = tbPool + pm.tbBase;
-        const int KGE = K * c_sc.gap_ext;
+        const int KGE = pm.K * c_sc.gap_ext;
+        const int nSteps = outs[p].nSteps;
 
         // ---- row 0 (mz_yama.c:83-94) into the ring + its traceback bytes ------------------------
         {
-            const int RB0 = rows[0].RB;
+            const int RB0 = rows[0].RB16 >> 4;
+            const int RB1 = rows[0].RBn;
             int carry = 0;
-            for (int base = 0; base <= RB0; base += 32) {
+            for (int base = 0; base <= RB1; base += 32) {
                 int c = base + lane;
                 int nd = 0;
-                if (c >= 1 && c <= RB0) nd = (int)((cols[c].w0 >> 8) & 0xffu);
+                if (c >= 1 && c <= RB0) nd = (int)((__ldg(&cols[c].w0) >> 8) & 0xffu);
                 int inc = nd;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     int o = __shfl_up_sync(0xffffffffu, inc, d);
                     if (lane >= d) inc += o;
                 }
+                unsigned a = and_xor((unsigned)c << 4, (unsigned)(RING * 16 - 16), ringAddr);
                 if (c <= RB0) {
                     int I0 = -(carry + inc) * KGE;
-                    unsigned a = ringAddr + ((c & (RING - 1)) << 4);
                     if (c == 0) sts128(a, 0, 0, 0, 0u);                    // (0,0): nothing is ever charged
                     else sts128(a, MININT, MININT, I0, pack16(0, nGO));    // only the I node exists in row 0
                     tb[c] = (c == 0) ? 0 : (unsigned char)(FLAG_I << 4);
+                } else if (c <= RB1) {
+                    sts128(a, MININT, MININT, MININT, E_both);             // stale dp[] entry, mz_yama.c:93-94
                 }
                 carry += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
-        __syncwarp();
 
         // ---- per-lane row state --------------------------------------------------------------------
-        int r = lane + 1 - 32;
-        int LBr = 0, RBr = -1, LBp = 0, RBp = 0, off = 0, eD = 0;
+        int r = lane + 1;
+        const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
         unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avYI = 0, avZI = 0, avXD = 0, avYD = 0, avZD = 0;
-        unsigned w01 = 0, w23 = 0, w45 = 0;
-        unsigned *tbRow = nullptr;
+        unsigned w01 = 0, w23 = 0, w45 = 0, Efirst = 0;
+        int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBp16 = 0, RBn = 0, c16 = 0;
+        unsigned *tbw = nullptr;
+        auto load_row = [&](int t) {
+            uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3), q4 = __ldg(rp + 4);
+            avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
+            avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
+            w01 = q2.x; w23 = q2.y; w45 = q2.z; avYI = q2.w;
+            avZI = q3.x; LB16 = (int)q3.y; RB16 = (int)q3.z; LBp16 = (int)q3.w;
+            c16 = (t - (int)q4.x) * 16;
+            tbw = reinterpret_cast<unsigned *>(tb + (q4.y & ~3u));
+            RBn = (int)q4.z; Efirst = q4.w;
+        };
+        if (r <= M) load_row(0);
         unsigned acc = 0;
-        bool done = false;
         int Cl = MININT, Dl = MININT, Il = MININT, gCl = 0, gIl = 0;     // grid point (r, c-1)
         int Cd = MININT, Dd = MININT, Id = MININT, gCd = 0, gId = 0;     // grid point (r-1, c-1)
+        __syncwarp();
 
-        for (int t = 0;; ++t) {
-            int c = t - off;
-            if (c > RBr) {
-                // ---- this lane finished its row: flush, publish, move 32 rows down -------------------
-                if (r >= 1) {
-                    int kLast = RBr - LBr;
-                    int rem = kLast & 3;
-                    if (rem != 3) tbRow[kLast >> 2] = acc >> (8 * (3 - rem));
-                    if (r == M) {
-                        outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il;
-                    }
+        for (int t4 = 0; t4 < nSteps; t4 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // ---- grid point (r-1, c): read before anybody may overwrite it ------------------------
+                const uint4 up = lds128(and_xor((unsigned)c16, rdMask, rdBase));
+                if (c16 > RB16) {
+                    // ---- this lane finished its row -----------------------------------------------------
+                    // (a) the row below keeps reading us up to its own right bound: stale dp[] entries
+#pragma unroll 1
+                    for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
+                        sts128(and_xor((unsigned)cc << 4, wrMask, wrBase), MININT, MININT, MININT, E_both);
+                    // (b) flush the partial traceback word (u bytes of it are valid)
+                    if (u != 0) *tbw = acc >> (8 * (4 - u));
+                    // (c) final scores
+                    if (r == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
+                    // (d) move 32 rows down
+                    r += 32;
+                    rp += 32 * (sizeof(RowRec) / 16);
+                    if (r <= M) load_row(t4 + u);
+                    else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; RBn = 0; }
                 }
-                r += 32;
-                if (r <= M) {
-                    const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
-                    uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
-                    avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
-                    avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
-                    w01 = q2.x; w23 = q2.y; w45 = q2.z; LBr = (int)q2.w;
-                    RBr = (int)q3.x; LBp = (int)q3.y; RBp = (int)q3.z;
-                    tbRow = reinterpret_cast<unsigned *>(tb + q3.w);
-                    bool inner = r < M;                                     // mz_yama.c:123
-                    avYI = inner ? ((unsigned)K << 8) : 0u;                 // K * ndB
-                    avZI = inner ? ((unsigned)K << 24) : 0u;                // K * b10
-                    off = __ldg(sched + ((r - 1) >> 5)) + lane;
-                    c = t - off;
-                } else {
-                    done = true;
-                    r = -1000000;
-                    LBr = 0x7fffffff; RBr = 0x7fffffff;
+                const int Cu = (int)up.x, Du = (int)up.y, Iu = (int)up.z;
+                const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
+                const bool active = (c16 >= LB16);
+
+                uint4 cw = make_uint4(0u, 0u, 0u, 0u);
+                if (active) cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) + c16));
+
+                // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
+                unsigned fI, fC, fD;
+                int vI, vC, vD;
+                {
+                    int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
+                    int y = Dl + dp4a_uu(cw.x, avYI, 0) * nGO;
+                    int z = Il + dp4a_uu(cw.x, avZI, 0) * gIl;
+                    vI = pick3<4>(x, y, z, fI);
+                    vI -= (int)__byte_perm(cw.x, 0, 0x4441) * KGE;
                 }
+                const bool hasI = c16 > LB16;
+                vI = hasI ? vI : MININT;
+                // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
+                {
+                    int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
+                    int y = Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
+                    int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
+                    vC = pick3<0>(x, y, z, fC);
+                    vC = dp2a_lo_su(w01, cw.y, vC);
+                    vC = dp2a_hi_su(w23, cw.y, vC);
+                    vC = dp2a_lo_su(w45, cw.z, vC);
+                }
+                const bool hasC = c16 > LBp16;
+                vC = hasC ? vC : MININT;
+                // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
+                {
+                    int x = Cu + dp4a_uu(cw.z, avXD, 0) * gCu;
+                    int y = Du + dp4a_uu(cw.z, avYD, 0) * nGO;
+                    int z = Iu + dp4a_uu(cw.z, avZD, 0) * gIu;
+                    vD = pick3<2>(x, y, z, fD) - eD;
+                }
+                // traceback byte (mz_yama.c:253); the flags of nodes that do not exist are never consulted
+                // (K3 treats them as 0, which is what the reference stores)
+                acc = __funnelshift_r(acc, fC | fD | fI, 8);
+                if (active) {
+                    sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, hasI ? E_both : Efirst);
+                    if (u == 3) *tbw++ = acc;
+                }
+                Cl = vC; Dl = vD; Il = vI;
+                gCl = hasC ? nGO : 0; gIl = hasI ? nGO : 0;
+                Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
+                c16 += 16;
+                __syncwarp();
             }
-            __syncwarp();
-            if (__all_sync(0xffffffffu, done)) break;
-
-            const bool active = (c >= LBr);
-            // ---- grid point (r-1, c) ------------------------------------------------------------------
-            const unsigned ra = (c > RBp) ? minAddr : rdBase + ((unsigned)(c & rdMask) << 4);
-            const uint4 up = lds128(ra);
-            const int Cu = (int)up.x, Du = (int)up.y, Iu = (int)up.z;
-            const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
-
-            uint4 cw = make_uint4(0u, 0u, 0u, 0u);
-            if (active) cw = __ldg(reinterpret_cast<const uint4 *>(cols + c));
-
-            // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
-            int vI, fI;
-            {
-                int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
-                int y = Dl + dp4a_uu(cw.x, avYI, 0) * nGO;
-                int z = Il + dp4a_uu(cw.x, avZI, 0) * gIl;
-                fI = pick3(x, y, z, vI);
-                vI -= (int)((cw.x >> 8) & 0xffu) * KGE;
-            }
-            const bool hasI = c > LBr;
-            vI = hasI ? vI : MININT;
-            fI = hasI ? fI : 0;
-            const int gI = hasI ? nGO : 0;
-
-            // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
-            int vC, fC;
-            {
-                int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
-                int y = Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
-                int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
-                fC = pick3(x, y, z, vC);
-                vC = dp2a_lo_su(w01, cw.y, vC);
-                vC = dp2a_hi_su(w23, cw.y, vC);
-                vC = dp2a_lo_su(w45, cw.z, vC);
-            }
-            const bool hasC = c > LBp;
-            vC = hasC ? vC : MININT;
-            fC = hasC ? fC : 0;
-            const int gC = hasC ? nGO : 0;
-
-            // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
-            int vD, fD;
-            {
-                int x = Cu + dp4a_uu(cw.z, avXD, 0) * gCu;
-                int y = Du + dp4a_uu(cw.z, avYD, 0) * nGO;
-                int z = Iu + dp4a_uu(cw.z, avZD, 0) * gIu;
-                fD = pick3(x, y, z, vD);
-                vD -= eD;
-            }
-
-            if (active) {
-                sts128(wrBase + ((unsigned)(c & wrMask) << 4), vC, vD, vI, pack16(gC, gI));
-                unsigned byte = (unsigned)(fC | (fD << 2) | (fI << 4));     // mz_yama.c:253
-                acc = __funnelshift_r(acc, byte, 8);
-                int k = c - LBr;
-                if ((k & 3) == 3) tbRow[k >> 2] = acc;
-            }
-            Cl = vC; Dl = vD; Il = vI; gCl = gC; gIl = gI;
-            Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
-            __syncwarp();
         }
         __syncwarp();
     }
@@ -447,6 +474,7 @@ __global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, int nPai
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nPairs) return;
     const PairMeta pm = metas[p];
+    if (pm.M < 1) return;
     const RowRec *rows = rowPool + pm.rowBase;
     const unsigned char *tb = tbPool + pm.tbBase;
     unsigned char *script = scriptPool + pm.scriptBase;
@@ -459,9 +487,12 @@ __global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, int nPai
     const int limit = pm.M + pm.N;
     while (r > 0 || c > 0) {
         if (r < 0 || c < 0 || n >= limit) { status = -5; break; }           // mz_yama.c:274-276
-        int lb = rows[r].LB, rb = rows[r].RB;
+        const int lb = rows[r].LB16 >> 4, rb = rows[r].RB16 >> 4, lbp = rows[r].LBp16 >> 4;
         if (c < lb || c > rb) { status = -5; break; }                       // left the band (reference: undefined)
-        unsigned st = tb[rows[r].rowoff + (unsigned)(c - lb)];
+        unsigned st = tb[rows[r].tbOff + (unsigned)(c - lb)];
+        // flags of nodes that do not exist are stored as 0 by the reference (mz_yama.c:165,204)
+        if (r > 0 && c <= lb) st &= 0x0fu;
+        if (r > 0 && c <= lbp) st &= 0xfcu;
         script[n++] = (unsigned char)node;
         if (node == FLAG_I) { c--; node = st >> 4; }
         else if (node == FLAG_D) { r--; node = (st >> 2) & 3; }
