@@ -58,7 +58,8 @@ const int kRingOf[NBINS] = {128, 512, 2048, 4096};
 
 struct JobInfo {           // host-side facts about one pair
     int64_t cells = 0;     // tback_size of the reference
-    int64_t tbBytes = 0;   // traceback bytes with rows padded to 4
+    int64_t tbBytes = 0;   // traceback bytes (window-major layout: 32 B per wavefront step)
+    int nSteps = 0;        // wavefront steps (schedule below)
     int wmax = 0;          // widest band row
     int status = YB_OK;
 };
@@ -220,14 +221,35 @@ int64_t check_band(int M, int N, const int *LB, const int *RB, char *msg, int ms
             return YB_ERR_BAND;
         }
         cells += j + 1;
-        tb += (j + 1 + 6) & ~3;          // row padded to 4 B plus up to 3 B of phase (see K1)
         if (j + 1 > wm) wm = j + 1;
         if (r > 0 && LB[r] < LB[r - 1]) { if (msg) snprintf(msg, msglen, "LB not monotonic"); return YB_ERR_BAND; }
         if (r > 0 && RB[r] < RB[r - 1]) { if (msg) snprintf(msg, msglen, "RB not monotonic"); return YB_ERR_BAND; }
     }
-    if (tbBytes) *tbBytes = tb;
+    (void)tb;
     if (wmax) *wmax = wm;
     return cells;
+}
+
+// Wavefront schedule (see K2): rows 32b+1..32b+32 run on lanes 0..31 with column = step - (OFF_b + lane).
+// OFF grows per block by at least 32 (lane 0 stays behind lane 31 of the previous block) and by enough
+// that a lane starts its next row only after the row below its current one has stopped reading it.
+// Returns the step count; sched (may be null) receives ceil(M/32) block offsets.
+int make_schedule(int M, const int *LB, const int *RB, int *sched) {
+    int off = 0;
+    const int nblk = (M + 31) >> 5;
+    for (int b = 0; b < nblk; ++b) {
+        if (sched) sched[b] = off;
+        int need = 32;
+        const int r0 = 32 * b + 1, r1 = std::min(M - 32, 32 * b + 32);
+        for (int r = r0; r <= r1; ++r) need = std::max(need, RB[r + 1] - LB[r + 32] + 3);
+        if (b == nblk - 1) {
+            int lane = (M - 1) & 31;
+            int last = off + lane + RB[M];                 // step of the last cell
+            return ((last + 2) + 3) & ~3;                  // +1 step to publish the final scores, whole windows
+        }
+        off += need;
+    }
+    return 4;
 }
 
 int analyse_jobs(yb_ctx *ctx, int64_t n, const yb_job *jobs, std::vector<JobInfo> &info) {
@@ -249,6 +271,8 @@ int analyse_jobs(yb_ctx *ctx, int64_t n, const yb_job *jobs, std::vector<JobInfo
             continue;
         }
         ji.cells = cells;
+        ji.nSteps = make_schedule(j.M, j.LB, j.RB, nullptr);
+        ji.tbBytes = (int64_t)ji.nSteps * 32;
         if (j.K > ctx->maxDepth || j.L > 255) {
             ji.status = YB_ERR_LIMIT;
             if (rc == YB_OK) { set_err(ctx, "job %lld: profile depth K=%d L=%d exceeds the kernel limit (%d/255 rows)", (long long)i, j.K, j.L, ctx->maxDepth); rc = YB_ERR_LIMIT; }
@@ -266,7 +290,8 @@ int analyse_jobs(yb_ctx *ctx, int64_t n, const yb_job *jobs, std::vector<JobInfo
 struct Need { size_t blob, rows, cols, tb, script; };
 inline Need need_of(const yb_job &j, const JobInfo &ji) {
     Need n;
-    n.blob = align_up((size_t)j.K * j.M, 16) + align_up((size_t)j.L * j.N, 16) + 2 * align_up((size_t)(j.M + 1) * 4, 16);
+    n.blob = align_up((size_t)j.K * j.M, 16) + align_up((size_t)j.L * j.N, 16) + 2 * align_up((size_t)(j.M + 1) * 4, 16) +
+             align_up((size_t)((j.M + 31) >> 5) * 4, 16);
     n.rows = (size_t)j.M + 1;
     n.cols = (size_t)j.N + 1;
     n.tb = align_up((size_t)ji.tbBytes, 16);
@@ -319,12 +344,13 @@ int wave_upload(yb_ctx *ctx, Device &d, const yb_job *jobs, const std::vector<Jo
         pm.offB = off; memcpy(h + off, j.B, (size_t)j.L * j.N); off += align_up((size_t)j.L * j.N, 16);
         pm.offLB = off; memcpy(h + off, j.LB, (size_t)(j.M + 1) * 4); off += align_up((size_t)(j.M + 1) * 4, 16);
         pm.offRB = off; memcpy(h + off, j.RB, (size_t)(j.M + 1) * 4); off += align_up((size_t)(j.M + 1) * 4, 16);
+        pm.offSched = off; pm.nSteps = make_schedule(j.M, j.LB, j.RB, reinterpret_cast<int *>(h + off));
+        off += align_up((size_t)((j.M + 31) >> 5) * 4, 16);
         Need n = need_of(j, ji);
         pm.rowBase = rowBase; rowBase += n.rows;
         pm.colBase = colBase; colBase += n.cols;
         pm.tbBase = tbBase; tbBase += n.tb;
         pm.scriptBase = scriptBase; w.scriptOff[(size_t)i] = scriptBase; scriptBase += n.script;
-        pm.ringNeed = ji.wmax + 32;
         metas[i] = pm;
         binned[bin_of(ji.wmax)].push_back({ji.cells, (int)i});
     }
@@ -370,7 +396,7 @@ int wave_compute(Device &d, const Wave &w) {
     CUDA_TRY(d, cudaEventRecord(d.ev[2], d.stream));
     CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)w.count * sizeof(PairOut), d.stream));
     CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, d.stream));
-    yb_profile_kernel<<<(unsigned)w.count, K1_THREADS, 0, d.stream>>>(metas, blob, rows, cols, outs);
+    yb_profile_kernel<<<(unsigned)w.count, K1_THREADS, 0, d.stream>>>(metas, blob, rows, cols);
     d.launches++;
     CUDA_TRY(d, cudaEventRecord(d.ev[3], d.stream));
     for (int b = 0; b < NBINS; ++b) {
@@ -382,7 +408,10 @@ int wave_compute(Device &d, const Wave &w) {
         d.launches++;
     }
     CUDA_TRY(d, cudaEventRecord(d.ev[4], d.stream));
-    yb_traceback_kernel<<<(unsigned)((w.count + 127) / 128), 128, 0, d.stream>>>(metas, (int)w.count, rows, tb, script, outs);
+    {
+        const int nv = (int)w.order.size();
+        yb_traceback_kernel<<<(unsigned)((nv + 63) / 64), 64, 0, d.stream>>>(metas, order, nv, blob, tb, script, outs);
+    }
     d.launches++;
     CUDA_TRY(d, cudaEventRecord(d.ev[5], d.stream));
     CUDA_TRY(d, cudaStreamSynchronize(d.stream));

@@ -50,25 +50,32 @@ struct PairMeta {
     unsigned long long colBase;        // index of column 0's ColRec in the ColRec pool (N+1 records)
     unsigned long long tbBase;         // byte offset of this pair's traceback matrix
     unsigned long long scriptBase;     // byte offset of this pair's script (M+N bytes)
-    int ringNeed;                      // widest band row + 32 (host computed)
+    unsigned long long offSched;       // byte offset into the input blob: wavefront schedule, ceil(M/32) ints
+    int nSteps;                        // wavefront steps of this pair (host computed from the schedule)
     int pad;
 };
 
-// Row record, 80 B (5 x 16 B).  av* are byte-count vectors matched against the column words (see
+// Row record, 64 B (4 x 16 B).  av* are byte-count vectors matched against the column words (see
 // ColRec) with dp4a; everything a lane needs to run one row of the band.
 struct __align__(16) RowRec {
     unsigned avXC, avYC, avZC, avXI;   // q0: C-node x,y,z and I-node x coefficient bytes
     unsigned avXD, avYD, avZD;         // q1: D-node x,y,z coefficient bytes (bytes 2,3 only)
     int eD;                            //     ndA*L*gap_ext  (mz_yama.c:239-242)
     unsigned w01, w23, w45;            // q2: S6^T * classcount(A row) as int16 pairs (sum-of-pairs weights)
-    unsigned avYI;                     //     K<<8  (K*ndB)  or 0 on the last row (mz_yama.c:123)
-    unsigned avZI;                     // q3: K<<24 (K*b10)  or 0 on the last row
-    int LB16, RB16, LBp16;             //     16*LB[r], 16*RB[r], 16*LB[r-1]
-    int off;                           // q4: wavefront schedule: this row computes column (step - off)
-    unsigned tbOff;                    //     byte offset of cell (r, LB[r]) inside the pair's traceback matrix
+    int LB16;                          //     16*LB[r]
+    int RB16, LBp16;                   // q3: 16*RB[r], 16*LB[r-1]
+    int off;                           //     wavefront schedule: this row computes column (step - off)
     int RBn;                           //     RB[r+1] (RB[r] on the last row): how far the row below reads us
-    unsigned Efirst;                   //     guard multipliers published by the first cell of the row
 };
+
+// Traceback matrix layout ("window-major"): the warp advances one anti-diagonal per step; the byte of
+// the cell that lane l computed at step t lives at  (t>>2)*128 + 4*l + (t&3).  Every 4 steps the warp
+// stores one fully coalesced 128-B line, and a traceback path (which walks anti-diagonals backwards)
+// stays inside one line for ~32 moves.  Cell (r,c) was computed by lane (r-1)&31 at step c + off[r].
+__device__ __forceinline__ unsigned long long tb_index(int r, int c, int off) {
+    const unsigned t = (unsigned)(c + off);
+    return (unsigned long long)(t >> 2) * 128ull + (unsigned)(((r - 1) & 31) << 2) + (t & 3u);
+}
 
 // Column record, 16 B.
 //  w0 = (b01, ndB, dB, b10)           raw transition / dash counts of column c against column c-1
@@ -77,7 +84,7 @@ struct __align__(16) RowRec {
 //  w3 = w0 zeroed for c==1            (mz_yama.c:173, no gap-open at the start)
 struct __align__(16) ColRec { unsigned w0, w1, w2, w3; };
 
-struct PairOut { int m_new, C, D, I, status, nSteps; };
+struct PairOut { int m_new, C, D, I, status, pad; };
 
 __device__ __forceinline__ int classify(unsigned ch) {
     unsigned u = ch | 0x20u;
@@ -118,7 +125,7 @@ constexpr int K1_THREADS = 128;
 
 __global__ void __launch_bounds__(K1_THREADS)
 yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__restrict__ blob,
-                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, PairOut *__restrict__ outs) {
+                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool) {
     const PairMeta pm = metas[blockIdx.x];
     const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
     if (M < 1) return;                                  // invalid pair (rejected on the host)
@@ -128,8 +135,8 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     const int *RB = reinterpret_cast<const int *>(blob + pm.offRB);
     RowRec *rows = rowPool + pm.rowBase;
     ColRec *cols = colPool + pm.colBase;
+    const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
     const int GE = c_sc.gap_ext;
-    const int nGO = -c_sc.gap_open;
 
     // ---- columns of B (c = 0..N) -------------------------------------------------------------
     for (int c = threadIdx.x; c <= N; c += K1_THREADS) {
@@ -160,14 +167,12 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     // ---- rows of A (r = 0..M) ------------------------------------------------------------------
     for (int r = threadIdx.x; r <= M; r += K1_THREADS) {
         RowRec rr;
-        rr.avXC = rr.avYC = rr.avZC = rr.avXI = rr.avXD = rr.avYD = rr.avZD = rr.avYI = rr.avZI = 0u;
+        rr.avXC = rr.avYC = rr.avZC = rr.avXI = rr.avXD = rr.avYD = rr.avZD = 0u;
         rr.eD = 0; rr.w01 = rr.w23 = rr.w45 = 0u;
         const int lb = LB[r], lbp = r > 0 ? LB[r - 1] : 0;
         rr.LB16 = lb * 16; rr.RB16 = RB[r] * 16; rr.LBp16 = lbp * 16;
-        rr.off = 0; rr.tbOff = 0u;
+        rr.off = r >= 1 ? sched[(r - 1) >> 5] + ((r - 1) & 31) : 0;
         rr.RBn = r < M ? RB[r + 1] : RB[r];
-        // first cell of the row: its I node never exists, its C node only if the band moved right
-        rr.Efirst = pack16((r > 0 && lb > lbp) ? nGO : 0, 0);
         if (r >= 1) {
             const unsigned char *now = A + (size_t)(r - 1) * K;
             const unsigned char *up = now - K;    // only dereferenced when r > 1
@@ -193,11 +198,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
             }
             rr.avZC = pack4(0, 0, ndA, dA);
             rr.avZD = pack4(0, 0, ndA, ndA);
-            if (r < M) {                                        // mz_yama.c:123 (row<M)
-                rr.avXI = pack4(0, ndA, 0, dA);
-                rr.avYI = (unsigned)K << 8;
-                rr.avZI = (unsigned)K << 24;
-            }
+            if (r < M) rr.avXI = pack4(0, ndA, 0, dA);         // mz_yama.c:123 (row<M)
             rr.eD = (int)ndA * L * GE;
             int w[6];
 #pragma unroll
@@ -210,48 +211,6 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
             rr.w01 = pack16(w[0], w[1]); rr.w23 = pack16(w[2], w[3]); rr.w45 = pack16(w[4], w[5]);
         }
         rows[r] = rr;
-    }
-    __syncthreads();
-
-    // ---- warp 0: wavefront schedule, then traceback row offsets -----------------------------------
-    // Rows 32b+1..32b+32 (lanes 0..31) run with column = step - (OFF_b + lane).  OFF grows per block by
-    // at least 32 (lane 0 stays behind lane 31 of the previous block) and by enough that a lane starts
-    // its next row only after the row below its current one has stopped reading it.
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int off = 0;
-        const int nblk = (M + 31) >> 5;
-        unsigned run = (unsigned)((RB[0] + 1 + 3) & ~3);       // row 0 occupies bytes [0, RB[0]]
-        int lastStart = 0;
-        for (int b = 0; b < nblk; ++b) {
-            int r = 32 * b + 1 + lane;
-            int need = 32;
-            if (r + 32 <= M) need = max(need, RB[r + 1] - LB[r + 32] + 3);
-            need = __reduce_max_sync(0xffffffffu, need);
-            // traceback bytes: cell (r,c) lives at tbOff + (c-LB[r]); tbOff = 4-aligned base + phase so
-            // that the byte position is congruent to the step number mod 4 (uniform 4-step word stores)
-            unsigned wdt = 0, phase = 0;
-            int myoff = off + lane;
-            if (r <= M) {
-                phase = (unsigned)(LB[r] + myoff) & 3u;
-                wdt = (phase + (unsigned)(RB[r] - LB[r] + 1) + 3u) & ~3u;
-            }
-            unsigned inc = wdt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            if (r <= M) {
-                rows[r].off = myoff;
-                rows[r].tbOff = run + inc - wdt + phase;
-                if (r == M) lastStart = myoff + RB[r];
-            }
-            run += __shfl_sync(0xffffffffu, inc, 31);
-            off += need;
-        }
-        lastStart = __reduce_max_sync(0xffffffffu, lastStart);
-        if (lane == 0) outs[blockIdx.x].nSteps = lastStart + 2;   // last cell at step lastStart, +1 to flush
     }
 }
 
@@ -334,7 +293,9 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const ColRec *cols = colPool + pm.colBase;
         unsigned char *tb = tbPool + pm.tbBase;
         const int KGE = pm.K * c_sc.gap_ext;
-        const int nSteps = outs[p].nSteps;
+        const int nSteps = pm.nSteps;
+        const unsigned avYI_in = (unsigned)pm.K << 8, avZI_in = (unsigned)pm.K << 24;   // K*ndB, K*b10
+        const unsigned E_c0 = pack16(nGO, 0);
 
         // ---- row 0 (mz_yama.c:83-94) into the ring + its traceback bytes ------------------------
         {
@@ -356,7 +317,6 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     int I0 = -(carry + inc) * KGE;
                     if (c == 0) sts128(a, 0, 0, 0, 0u);                    // (0,0): nothing is ever charged
                     else sts128(a, MININT, MININT, I0, pack16(0, nGO));    // only the I node exists in row 0
-                    tb[c] = (c == 0) ? 0 : (unsigned char)(FLAG_I << 4);
                 } else if (c <= RB1) {
                     sts128(a, MININT, MININT, MININT, E_both);             // stale dp[] entry, mz_yama.c:93-94
                 }
@@ -370,16 +330,19 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avYI = 0, avZI = 0, avXD = 0, avYD = 0, avZD = 0;
         unsigned w01 = 0, w23 = 0, w45 = 0, Efirst = 0;
         int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBp16 = 0, RBn = 0, c16 = 0;
-        unsigned *tbw = nullptr;
         auto load_row = [&](int t) {
-            uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3), q4 = __ldg(rp + 4);
+            uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
             avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
             avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
-            w01 = q2.x; w23 = q2.y; w45 = q2.z; avYI = q2.w;
-            avZI = q3.x; LB16 = (int)q3.y; RB16 = (int)q3.z; LBp16 = (int)q3.w;
-            c16 = (t - (int)q4.x) * 16;
-            tbw = reinterpret_cast<unsigned *>(tb + (q4.y & ~3u));
-            RBn = (int)q4.z; Efirst = q4.w;
+            w01 = q2.x; w23 = q2.y; w45 = q2.z; LB16 = (int)q2.w;
+            RB16 = (int)q3.x; LBp16 = (int)q3.y;
+            c16 = (t - (int)q3.z) * 16;
+            RBn = (int)q3.w;
+            const bool inner = r < M;                               // mz_yama.c:123: no I-node gap-open on the last row
+            avYI = inner ? avYI_in : 0u;
+            avZI = inner ? avZI_in : 0u;
+            // first cell of the row: its I node never exists, its C node only if the band moved right
+            Efirst = (LB16 > LBp16) ? E_c0 : 0u;
         };
         if (r <= M) load_row(0);
         unsigned acc = 0;
@@ -398,11 +361,9 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 #pragma unroll 1
                     for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
                         sts128(and_xor((unsigned)cc << 4, wrMask, wrBase), MININT, MININT, MININT, E_both);
-                    // (b) flush the partial traceback word (u bytes of it are valid)
-                    if (u != 0) *tbw = acc >> (8 * (4 - u));
-                    // (c) final scores
+                    // (b) final scores
                     if (r == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
-                    // (d) move 32 rows down
+                    // (c) move 32 rows down
                     r += 32;
                     rp += 32 * (sizeof(RowRec) / 16);
                     if (r <= M) load_row(t4 + u);
@@ -451,8 +412,9 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 acc = __funnelshift_r(acc, fC | fD | fI, 8);
                 if (active) {
                     sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, hasI ? E_both : Efirst);
-                    if (u == 3) *tbw++ = acc;
                 }
+                // one coalesced 128-B line of traceback bytes per 4 steps (see tb_index)
+                if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)t4 * 8 + lane] = acc;
                 Cl = vC; Dl = vD; Il = vI;
                 gCl = hasC ? nGO : 0; gIl = hasI ? nGO : 0;
                 Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
@@ -465,17 +427,22 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 }
 
 // =================================================================================================
-// K3: traceback (mz_yama.c:257-291), one thread per pair.
+// K3: traceback (mz_yama.c:257-291), one thread per pair; threads of a warp get pairs of similar size
+// (the launch order is sorted by cell count).  Per move it needs LB[r], LB[r-1], RB[r] (int arrays of
+// the input blob, 32 rows per cache line) and one traceback byte (window-major layout, ~32 moves per
+// cache line), so the dependent-load chain mostly hits L1.
 // =================================================================================================
-__global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, int nPairs,
-                                    const RowRec *__restrict__ rowPool,
+__global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order,
+                                    int nPairs, const unsigned char *__restrict__ blob,
                                     const unsigned char *__restrict__ tbPool,
                                     unsigned char *__restrict__ scriptPool, PairOut *__restrict__ outs) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nPairs) return;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nPairs) return;
+    const int p = order[idx];
     const PairMeta pm = metas[p];
-    if (pm.M < 1) return;
-    const RowRec *rows = rowPool + pm.rowBase;
+    const int *LB = reinterpret_cast<const int *>(blob + pm.offLB);
+    const int *RB = reinterpret_cast<const int *>(blob + pm.offRB);
+    const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
     const unsigned char *tb = tbPool + pm.tbBase;
     unsigned char *script = scriptPool + pm.scriptBase;
     PairOut o = outs[p];
@@ -485,14 +452,22 @@ __global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, int nPai
     else node = FLAG_I;
     int r = pm.M, c = pm.N, n = 0, status = 0;
     const int limit = pm.M + pm.N;
+    int blk = -1, offBlk = 0;
     while (r > 0 || c > 0) {
         if (r < 0 || c < 0 || n >= limit) { status = -5; break; }           // mz_yama.c:274-276
-        const int lb = rows[r].LB16 >> 4, rb = rows[r].RB16 >> 4, lbp = rows[r].LBp16 >> 4;
-        if (c < lb || c > rb) { status = -5; break; }                       // left the band (reference: undefined)
-        unsigned st = tb[rows[r].tbOff + (unsigned)(c - lb)];
-        // flags of nodes that do not exist are stored as 0 by the reference (mz_yama.c:165,204)
-        if (r > 0 && c <= lb) st &= 0x0fu;
-        if (r > 0 && c <= lbp) st &= 0xfcu;
+        unsigned st;
+        if (r == 0) {
+            st = (c == 0) ? 0u : (unsigned)(FLAG_I << 4);                   // row 0, mz_yama.c:80,91
+        } else {
+            if (((r - 1) >> 5) != blk) { blk = (r - 1) >> 5; offBlk = __ldg(sched + blk); }
+            // all four loads are independent of each other: one round trip per move
+            const int lb = __ldg(LB + r), lbp = __ldg(LB + r - 1), rb = __ldg(RB + r);
+            st = __ldg(tb + tb_index(r, min(c, pm.N), offBlk + ((r - 1) & 31)));
+            if (c < lb || c > rb) { status = -5; break; }                   // left the band (reference: undefined)
+            // flags of nodes that do not exist are stored as 0 by the reference (mz_yama.c:165,204)
+            if (c <= lb) st &= 0x0fu;
+            if (c <= lbp) st &= 0xfcu;
+        }
         script[n++] = (unsigned char)node;
         if (node == FLAG_I) { c--; node = st >> 4; }
         else if (node == FLAG_D) { r--; node = (st >> 2) & 3; }
