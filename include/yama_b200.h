@@ -106,6 +106,13 @@ int yb_assemble(const yb_job *job, const yb_result *res, uint8_t *out);
  * wording. */
 int64_t yb_check_band(int32_t M, int32_t N, const int32_t *LB, const int32_t *RB, char *msg, int msglen);
 
+/* ---- sharding plan (the reference has no counterpart: it is single-process) ------ */
+/* Cuts jobs 0..n-1, kept in reference order, into nparts contiguous ranges of near-equal cost, where
+ * cost(job) = cells[job] + a fixed per-pair overhead.  cuts receives nparts+1 boundaries
+ * (cuts[0]=0, cuts[nparts]=n).  The library uses exactly this plan to spread one batch over its
+ * devices; a multi-process host (one rank per GPU) calls it to pick its own range. Host-only. */
+int yb_plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cuts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,4 +6,4 @@ tests and the benchmark.  The C host of multiz (multiz/tba/roast command lines, 
 pre_yama, stitching) stays the reference's own code and links against libyama_b200.so through
 integration/ (see INTEGRATION.md).
 """
-from .yama import (YamaB200, YamaError, lib_path, load_library, ABI_SYMBOLS, hox70_tables)  # noqa: F401
+from .yama import (YamaB200, YamaError, lib_path, load_library, ABI_SYMBOLS, hox70_tables, plan_split, JOB_DTYPE, RESULT_DTYPE)  # noqa: F401

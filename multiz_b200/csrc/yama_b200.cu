@@ -487,21 +487,31 @@ void collect_stats(yb_ctx *ctx, yb_stats *st, double total_ms, int64_t cells, in
     st->n_devices = (int)ctx->devs.size();
 }
 
-// contiguous, cell-balanced split of [0,n) over the devices
-std::vector<int64_t> split_jobs(const std::vector<JobInfo> &info, int ndev) {
-    int64_t n = (int64_t)info.size();
-    std::vector<int64_t> cut((size_t)ndev + 1, n);
+// contiguous, cell-balanced split of [0,n) into nparts ranges (devices of one context, or ranks)
+constexpr int64_t kPairOverheadCells = 2000;   // fixed cost of one pair (row-0 setup, queue pop) in cell units
+void plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cut) {
+    for (int k = 0; k <= nparts; ++k) cut[k] = n;
     cut[0] = 0;
     long double total = 0;
-    for (auto &ji : info) total += (long double)ji.cells + 2000;   // +launch/row overhead per pair
+    for (int64_t i = 0; i < n; ++i) total += (long double)std::max<int64_t>(cells[i], 0) + kPairOverheadCells;
     long double acc = 0;
     int d = 1;
-    for (int64_t i = 0; i < n && d < ndev; ++i) {
-        acc += (long double)info[(size_t)i].cells + 2000;
-        while (d < ndev && acc >= total * d / ndev) cut[(size_t)d++] = i + 1;
+    for (int64_t i = 0; i < n && d < nparts; ++i) {
+        const long double before = acc;
+        acc += (long double)std::max<int64_t>(cells[i], 0) + kPairOverheadCells;
+        while (d < nparts && acc >= total * d / nparts) {
+            // boundary d goes to whichever side of job i is nearer to the ideal cost d/nparts
+            const long double target = total * d / nparts;
+            cut[d++] = (target - before < acc - target) ? i : i + 1;
+        }
     }
-    for (int k = 1; k <= ndev; ++k) cut[(size_t)k] = std::max(cut[(size_t)k], cut[(size_t)k - 1]);
-    cut[(size_t)ndev] = n;
+    for (int k = 1; k <= nparts; ++k) cut[k] = std::max(cut[k], cut[k - 1]);
+    cut[nparts] = n;
+}
+std::vector<int64_t> split_jobs(const std::vector<JobInfo> &info, int ndev) {
+    std::vector<int64_t> cells(info.size()), cut((size_t)ndev + 1);
+    for (size_t i = 0; i < info.size(); ++i) cells[i] = info[i].cells;
+    plan_split((int64_t)info.size(), cells.data(), ndev, cut.data());
     return cut;
 }
 
@@ -654,6 +664,12 @@ int yb_set_scores(yb_ctx *ctx, const int32_t *ss, const int32_t *gop, int32_t ga
         }
     }
     ctx->scoresSet = true;
+    return YB_OK;
+}
+
+int yb_plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cuts) {
+    if (n < 0 || nparts < 1 || !cuts || (n > 0 && !cells)) return YB_ERR_ARG;
+    plan_split(n, cells, nparts, cuts);
     return YB_OK;
 }
 

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ABI_SYMBOLS = (
     "yb_create", "yb_destroy", "yb_last_error", "yb_device_count", "yb_set_scores",
     "yb_run_batch", "yb_resident_load", "yb_resident_step", "yb_resident_fetch",
-    "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band",
+    "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band", "yb_plan_split",
 )
 
 
@@ -105,8 +105,21 @@ def load_library():
     lib.yb_assemble.restype = C.c_int
     lib.yb_check_band.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
     lib.yb_check_band.restype = C.c_int64
+    lib.yb_plan_split.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    lib.yb_plan_split.restype = C.c_int
     _LIB = lib
     return lib
+
+
+def plan_split(cells, nparts: int) -> np.ndarray:
+    """Contiguous, cell-balanced cut of a reference-ordered job list into `nparts` ranges (yb_plan_split).
+    Host-only: usable without a GPU (e.g. by every rank of a multi-process run to find its own range)."""
+    cells = np.ascontiguousarray(cells, dtype=np.int64)
+    cuts = np.zeros(nparts + 1, dtype=np.int64)
+    rc = load_library().yb_plan_split(len(cells), cells.ctypes.data, int(nparts), cuts.ctypes.data)
+    if rc != 0:
+        raise YamaError(rc, "yb_plan_split: bad arguments")
+    return cuts
 
 
 def hox70_tables(which: int = 70):

@@ -72,3 +72,18 @@ def test_single_call_mirror(yama_ctx, oracle):
     al, m = yama_ctx.yama(A, 3, 70, B, 2, 66, LB, RB)
     o = oracle.yama(A, B, LB, RB)
     assert m == o["m_new"] and np.array_equal(al, o["al"])
+
+
+@pytest.mark.parametrize("name", ["yama_small.npz", "yama_deep.npz"])
+def test_golden_fixtures(yama_ctx, name):
+    """The CUDA path against the committed outputs of the compiled reference (tools/make_golden.py) --
+    no oracle in the loop.  yama_deep.npz includes K+L=100 profiles and the int32 wrap case."""
+    from golden_util import GoldenYama
+    g = GoldenYama(name)
+    jobs, keep = yama_ctx.make_jobs(g.problems())
+    res, _ = yama_ctx.run_batch(jobs)
+    for i in range(g.n):
+        r = res[i]
+        assert r["status"] == 0
+        g.check(i, dict(cdi=(r["C"], r["D"], r["I"]), m_new=r["m_new"], script=yama_ctx.script_of(r),
+                        al=yama_ctx.assemble(jobs[i], r), cells=r["cells"]))
