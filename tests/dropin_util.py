@@ -1,0 +1,75 @@
+"""Helpers for the MAF-level parity tests: run a multiz-compatible tool and compare every output byte with
+the reference's (committed golden outputs, or the reference binary in oracle/_ref/bin run beside it)."""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from tools.make_golden import MAF_CASES  # noqa: E402  (the argv of every golden case)
+
+GOLD_MAF = os.path.join(ROOT, "tests", "golden", "maf")
+REF_MULTIZ = os.path.join(ROOT, "oracle", "_ref", "bin", "multiz")
+GPU_MULTIZ = os.path.join(ROOT, "integration", "_ref", "bin", "multiz")
+GPU_MULTIC = os.path.join(ROOT, "integration", "_ref", "bin", "multic")
+SHIM_MULTIZ = os.path.join(ROOT, "integration", "_ref", "bin", "multiz_shim")
+
+
+def run_tool(tool, argv, cwd, env=None, timeout=600):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([tool] + list(argv), cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=timeout)
+    return p.returncode, p.stdout, p.stderr
+
+
+def check_golden_cases(tool, tmp_path, env=None):
+    """Every case of tools/make_golden.py:MAF_CASES, byte for byte (stdout + out1 + out2)."""
+    d = str(tmp_path / "maf")
+    os.makedirs(d, exist_ok=True)
+    for f in ("ref.sp1.maf", "ref.sp2.maf", "ref.sp3.maf", "v1.stdout"):
+        shutil.copy(os.path.join(GOLD_MAF, f), d)
+    for name, argv in MAF_CASES:
+        outs = [a for a in argv if a.startswith(name + ".out")]
+        # the tool writes NAME.out1/2 into the scratch dir; the expected bytes are the golden files of that name
+        rc, out, err = run_tool(tool, argv, d, env)
+        assert rc == 0, (name, err.decode()[-500:])
+        want = open(os.path.join(GOLD_MAF, name + ".stdout"), "rb").read()
+        if name == "step2":
+            pass    # its input v1.stdout was copied from the golden set above
+        assert out == want, f"{name}: stdout differs from the reference's"
+        for o in outs:
+            assert open(os.path.join(d, o), "rb").read() == open(os.path.join(GOLD_MAF, o), "rb").read(), (name, o)
+
+
+def check_against_live_reference(tool, tmp_path, ref_len, n_species, seed, env=None, versions=(1, 0), extra=()):
+    """Fresh synthetic data; the reference binary and `tool` run with identical argv in sibling dirs."""
+    from tools.mafsynth import make_dataset
+    da, db = str(tmp_path / "ref"), str(tmp_path / "our")
+    make_dataset(da, ref_len=ref_len, n_species=n_species, seed=seed, lower=0.01)
+    shutil.copytree(da, db)
+    report = []
+    for v in versions:
+        argv = list(extra) + ["ref.sp1.maf", "ref.sp2.maf", str(v), f"u1.v{v}", f"u2.v{v}"]
+        rc_r, out_r, _ = run_tool(REF_MULTIZ, argv, da)
+        rc_o, out_o, err_o = run_tool(tool, argv, db, env)
+        assert rc_r == 0 and rc_o == 0, err_o.decode()[-500:]
+        assert out_o == out_r, f"v={v}: stdout differs"
+        for f in (f"u1.v{v}", f"u2.v{v}"):
+            assert open(os.path.join(db, f), "rb").read() == open(os.path.join(da, f), "rb").read(), f
+        report.append((v, len(out_r), err_o.decode().strip().splitlines()[-1:] if err_o else []))
+        if v == 1 and n_species >= 3:          # progressive merge: acc = multiz(acc, ref.spI, 1)
+            acc = "acc2.maf"
+            for d, o in ((da, out_r), (db, out_o)):
+                open(os.path.join(d, acc), "wb").write(o)
+            for i in range(3, n_species + 1):
+                argv = list(extra) + [acc, f"ref.sp{i}.maf", "1", "w1", "w2"]
+                rc_r, out_r, _ = run_tool(REF_MULTIZ, argv, da)
+                rc_o, out_o, err_o = run_tool(tool, argv, db, env)
+                assert rc_r == 0 and rc_o == 0, err_o.decode()[-500:]
+                assert out_o == out_r, f"progressive step {i}: stdout differs"
+                acc = f"acc{i}.maf"
+                for d, o in ((da, out_r), (db, out_o)):
+                    open(os.path.join(d, acc), "wb").write(o)
+    return report

@@ -1,0 +1,27 @@
+"""CPU suite, part 4: host logic of the drop-in (integration/yama_dropin.cpp).  The reference's own host code
+(multiz.c, mz_preyama.c, maf.c, ...) runs unmodified around our `yama` symbol; the speculative record/replay
+driver must reproduce the reference's output byte for byte whatever the aligner behind the C ABI is.  Here
+that aligner is the oracle (integration/_ref/bin/multiz_shim -> oracle/libyama_shim.so): a test of the HOST
+side only.  The same cases run against the CUDA library in tests/test_dropin_gpu.py."""
+import os
+
+import pytest
+
+from dropin_util import REF_MULTIZ, SHIM_MULTIZ, check_against_live_reference, check_golden_cases
+
+pytestmark = pytest.mark.skipif(not os.path.exists(SHIM_MULTIZ),
+                                reason="integration/_ref/bin/multiz_shim not built (needs /root/reference at build time)")
+
+
+@pytest.mark.parametrize("mode", ["batch", "direct"])
+def test_golden_maf_cases(tmp_path, mode):
+    check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_DROPIN": mode})
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin/multiz not built")
+def test_fresh_data_against_reference_binary(tmp_path):
+    rep = check_against_live_reference(SHIM_MULTIZ, tmp_path, ref_len=60_000, n_species=4, seed=5,
+                                       env={"YB_DROPIN_STATS": "1"})
+    # v=1 needs one speculative pass, v=0 two (stage 2 consumes stage 1's output, mz_preyama.c:335); no misses
+    for v, _, last in rep:
+        assert last and "misses=0" in last[0] and f"passes={1 if v == 1 else 2}" in last[0], last

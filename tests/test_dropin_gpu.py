@@ -1,0 +1,54 @@
+"""GPU parity at the MAF level (BASELINE.json configs[0]): the reference's own multiz host linked against
+libyama_b200.so (integration/_ref/bin/multiz) must write byte-identical MAF to the reference binary --
+stdout, out1 and out2 -- in v=1 and v=0, batched (record/replay) and one pair per launch."""
+import os
+
+import pytest
+
+from dropin_util import GPU_MULTIC, GPU_MULTIZ, REF_MULTIZ, check_against_live_reference, check_golden_cases, run_tool
+
+pytestmark = [pytest.mark.gpu]
+
+
+def _need(path):
+    assert os.path.exists(path), f"{path} missing: run __graft_entry__.build() where /root/reference exists"
+
+
+@pytest.mark.parametrize("mode", ["batch", "direct"])
+def test_golden_maf_cases_gpu(tmp_path, mode):
+    _need(GPU_MULTIZ)
+    check_golden_cases(GPU_MULTIZ, tmp_path, env={"YB_DROPIN": mode})
+
+
+def test_cfg1_one_megabase_merge(tmp_path):
+    """configs[0]: multiz merge of two synthetic pairwise MAFs on a 1 Mb reference, R=30 M=1, v=1 and v=0."""
+    _need(GPU_MULTIZ); _need(REF_MULTIZ)
+    rep = check_against_live_reference(GPU_MULTIZ, tmp_path, ref_len=1_000_000, n_species=2, seed=1,
+                                       env={"YB_DROPIN_STATS": "1"})
+    for v, _, last in rep:
+        assert last and "misses=0" in last[0], last
+        print("cfg1 v=%d:" % v, last[0])
+
+
+def test_progressive_five_way_small(tmp_path):
+    """configs[1] in miniature: progressive 5-way merge (K grows 2..5), 200 kb, R=30 and R=100."""
+    _need(GPU_MULTIZ); _need(REF_MULTIZ)
+    check_against_live_reference(GPU_MULTIZ, tmp_path / "r30", ref_len=200_000, n_species=5, seed=2, versions=(1,))
+    check_against_live_reference(GPU_MULTIZ, tmp_path / "r100", ref_len=100_000, n_species=3, seed=3, versions=(1, 0),
+                                 extra=("R=100",))
+
+
+def test_multic_same_boundary(tmp_path):
+    """multic reaches yama through the same pre_yama() (multic.c:72); its drop-in build must agree with the
+    reference's multic."""
+    _need(GPU_MULTIC)
+    ref_multic = os.path.join(os.path.dirname(REF_MULTIZ), "multic")
+    _need(ref_multic)
+    from tools.mafsynth import make_dataset
+    d = str(tmp_path / "d")
+    make_dataset(d, ref_len=80_000, n_species=2, seed=9)
+    argv = ["ref.sp1.maf", "ref.sp2.maf", "1"]
+    rc_r, out_r, _ = run_tool(ref_multic, argv, d)
+    rc_o, out_o, err = run_tool(GPU_MULTIC, argv, d)
+    assert rc_r == rc_o, err.decode()[-300:]
+    assert out_o == out_r

@@ -10,7 +10,11 @@ container, where /root/reference exists; the fixtures travel, the reference does
   scores.npz       ss[128][128], gop[16], gap_extend as init_scores70/85 leave them (mz_scores.c:94-122).
   smooth.npz       LB/RB before/after the reference's smooth() (mz_preyama.c:17-35).
 
-  python tools/make_golden.py            # rewrites tests/golden/*.npz deterministically
+  maf/             a 12 kb three-species synthetic data set (tools/mafsynth.py) and the byte-exact outputs of
+                   the reference's own `multiz` on it: v=1, v=0, and the second step of a progressive merge
+                   (stdout + out1 + out2 each).
+
+  python tools/make_golden.py            # rewrites tests/golden/ deterministically
 """
 from __future__ import annotations
 
@@ -113,6 +117,29 @@ def smooth_cases(host):
     return cases
 
 
+MAF_CASES = (   # name, argv after the tool name (run with cwd = tests/golden/maf)
+    ("v1", ["ref.sp1.maf", "ref.sp2.maf", "1", "v1.out1", "v1.out2"]),
+    ("v0", ["ref.sp1.maf", "ref.sp2.maf", "0", "v0.out1", "v0.out2"]),
+    ("v1r12", ["R=12", "M=50", "ref.sp1.maf", "ref.sp2.maf", "1", "v1r12.out1", "v1r12.out2"]),
+    ("step2", ["v1.stdout", "ref.sp3.maf", "1", "step2.out1", "step2.out2"]),
+    ("mixed", ["ref.sp1.maf", "ref.sp3.maf", "1"]),          # no out files: unused pieces interleave on stdout
+)
+
+
+def make_maf_golden():
+    import subprocess
+    from tools.mafsynth import make_dataset
+    d = os.path.join(GOLD, "maf")
+    os.makedirs(d, exist_ok=True)
+    for f in os.listdir(d):
+        os.remove(os.path.join(d, f))
+    make_dataset(d, ref_len=12_000, n_species=3, seed=11, lower=0.02, blk=(150, 900))
+    tool = os.path.join(ROOT, "oracle", "_ref", "bin", "multiz")
+    for name, argv in MAF_CASES:
+        with open(os.path.join(d, name + ".stdout"), "wb") as f:
+            subprocess.run([tool] + argv, cwd=d, stdout=f, check=True)
+
+
 def main():
     build(quiet=True)
     if not Reference.available():
@@ -141,8 +168,10 @@ def main():
         off=np.concatenate([[0], np.cumsum([c[0] + 1 for c in cases])]).astype(np.int64),
         LB_in=np.concatenate([c[3] for c in cases]), RB_in=np.concatenate([c[4] for c in cases]),
         LB_out=np.concatenate([c[5] for c in cases]), RB_out=np.concatenate([c[6] for c in cases]))
-    for f in sorted(os.listdir(GOLD)):
-        print(f, os.path.getsize(os.path.join(GOLD, f)))
+    make_maf_golden()
+    for dp, _, fs in sorted(os.walk(GOLD)):
+        for f in sorted(fs):
+            print(os.path.relpath(os.path.join(dp, f), GOLD), os.path.getsize(os.path.join(dp, f)))
 
 
 if __name__ == "__main__":
