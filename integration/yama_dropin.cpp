@@ -94,8 +94,10 @@ struct Globals {
     bool stats = false;
     uint64_t calls = 0, misses = 0, direct = 0;
     double gpu_ms = 0, kernel_ms = 0;
-    int64_t cells = 0, batches = 0, jobs = 0;
+    int64_t cells = 0, batches = 0, jobs = 0, failed = 0;
     int passes = 0;
+    bool debug = false;
+    std::unordered_map<Key, int, KeyHash> failedKeys;   // debug: batch status of jobs that did not align
 } G;
 
 double now_ms() {
@@ -350,7 +352,15 @@ void align_pending() {
     // per-pair failures (band / limit / traceback) are not fatal here: the final pass meets the same job
     // as a miss and reports it at the point where the reference would
     for (size_t i = 0; i < n; ++i) {
-        if (res[i].status != YB_OK) continue;
+        if (res[i].status != YB_OK) {
+            ++G.failed;
+            if (G.debug) {
+                G.failedKeys.emplace(G.pending[i].key, res[i].status);
+                fprintf(stderr, "yama_b200[debug]: batch job %zu failed status=%d K=%d M=%d L=%d N=%d\n", i, res[i].status,
+                        G.pending[i].K, G.pending[i].M, G.pending[i].L, G.pending[i].N);
+            }
+            continue;
+        }
         Entry e;
         e.m_new = res[i].m_new;
         e.off = G.scripts.size();
@@ -396,9 +406,9 @@ int run_batched(int argc, char **argv) {
 void print_stats() {
     if (!G.stats) return;
     fprintf(stderr,
-            "yama_b200: passes=%d batches=%lld jobs=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
+            "yama_b200: passes=%d batches=%lld jobs=%lld failed=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
             "gpu_ms=%.2f kernel_ms=%.2f devices=%d\n",
-            G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.cells, (unsigned long long)G.calls,
+            G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.failed, (long long)G.cells, (unsigned long long)G.calls,
             (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms,
             G.ctx ? yb_device_count(G.ctx) : 0);
 }
@@ -458,6 +468,11 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
         return;
     }
     ++G.misses;                 // REPLAY miss: speculation did not cover this call; still exact
+    if (G.debug) {
+        auto f = G.failedKeys.find(key);
+        fprintf(stderr, "yama_b200[debug]: replay miss at call %llu K=%d M=%d L=%d N=%d batch_status=%d\n",
+                (unsigned long long)G.calls, K, M, L, N, f == G.failedKeys.end() ? 1 : f->second);
+    }
     run_direct(job, OAL, OM);
 }
 
@@ -471,6 +486,7 @@ int main(int argc, char **argv) {
         return 2;
     }
     G.stats = getenv("YB_DROPIN_STATS") != nullptr;
+    G.debug = getenv("YB_DROPIN_DEBUG") != nullptr;
     const char *m = getenv("YB_DROPIN");
     int rc;
     if (m && strcmp(m, "direct") == 0) {

@@ -73,3 +73,25 @@ def check_against_live_reference(tool, tmp_path, ref_len, n_species, seed, env=N
                 for d, o in ((da, out_r), (db, out_o)):
                     open(os.path.join(d, acc), "wb").write(o)
     return report
+
+
+def parse_stats(line):
+    """'yama_b200: passes=2 batches=2 jobs=...' -> dict of numbers."""
+    import re
+    return {k: float(v) for k, v in re.findall(r"(\w+)=([0-9.]+)", line)}
+
+
+def check_speculation(report):
+    """v=1: one speculative pass covers every call.  v=0: two passes; a handful of stage-2 calls may miss
+    because the REFERENCE's band for them depends on an uninitialised heap byte (mz_preyama.c:296 passes rows
+    1..K of a K-row A to mapping(), which reads one byte past the buffer when no column was removed) -- the
+    drop-in then aligns that pair synchronously, so the output stays exact; see DESIGN.md."""
+    for v, _, last in report:
+        assert last, "no stats line"
+        st = parse_stats(last[0])
+        assert st["passes"] == (1 if v == 1 else 2), last
+        assert st["failed"] == 0
+        if v == 1:
+            assert st["misses"] == 0, last
+        else:
+            assert st["misses"] <= max(2, 0.01 * st["calls"]), last

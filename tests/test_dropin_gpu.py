@@ -5,7 +5,7 @@ import os
 
 import pytest
 
-from dropin_util import GPU_MULTIC, GPU_MULTIZ, REF_MULTIZ, check_against_live_reference, check_golden_cases, run_tool
+from dropin_util import GPU_MULTIC, GPU_MULTIZ, REF_MULTIZ, check_against_live_reference, check_golden_cases, check_speculation, run_tool
 
 pytestmark = [pytest.mark.gpu]
 
@@ -25,8 +25,8 @@ def test_cfg1_one_megabase_merge(tmp_path):
     _need(GPU_MULTIZ); _need(REF_MULTIZ)
     rep = check_against_live_reference(GPU_MULTIZ, tmp_path, ref_len=1_000_000, n_species=2, seed=1,
                                        env={"YB_DROPIN_STATS": "1"})
+    check_speculation(rep)
     for v, _, last in rep:
-        assert last and "misses=0" in last[0], last
         print("cfg1 v=%d:" % v, last[0])
 
 
