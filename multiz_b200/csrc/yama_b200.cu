@@ -1,9 +1,15 @@
 // yama_b200.cu -- host runtime + C ABI (include/yama_b200.h) around the sm_100a kernels.
 //
-// One context owns 1..8 devices.  A batch of independent block pairs is cut into contiguous,
-// cell-balanced ranges (one per device, no collective: the merge has no cross-pair dependency,
-// SURVEY §8(e)); each device processes its range in waves sized to its staging buffers:
-//   pack (host, pinned) -> H2D -> K1 profile -> K2 fill (per ring-size bin) -> K3 traceback -> D2H.
+// One context owns 1..8 devices.  A batch of independent block pairs is cut into WAVES (contiguous job
+// ranges, ~64 MB of input each).  Waves are handed out dynamically to the devices -- no collective: the
+// merge has no cross-pair dependency -- and every device pipelines its waves through a
+// ring of staging slots, each with its own stream, pinned buffers and device buffers:
+//
+//     host threads: analyse (band checks of mz_yama.c:58-71, wavefront schedule) + pack into pinned memory
+//     stream:       H2D -> K1 profile -> K2 fill (one launch per ring-size bin) -> K3 traceback -> D2H
+//     host threads: expand the 2-bit edit scripts into the caller's result array
+//
+// so that packing wave w+1 and unpacking wave w-1 overlap the copies and kernels of wave w.
 // There is no CPU implementation of the DP in this library.
 #include "../../include/yama_b200.h"
 #include "yama_kernels.cuh"
@@ -15,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -30,9 +38,9 @@ struct DevBuf {
         if (need <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = need + need / 8 + (1u << 20);
+        size_t want = need + need / 4 + (1u << 20);
         cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, need); want = need; }
+        if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(&p, need); want = need; }
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -45,7 +53,7 @@ struct PinBuf {
         if (need <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        size_t want = need + need / 8 + (1u << 20);
+        size_t want = need + need / 4 + (1u << 20);
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -55,38 +63,46 @@ struct PinBuf {
 
 constexpr int NBINS = 4;
 const int kRingOf[NBINS] = {128, 512, 2048, 4096};
+constexpr int NSLOTS = 3;
 
 struct JobInfo {           // host-side facts about one pair
     int64_t cells = 0;     // tback_size of the reference
-    int64_t tbBytes = 0;   // traceback bytes (window-major layout: 32 B per wavefront step)
-    int nSteps = 0;        // wavefront steps (schedule below)
+    int nSteps = 0;        // wavefront steps (schedule below); traceback bytes = 32 * nSteps
     int wmax = 0;          // widest band row
     int status = YB_OK;
 };
 
-struct Wave {              // everything needed to (re)launch the kernels of one wave
-    int64_t first = 0, count = 0;          // job range [first, first+count)
-    size_t blobBytes = 0, metaBytes = 0;
-    size_t rowRecs = 0, colRecs = 0, tbBytes = 0, scriptBytes = 0;
-    std::vector<int> order;                // pair indices (within wave) grouped by bin, big first
+struct Need { size_t blob, rows, cols, tb, scriptWords, sched; };
+
+// One staging slot = one wave in flight.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    DevBuf dIn, dRow, dCol, dTb, dScript, dOut, dQueue;
+    PinBuf hIn, hScript, hOut;
+    bool busy = false;
+    // the wave it holds
+    int64_t first = 0, count = 0;
+    std::vector<JobInfo> info;
+    std::vector<uint32_t> scriptOff;       // per pair, word offset in the wave's script pool
+    std::vector<int> schedTmp;             // schedules of the wave's pairs, back to back
+    std::vector<size_t> schedOff;
+    size_t blobBytes = 0, metaBytes = 0, orderOff = 0, scriptWords = 0;
+    int nValid = 0;
     int binStart[NBINS + 1] = {0, 0, 0, 0, 0};
-    std::vector<uint64_t> scriptOff;       // per pair, offset in the wave's script pool
 };
 
 struct Device {
     int id = -1;
     int sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
-    DevBuf dIn, dRow, dCol, dTb, dScript, dOut, dOrder, dQueue;
-    PinBuf hIn, hScript, hOut;
+    Slot slots[NSLOTS];
     int fillBlocks[NBINS] = {0, 0, 0, 0};
+    int helpers = 1;
     // accumulated stats of the current call
-    double kernel_ms = 0, fill_ms = 0, profile_ms = 0, tb_ms = 0, h2d_ms = 0, d2h_ms = 0, pack_ms = 0;
-    int64_t h2d_bytes = 0, d2h_bytes = 0;
-    int launches = 0;
+    double kernel_ms = 0, fill_ms = 0, profile_ms = 0, tb_ms = 0, h2d_ms = 0, d2h_ms = 0, pack_ms = 0, unpack_ms = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0, cells = 0;
+    int launches = 0, waves = 0;
     std::string err;
-    Wave resident;         // resident mode: the loaded wave
     bool hasResident = false;
 };
 
@@ -98,10 +114,13 @@ struct yb_ctx {
     bool scoresSet = false;
     ScoreConst sc{};
     int maxDepth = 255;
-    size_t waveBytes = (size_t)24 << 30;    // device working-set budget per wave
-    size_t stageBytes = (size_t)1 << 30;    // pinned input budget per wave
+    int nThreads = 1;
+    size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave
+    size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
+    int64_t wavePairs = 1 << 20;
     // results of the last batch
-    std::vector<uint8_t> scriptStore;
+    std::unique_ptr<uint8_t[]> scriptStore;
+    size_t scriptStoreCap = 0;
     std::vector<uint64_t> scriptOff;
     // record/replay queue
     std::vector<uint8_t> arena;
@@ -110,8 +129,8 @@ struct yb_ctx {
     std::vector<yb_result> queuedRes;
     // resident mode
     std::vector<yb_job> resJobs;
-    std::vector<JobInfo> resInfo;
     std::vector<int64_t> resSplit;          // device d owns jobs [resSplit[d], resSplit[d+1])
+    int64_t resCells = 0;
 };
 
 namespace {
@@ -143,6 +162,29 @@ double now_ms() {
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// fn(lo, hi) over [0,n) in dynamic chunks on `threads` host threads (the caller is one of them)
+template <class F>
+void parallel_for(int threads, int64_t n, int64_t chunk, F &&fn) {
+    if (n <= 0) return;
+    if (chunk < 1) chunk = 1;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    threads = (int)std::min<int64_t>(threads, nchunks);
+    if (threads <= 1) { fn((int64_t)0, n); return; }
+    std::atomic<int64_t> next{0};
+    auto body = [&] {
+        for (;;) {
+            int64_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            fn(c * chunk, std::min(n, (c + 1) * chunk));
+        }
+    };
+    std::vector<std::thread> th;
+    th.reserve((size_t)threads - 1);
+    for (int t = 1; t < threads; ++t) th.emplace_back(body);
+    body();
+    for (auto &t : th) t.join();
+}
 
 int bin_of(int wmax) {
     for (int b = 0; b < NBINS; ++b)
@@ -185,13 +227,15 @@ FillFn fill_fn(int bin) {
     }
 }
 
-int device_init(yb_ctx *ctx, Device &d) {
+int device_init(Device &d) {
     CUDA_TRY(d, cudaSetDevice(d.id));
     cudaDeviceProp prop;
     CUDA_TRY(d, cudaGetDeviceProperties(&prop, d.id));
     d.sms = prop.multiProcessorCount;
-    CUDA_TRY(d, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-    for (auto &e : d.ev) CUDA_TRY(d, cudaEventCreate(&e));
+    for (auto &s : d.slots) {
+        CUDA_TRY(d, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        for (auto &e : s.ev) CUDA_TRY(d, cudaEventCreate(&e));
+    }
     for (int b = 0; b < NBINS; ++b) {
         FillFn fn = fill_fn(b);
         size_t sm = fill_smem(b);
@@ -201,18 +245,17 @@ int device_init(yb_ctx *ctx, Device &d) {
         if (occ < 1) occ = 1;
         d.fillBlocks[b] = occ * d.sms;
     }
-    (void)ctx;
     return YB_OK;
 }
 
-// Host-side per-job facts; mirrors the validation loop of mz_yama.c:58-71.
-int64_t check_band(int M, int N, const int *LB, const int *RB, char *msg, int msglen, int64_t *tbBytes, int *wmax) {
+// Validation loop of mz_yama.c:58-71 in the reference's wording; returns the cell count (tback_size).
+int64_t check_band(int M, int N, const int *LB, const int *RB, char *msg, int msglen, int *wmax) {
     if (LB[0] != 0 || RB[M] != N) {
         if (msg) snprintf(msg, msglen, "LB and RB not terminated properly: %d %d %d", LB[0], RB[M], N);
         return YB_ERR_BAND;
     }
     const int need = N < 10 ? N : 10;
-    int64_t cells = 0, tb = 0;
+    int64_t cells = 0;
     int wm = 0;
     for (int r = 0; r <= M; ++r) {
         int j = RB[r] - LB[r];
@@ -225,7 +268,6 @@ int64_t check_band(int M, int N, const int *LB, const int *RB, char *msg, int ms
         if (r > 0 && LB[r] < LB[r - 1]) { if (msg) snprintf(msg, msglen, "LB not monotonic"); return YB_ERR_BAND; }
         if (r > 0 && RB[r] < RB[r - 1]) { if (msg) snprintf(msg, msglen, "RB not monotonic"); return YB_ERR_BAND; }
     }
-    (void)tb;
     if (wmax) *wmax = wm;
     return cells;
 }
@@ -252,217 +294,282 @@ int make_schedule(int M, const int *LB, const int *RB, int *sched) {
     return 4;
 }
 
-int analyse_jobs(yb_ctx *ctx, int64_t n, const yb_job *jobs, std::vector<JobInfo> &info) {
-    info.resize((size_t)n);
-    int rc = YB_OK;
-    for (int64_t i = 0; i < n; ++i) {
-        const yb_job &j = jobs[i];
-        JobInfo &ji = info[(size_t)i];
-        char msg[256];
-        if (j.K < 1 || j.L < 1 || j.M < 1 || j.N < 1 || !j.A || !j.B || !j.LB || !j.RB) {
-            ji.status = YB_ERR_ARG;
-            if (rc == YB_OK) { set_err(ctx, "job %lld: bad dimensions K=%d M=%d L=%d N=%d", (long long)i, j.K, j.M, j.L, j.N); rc = YB_ERR_ARG; }
-            continue;
-        }
-        int64_t cells = check_band(j.M, j.N, j.LB, j.RB, msg, sizeof msg, &ji.tbBytes, &ji.wmax);
-        if (cells < 0) {
-            ji.status = YB_ERR_BAND;
-            if (rc == YB_OK) { ctx->err = msg; rc = YB_ERR_BAND; }
-            continue;
-        }
-        ji.cells = cells;
-        ji.nSteps = make_schedule(j.M, j.LB, j.RB, nullptr);
-        ji.tbBytes = (int64_t)ji.nSteps * 32;
-        if (j.K > ctx->maxDepth || j.L > 255) {
-            ji.status = YB_ERR_LIMIT;
-            if (rc == YB_OK) { set_err(ctx, "job %lld: profile depth K=%d L=%d exceeds the kernel limit (%d/255 rows)", (long long)i, j.K, j.L, ctx->maxDepth); rc = YB_ERR_LIMIT; }
-            continue;
-        }
-        if (bin_of(ji.wmax) < 0) {
-            ji.status = YB_ERR_LIMIT;
-            if (rc == YB_OK) { set_err(ctx, "job %lld: band row of %d cells exceeds the kernel limit (%d)", (long long)i, ji.wmax, kRingOf[NBINS - 1] - 32); rc = YB_ERR_LIMIT; }
-            continue;
-        }
+// Everything the host needs to know about one job; msg (optional) gets the reference's wording.
+void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, char *msg, int msglen) {
+    ji = JobInfo();
+    if (j.K < 1 || j.L < 1 || j.M < 1 || j.N < 1 || !j.A || !j.B || !j.LB || !j.RB) {
+        ji.status = YB_ERR_ARG;
+        if (msg) snprintf(msg, msglen, "bad dimensions K=%d M=%d L=%d N=%d", j.K, j.M, j.L, j.N);
+        return;
     }
-    return rc;
+    int64_t cells = check_band(j.M, j.N, j.LB, j.RB, msg, msglen, &ji.wmax);
+    if (cells < 0) { ji.status = YB_ERR_BAND; return; }
+    ji.cells = cells;
+    if (j.K > ctx->maxDepth || j.L > 255) {
+        ji.status = YB_ERR_LIMIT;
+        if (msg) snprintf(msg, msglen, "profile depth K=%d L=%d exceeds the kernel limit (%d/255 rows)", j.K, j.L, ctx->maxDepth);
+        return;
+    }
+    if (bin_of(ji.wmax) < 0) {
+        ji.status = YB_ERR_LIMIT;
+        if (msg) snprintf(msg, msglen, "band row of %d cells exceeds the kernel limit (%d)", ji.wmax, kRingOf[NBINS - 1] - 32);
+        return;
+    }
+    ji.nSteps = make_schedule(j.M, j.LB, j.RB, sched);
 }
 
-struct Need { size_t blob, rows, cols, tb, script; };
+inline int band_fmt(const yb_job &j) { return j.N < 65536 ? 0 : 1; }
+inline size_t sched_ints(const yb_job &j) { return (size_t)((j.M + 31) >> 5); }
+
+// bytes a job takes in the input blob: known from its dimensions alone (wave planning needs no band read)
+inline size_t blob_bytes(const yb_job &j) {
+    return align_up((size_t)j.K * j.M, 16) + align_up((size_t)j.L * j.N, 16) +
+           align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 16) + align_up(sched_ints(j) * 4, 16);
+}
 inline Need need_of(const yb_job &j, const JobInfo &ji) {
     Need n;
-    n.blob = align_up((size_t)j.K * j.M, 16) + align_up((size_t)j.L * j.N, 16) + 2 * align_up((size_t)(j.M + 1) * 4, 16) +
-             align_up((size_t)((j.M + 31) >> 5) * 4, 16);
+    n.blob = blob_bytes(j);
     n.rows = (size_t)j.M + 1;
     n.cols = (size_t)j.N + 1;
-    n.tb = align_up((size_t)ji.tbBytes, 16);
-    n.script = align_up((size_t)j.M + j.N, 4);
+    n.tb = align_up((size_t)ji.nSteps * 32, 128);
+    n.scriptWords = ((size_t)j.M + j.N + 15) / 16;
+    n.sched = sched_ints(j);
     return n;
 }
 
-// Pack jobs [first,first+count) into the device's pinned buffer and upload.  Fills `w`.
-int wave_upload(yb_ctx *ctx, Device &d, const yb_job *jobs, const std::vector<JobInfo> &info, int64_t first,
-                int64_t count, Wave &w) {
-    double t0 = now_ms();
-    w.first = first; w.count = count;
-    w.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
-    size_t blob = w.metaBytes, rows = 0, cols = 0, tb = 0, script = 0;
-    int nvalid = 0;
-    for (int64_t i = 0; i < count; ++i) {
-        const JobInfo &ji = info[(size_t)(first + i)];
-        if (ji.status != YB_OK) continue;
-        Need n = need_of(jobs[first + i], ji);
-        blob += n.blob; rows += n.rows; cols += n.cols; tb += n.tb; script += n.script;
-        ++nvalid;
-    }
-    w.blobBytes = blob; w.rowRecs = rows; w.colRecs = cols; w.tbBytes = tb; w.scriptBytes = script;
-    CUDA_TRY(d, d.hIn.reserve(blob));
-    CUDA_TRY(d, d.dIn.reserve(blob));
-    CUDA_TRY(d, d.dRow.reserve(rows * sizeof(RowRec) + 64));
-    CUDA_TRY(d, d.dCol.reserve(cols * sizeof(ColRec) + 64));
-    CUDA_TRY(d, d.dTb.reserve(tb + 64));
-    CUDA_TRY(d, d.dScript.reserve(script + 64));
-    CUDA_TRY(d, d.dOut.reserve((size_t)count * sizeof(PairOut) + 64));
-    CUDA_TRY(d, d.dOrder.reserve((size_t)count * 4 + 64));
-    CUDA_TRY(d, d.dQueue.reserve(64));
-    CUDA_TRY(d, d.hScript.reserve(script + 64));
-    CUDA_TRY(d, d.hOut.reserve((size_t)count * sizeof(PairOut) + 64));
-
-    unsigned char *h = static_cast<unsigned char *>(d.hIn.p);
-    PairMeta *metas = reinterpret_cast<PairMeta *>(h);
-    size_t off = w.metaBytes;
-    size_t rowBase = 0, colBase = 0, tbBase = 0, scriptBase = 0;
-    w.scriptOff.assign((size_t)count, 0);
-    std::vector<std::pair<int64_t, int>> binned[NBINS];
+// Analyse + pack jobs [first, first+count) into the slot's pinned buffer.  `maxTb` caps the wave's
+// traceback bytes: the wave is cut short (count shrinks, at least one job stays) when it would not fit.
+int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t &count, size_t maxTb) {
+    const double t0 = now_ms();
+    const int T = d.helpers;
+    // ---- analysis (parallel): band validation, cells, schedule -----------------------------------------
+    s.info.assign((size_t)count, JobInfo());
+    s.schedOff.assign((size_t)count + 1, 0);
     for (int64_t i = 0; i < count; ++i) {
         const yb_job &j = jobs[first + i];
-        const JobInfo &ji = info[(size_t)(first + i)];
-        PairMeta pm;
-        memset(&pm, 0, sizeof pm);
-        if (ji.status != YB_OK) { metas[i] = pm; continue; }
-        pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
-        pm.offA = off; memcpy(h + off, j.A, (size_t)j.K * j.M); off += align_up((size_t)j.K * j.M, 16);
-        pm.offB = off; memcpy(h + off, j.B, (size_t)j.L * j.N); off += align_up((size_t)j.L * j.N, 16);
-        pm.offLB = off; memcpy(h + off, j.LB, (size_t)(j.M + 1) * 4); off += align_up((size_t)(j.M + 1) * 4, 16);
-        pm.offRB = off; memcpy(h + off, j.RB, (size_t)(j.M + 1) * 4); off += align_up((size_t)(j.M + 1) * 4, 16);
-        pm.offSched = off; pm.nSteps = make_schedule(j.M, j.LB, j.RB, reinterpret_cast<int *>(h + off));
-        off += align_up((size_t)((j.M + 31) >> 5) * 4, 16);
-        Need n = need_of(j, ji);
-        pm.rowBase = rowBase; rowBase += n.rows;
-        pm.colBase = colBase; colBase += n.cols;
-        pm.tbBase = tbBase; tbBase += n.tb;
-        pm.scriptBase = scriptBase; w.scriptOff[(size_t)i] = scriptBase; scriptBase += n.script;
-        metas[i] = pm;
-        binned[bin_of(ji.wmax)].push_back({ji.cells, (int)i});
+        s.schedOff[(size_t)i + 1] = s.schedOff[(size_t)i] + (j.M >= 1 ? sched_ints(j) : 0);
     }
-    // launch order: per ring bin, largest pairs first (longest-processing-time-first on the warp queue)
-    w.order.clear();
+    s.schedTmp.resize(s.schedOff[(size_t)count] + 1);
+    std::mutex errMu;
+    parallel_for(T, count, 256, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            char msg[256];
+            msg[0] = 0;
+            analyse_one(ctx, jobs[first + i], s.info[(size_t)i], s.schedTmp.data() + s.schedOff[(size_t)i], msg, sizeof msg);
+            if (s.info[(size_t)i].status != YB_OK) {
+                std::lock_guard<std::mutex> g(errMu);
+                if (d.err.empty()) {
+                    char b[400];
+                    if (s.info[(size_t)i].status == YB_ERR_BAND) snprintf(b, sizeof b, "%s", msg);   // reference wording
+                    else snprintf(b, sizeof b, "job %lld: %s", (long long)(first + i), msg);
+                    d.err = b;
+                }
+            }
+        }
+    });
+    // ---- offsets (serial prefix sums); cut the wave where the traceback pool would overflow ---------------
+    struct Off { size_t blob, row, col, tb; uint32_t script; };
+    std::vector<Off> off((size_t)count);
+    size_t blob = 0, rows = 0, cols = 0, tb = 0, words = 0;
+    int64_t kept = count;
+    for (int64_t i = 0; i < count; ++i) {
+        const JobInfo &ji = s.info[(size_t)i];
+        off[(size_t)i] = Off{blob, rows, cols, tb, (uint32_t)words};
+        if (ji.status != YB_OK) continue;
+        Need n = need_of(jobs[first + i], ji);
+        if (i > 0 && tb + n.tb > maxTb) { kept = i; break; }
+        blob += n.blob; rows += n.rows; cols += n.cols; tb += n.tb; words += n.scriptWords;
+    }
+    count = kept;
+    s.first = first; s.count = count;
+    s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
+    s.orderOff = s.metaBytes;
+    const size_t dataOff = s.metaBytes + align_up((size_t)count * 4, 256);
+    s.blobBytes = dataOff + blob;
+    s.scriptWords = words;
+    CUDA_TRY(d, s.hIn.reserve(s.blobBytes));
+    CUDA_TRY(d, s.dIn.reserve(s.blobBytes));
+    CUDA_TRY(d, s.dRow.reserve(rows * sizeof(RowRec) + 64));
+    CUDA_TRY(d, s.dCol.reserve(cols * sizeof(ColRec) + 64));
+    CUDA_TRY(d, s.dTb.reserve(tb + 256));
+    CUDA_TRY(d, s.dScript.reserve(words * 4 + 64));
+    CUDA_TRY(d, s.dOut.reserve((size_t)count * sizeof(PairOut) + 64));
+    CUDA_TRY(d, s.dQueue.reserve(64));
+    CUDA_TRY(d, s.hScript.reserve(words * 4 + 64));
+    CUDA_TRY(d, s.hOut.reserve((size_t)count * sizeof(PairOut) + 64));
+
+    unsigned char *h = static_cast<unsigned char *>(s.hIn.p);
+    PairMeta *metas = reinterpret_cast<PairMeta *>(h);
+    s.scriptOff.resize((size_t)count);
+    // ---- pack (parallel) -----------------------------------------------------------------------------------
+    parallel_for(T, count, 64, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const yb_job &j = jobs[first + i];
+            const JobInfo &ji = s.info[(size_t)i];
+            PairMeta pm;
+            memset(&pm, 0, sizeof pm);
+            s.scriptOff[(size_t)i] = off[(size_t)i].script;
+            if (ji.status != YB_OK) { metas[i] = pm; continue; }
+            size_t o = dataOff + off[(size_t)i].blob;
+            pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
+            pm.offA = o; memcpy(h + o, j.A, (size_t)j.K * j.M); o += align_up((size_t)j.K * j.M, 16);
+            pm.offB = o; memcpy(h + o, j.B, (size_t)j.L * j.N); o += align_up((size_t)j.L * j.N, 16);
+            pm.offBand = o;
+            pm.bandFmt = band_fmt(j);
+            if (pm.bandFmt == 0) {
+                uint32_t *w = reinterpret_cast<uint32_t *>(h + o);
+                for (int r = 0; r <= j.M; ++r) w[r] = (uint32_t)j.LB[r] | ((uint32_t)j.RB[r] << 16);
+                o += align_up((size_t)(j.M + 1) * 4, 16);
+            } else {
+                memcpy(h + o, j.LB, (size_t)(j.M + 1) * 4);
+                memcpy(h + o + (size_t)(j.M + 1) * 4, j.RB, (size_t)(j.M + 1) * 4);
+                o += align_up((size_t)(j.M + 1) * 8, 16);
+            }
+            pm.offSched = o;
+            memcpy(h + o, s.schedTmp.data() + s.schedOff[(size_t)i], sched_ints(j) * 4);
+            pm.nSteps = ji.nSteps;
+            pm.rowBase = off[(size_t)i].row;
+            pm.colBase = off[(size_t)i].col;
+            pm.tbBase = off[(size_t)i].tb;
+            pm.scriptBase = off[(size_t)i].script;
+            metas[i] = pm;
+        }
+    });
+    // ---- launch order: per ring bin, largest pairs first (longest-processing-time-first on the warp queue)
+    std::vector<std::pair<int64_t, int>> binned[NBINS];
+    for (int64_t i = 0; i < count; ++i)
+        if (s.info[(size_t)i].status == YB_OK) binned[bin_of(s.info[(size_t)i].wmax)].push_back({s.info[(size_t)i].cells, (int)i});
+    int *order = reinterpret_cast<int *>(h + s.orderOff);
+    int k = 0;
     for (int b = 0; b < NBINS; ++b) {
-        w.binStart[b] = (int)w.order.size();
+        s.binStart[b] = k;
         std::sort(binned[b].begin(), binned[b].end(), [](const std::pair<int64_t, int> &x, const std::pair<int64_t, int> &y) {
             return x.first != y.first ? x.first > y.first : x.second < y.second;
         });
-        for (auto &pr : binned[b]) w.order.push_back(pr.second);
+        for (auto &pr : binned[b]) order[k++] = pr.second;
     }
-    w.binStart[NBINS] = (int)w.order.size();
+    s.binStart[NBINS] = k;
+    s.nValid = k;
     d.pack_ms += now_ms() - t0;
-
-    CUDA_TRY(d, cudaEventRecord(d.ev[0], d.stream));
-    CUDA_TRY(d, cudaMemcpyAsync(d.dIn.p, d.hIn.p, blob, cudaMemcpyHostToDevice, d.stream));
-    if (!w.order.empty())
-        CUDA_TRY(d, cudaMemcpyAsync(d.dOrder.p, w.order.data(), w.order.size() * 4, cudaMemcpyHostToDevice, d.stream));
-    CUDA_TRY(d, cudaEventRecord(d.ev[1], d.stream));
-    CUDA_TRY(d, cudaStreamSynchronize(d.stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]);
-    d.h2d_ms += ms;
-    d.h2d_bytes += (int64_t)(blob + w.order.size() * 4);
-    (void)ctx; (void)nvalid;
     return YB_OK;
 }
 
-// Launch K1,K2,K3 for an uploaded wave; device-timed.
-int wave_compute(Device &d, const Wave &w) {
-    if (w.order.empty()) return YB_OK;
-    const PairMeta *metas = static_cast<const PairMeta *>(d.dIn.p);
-    const unsigned char *blob = static_cast<const unsigned char *>(d.dIn.p);
-    RowRec *rows = static_cast<RowRec *>(d.dRow.p);
-    ColRec *cols = static_cast<ColRec *>(d.dCol.p);
-    unsigned char *tb = static_cast<unsigned char *>(d.dTb.p);
-    unsigned char *script = static_cast<unsigned char *>(d.dScript.p);
-    PairOut *outs = static_cast<PairOut *>(d.dOut.p);
-    int *order = static_cast<int *>(d.dOrder.p);
-    int *queue = static_cast<int *>(d.dQueue.p);
+// Enqueue one wave on its slot's stream.  Nothing here waits for the device.
+int slot_launch(Device &d, Slot &s, bool h2d, bool d2h) {
+    const PairMeta *metas = static_cast<const PairMeta *>(s.dIn.p);
+    const unsigned char *blob = static_cast<const unsigned char *>(s.dIn.p);
+    RowRec *rows = static_cast<RowRec *>(s.dRow.p);
+    ColRec *cols = static_cast<ColRec *>(s.dCol.p);
+    unsigned char *tb = static_cast<unsigned char *>(s.dTb.p);
+    unsigned *script = static_cast<unsigned *>(s.dScript.p);
+    PairOut *outs = static_cast<PairOut *>(s.dOut.p);
+    const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
+    int *queue = static_cast<int *>(s.dQueue.p);
+    cudaStream_t st = s.stream;
 
-    CUDA_TRY(d, cudaEventRecord(d.ev[2], d.stream));
-    CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)w.count * sizeof(PairOut), d.stream));
-    CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, d.stream));
-    yb_profile_kernel<<<(unsigned)w.count, K1_THREADS, 0, d.stream>>>(metas, blob, rows, cols);
-    d.launches++;
-    CUDA_TRY(d, cudaEventRecord(d.ev[3], d.stream));
+    CUDA_TRY(d, cudaEventRecord(s.ev[0], st));
+    if (h2d) CUDA_TRY(d, cudaMemcpyAsync(s.dIn.p, s.hIn.p, s.blobBytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(d, cudaEventRecord(s.ev[1], st));
+    CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)s.count * sizeof(PairOut), st));
+    CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, st));
+    if (s.nValid > 0) {
+        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols);
+        d.launches++;
+    }
+    CUDA_TRY(d, cudaEventRecord(s.ev[2], st));
     for (int b = 0; b < NBINS; ++b) {
-        int n = w.binStart[b + 1] - w.binStart[b];
+        int n = s.binStart[b + 1] - s.binStart[b];
         if (n <= 0) continue;
         int wpc = warps_of(b);
         int blocks = std::min((n + wpc - 1) / wpc, d.fillBlocks[b]);
-        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), d.stream>>>(metas, order + w.binStart[b], n, queue + b, rows, cols, tb, outs);
+        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), st>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb, outs);
         d.launches++;
     }
-    CUDA_TRY(d, cudaEventRecord(d.ev[4], d.stream));
-    {
-        const int nv = (int)w.order.size();
-        yb_traceback_kernel<<<(unsigned)((nv + 63) / 64), 64, 0, d.stream>>>(metas, order, nv, blob, tb, script, outs);
+    CUDA_TRY(d, cudaEventRecord(s.ev[3], st));
+    if (s.nValid > 0) {
+        yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(metas, order, s.nValid, blob, tb, script, outs);
+        d.launches++;
     }
-    d.launches++;
-    CUDA_TRY(d, cudaEventRecord(d.ev[5], d.stream));
-    CUDA_TRY(d, cudaStreamSynchronize(d.stream));
+    CUDA_TRY(d, cudaEventRecord(s.ev[4], st));
+    if (d2h) {
+        CUDA_TRY(d, cudaMemcpyAsync(s.hOut.p, s.dOut.p, (size_t)s.count * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
+        if (s.scriptWords)
+            CUDA_TRY(d, cudaMemcpyAsync(s.hScript.p, s.dScript.p, s.scriptWords * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(d, cudaEventRecord(s.ev[5], st));
     CUDA_TRY(d, cudaGetLastError());
-    float a = 0, b = 0, c = 0;
-    cudaEventElapsedTime(&a, d.ev[2], d.ev[3]);
-    cudaEventElapsedTime(&b, d.ev[3], d.ev[4]);
-    cudaEventElapsedTime(&c, d.ev[4], d.ev[5]);
-    d.profile_ms += a; d.fill_ms += b; d.tb_ms += c;
-    d.kernel_ms += a + b + c;
+    s.busy = true;
+    d.waves++;
+    if (h2d) d.h2d_bytes += (int64_t)s.blobBytes;
+    if (d2h) d.d2h_bytes += (int64_t)((size_t)s.count * sizeof(PairOut) + s.scriptWords * 4);
     return YB_OK;
 }
 
-// D2H of scores + scripts of a wave into results / the context's script store.
-int wave_download(yb_ctx *ctx, Device &d, const Wave &w, const yb_job *jobs, const std::vector<JobInfo> &info,
-                  yb_result *results) {
-    CUDA_TRY(d, cudaEventRecord(d.ev[6], d.stream));
-    CUDA_TRY(d, cudaMemcpyAsync(d.hOut.p, d.dOut.p, (size_t)w.count * sizeof(PairOut), cudaMemcpyDeviceToHost, d.stream));
-    if (w.scriptBytes)
-        CUDA_TRY(d, cudaMemcpyAsync(d.hScript.p, d.dScript.p, w.scriptBytes, cudaMemcpyDeviceToHost, d.stream));
-    CUDA_TRY(d, cudaEventRecord(d.ev[7], d.stream));
-    CUDA_TRY(d, cudaStreamSynchronize(d.stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, d.ev[6], d.ev[7]);
-    d.d2h_ms += ms;
-    d.d2h_bytes += (int64_t)((size_t)w.count * sizeof(PairOut) + w.scriptBytes);
-    const PairOut *outs = static_cast<const PairOut *>(d.hOut.p);
-    const unsigned char *hs = static_cast<const unsigned char *>(d.hScript.p);
-    for (int64_t i = 0; i < w.count; ++i) {
-        int64_t g = w.first + i;
-        yb_result &r = results[g];
-        const JobInfo &ji = info[(size_t)g];
-        memset(&r, 0, sizeof r);
-        r.status = ji.status;
-        r.cells = ji.cells;
-        if (ji.status != YB_OK) continue;
-        const PairOut &o = outs[i];
-        r.status = o.status;
-        r.m_new = o.m_new; r.C = o.C; r.D = o.D; r.I = o.I;
-        uint8_t *dst = ctx->scriptStore.data() + ctx->scriptOff[(size_t)g];
-        memcpy(dst, hs + w.scriptOff[(size_t)i], (size_t)o.m_new);
-        r.script = dst;
-        (void)jobs;
-    }
+int slot_d2h(Device &d, Slot &s) {
+    CUDA_TRY(d, cudaMemcpyAsync(s.hOut.p, s.dOut.p, (size_t)s.count * sizeof(PairOut), cudaMemcpyDeviceToHost, s.stream));
+    if (s.scriptWords)
+        CUDA_TRY(d, cudaMemcpyAsync(s.hScript.p, s.dScript.p, s.scriptWords * 4, cudaMemcpyDeviceToHost, s.stream));
+    d.d2h_bytes += (int64_t)((size_t)s.count * sizeof(PairOut) + s.scriptWords * 4);
     return YB_OK;
+}
+
+// Wait for the slot's wave and add its device times to the statistics.
+int slot_wait(Device &d, Slot &s) {
+    CUDA_TRY(d, cudaStreamSynchronize(s.stream));
+    CUDA_TRY(d, cudaGetLastError());
+    float h = 0, a = 0, b = 0, c = 0, e = 0;
+    cudaEventElapsedTime(&h, s.ev[0], s.ev[1]);
+    cudaEventElapsedTime(&a, s.ev[1], s.ev[2]);
+    cudaEventElapsedTime(&b, s.ev[2], s.ev[3]);
+    cudaEventElapsedTime(&c, s.ev[3], s.ev[4]);
+    cudaEventElapsedTime(&e, s.ev[4], s.ev[5]);
+    d.h2d_ms += h; d.profile_ms += a; d.fill_ms += b; d.tb_ms += c; d.d2h_ms += e;
+    d.kernel_ms += a + b + c;
+    s.busy = false;
+    return YB_OK;
+}
+
+// Scores + edit scripts of a finished wave -> results / the context's script store.
+void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
+    const double t0 = now_ms();
+    const PairOut *outs = static_cast<const PairOut *>(s.hOut.p);
+    const uint32_t *hs = static_cast<const uint32_t *>(s.hScript.p);
+    parallel_for(d.helpers, s.count, 128, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const int64_t g = s.first + i;
+            yb_result &r = results[g];
+            const JobInfo &ji = s.info[(size_t)i];
+            memset(&r, 0, sizeof r);
+            r.status = ji.status;
+            r.cells = ji.cells;
+            if (ji.status != YB_OK) continue;
+            const PairOut &o = outs[i];
+            r.status = o.status;
+            r.m_new = o.m_new; r.C = o.C; r.D = o.D; r.I = o.I;
+            uint8_t *dst = ctx->scriptStore.get() + ctx->scriptOff[(size_t)g];
+            const uint32_t *src = hs + s.scriptOff[(size_t)i];
+            const int n = o.m_new;
+            int k = 0;
+            for (; k + 16 <= n; k += 16) {
+                uint32_t w = src[k >> 4];
+                for (int q = 0; q < 16; ++q) dst[k + q] = (uint8_t)((w >> (2 * q)) & 3u);
+            }
+            if (k < n) {
+                uint32_t w = src[k >> 4];
+                for (int q = 0; k + q < n; ++q) dst[k + q] = (uint8_t)((w >> (2 * q)) & 3u);
+            }
+            r.script = dst;
+        }
+    });
+    for (int64_t i = 0; i < s.count; ++i)
+        if (s.info[(size_t)i].status == YB_OK) d.cells += s.info[(size_t)i].cells;
+    d.unpack_ms += now_ms() - t0;
 }
 
 void reset_stats(Device &d) {
-    d.kernel_ms = d.fill_ms = d.profile_ms = d.tb_ms = d.h2d_ms = d.d2h_ms = d.pack_ms = 0;
-    d.h2d_bytes = d.d2h_bytes = 0;
-    d.launches = 0;
+    d.kernel_ms = d.fill_ms = d.profile_ms = d.tb_ms = d.h2d_ms = d.d2h_ms = d.pack_ms = d.unpack_ms = 0;
+    d.h2d_bytes = d.d2h_bytes = d.cells = 0;
+    d.launches = d.waves = 0;
     d.err.clear();
 }
 
@@ -473,7 +580,7 @@ void collect_stats(yb_ctx *ctx, yb_stats *st, double total_ms, int64_t cells, in
         st->kernel_ms = std::max(st->kernel_ms, d.kernel_ms);
         st->h2d_ms = std::max(st->h2d_ms, d.h2d_ms);
         st->d2h_ms = std::max(st->d2h_ms, d.d2h_ms);
-        st->pack_ms = std::max(st->pack_ms, d.pack_ms);
+        st->pack_ms = std::max(st->pack_ms, d.pack_ms + d.unpack_ms);
         st->h2d_bytes += d.h2d_bytes;
         st->d2h_bytes += d.d2h_bytes;
         st->kernel_launches += d.launches;
@@ -508,52 +615,72 @@ void plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cut) {
     for (int k = 1; k <= nparts; ++k) cut[k] = std::max(cut[k], cut[k - 1]);
     cut[nparts] = n;
 }
-std::vector<int64_t> split_jobs(const std::vector<JobInfo> &info, int ndev) {
-    std::vector<int64_t> cells(info.size()), cut((size_t)ndev + 1);
-    for (size_t i = 0; i < info.size(); ++i) cells[i] = info[i].cells;
-    plan_split((int64_t)info.size(), cells.data(), ndev, cut.data());
-    return cut;
-}
 
-int run_range(yb_ctx *ctx, Device &d, const yb_job *jobs, const std::vector<JobInfo> &info, int64_t lo, int64_t hi,
-              yb_result *results) {
-    if (cudaSetDevice(d.id) != cudaSuccess) { d.err = "cudaSetDevice failed"; return YB_ERR_CUDA; }
-    int64_t i = lo;
-    while (i < hi) {
-        // grow the wave until a budget is hit
-        size_t blob = 0, dev = 0;
-        int64_t j = i;
-        while (j < hi) {
-            const JobInfo &ji = info[(size_t)j];
-            size_t b = sizeof(PairMeta), dv = sizeof(PairOut) + 4;
-            if (ji.status == YB_OK) {
-                Need n = need_of(jobs[j], ji);
-                b += n.blob;
-                dv += n.blob + n.rows * sizeof(RowRec) + n.cols * sizeof(ColRec) + n.tb + n.script;
-            }
-            if (j > i && (blob + b > ctx->stageBytes || dev + dv > ctx->waveBytes || j - i >= (1 << 24))) break;
-            blob += b; dev += dv; ++j;
+// Hands out waves: contiguous job ranges whose input fits one staging slot (sizes known from dimensions).
+struct Dispatcher {
+    const yb_job *jobs = nullptr;
+    int64_t n = 0, cursor = 0;
+    size_t maxBytes = 0;
+    int64_t maxPairs = 0;
+    std::mutex mu;
+    bool grab(int64_t &lo, int64_t &hi) {
+        std::lock_guard<std::mutex> g(mu);
+        if (cursor >= n) return false;
+        lo = cursor;
+        size_t bytes = 0;
+        int64_t i = lo;
+        while (i < n && i - lo < maxPairs) {
+            const yb_job &j = jobs[i];
+            size_t b = sizeof(PairMeta) + 4;
+            if (j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1) b += blob_bytes(j);
+            if (i > lo && bytes + b > maxBytes) break;
+            bytes += b;
+            ++i;
         }
-        Wave w;
-        int rc = wave_upload(ctx, d, jobs, info, i, j - i, w);
-        if (rc != YB_OK) return rc;
-        rc = wave_compute(d, w);
-        if (rc != YB_OK) return rc;
-        rc = wave_download(ctx, d, w, jobs, info, results);
-        if (rc != YB_OK) return rc;
-        i = j;
+        hi = cursor = i;
+        return true;
     }
-    return YB_OK;
+};
+
+// One device's share of a batch: grab waves until none are left, keeping up to NSLOTS in flight.
+int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
+    if (cudaSetDevice(d.id) != cudaSuccess) { d.err = "cudaSetDevice failed"; return YB_ERR_CUDA; }
+    int rc = YB_OK, next = 0;
+    int64_t lo = 0, hi = 0;                      // jobs grabbed but not yet packed
+    for (;;) {
+        if (lo >= hi && !disp.grab(lo, hi)) break;
+        Slot &s = d.slots[next];
+        next = (next + 1) % NSLOTS;
+        if (s.busy) {                            // the wave launched NSLOTS rounds ago
+            if ((rc = slot_wait(d, s)) != YB_OK) break;
+            slot_unpack(ctx, d, s, results);
+        }
+        int64_t count = hi - lo;
+        if ((rc = slot_pack(ctx, d, s, disp.jobs, lo, count, ctx->waveTbBytes)) != YB_OK) break;
+        lo += count;
+        if ((rc = slot_launch(d, s, true, true)) != YB_OK) break;
+    }
+    for (int k = 0; k < NSLOTS; ++k) {           // drain, oldest first
+        Slot &s = d.slots[(next + k) % NSLOTS];
+        if (!s.busy) continue;
+        int r2 = slot_wait(d, s);
+        if (r2 != YB_OK) { if (rc == YB_OK) rc = r2; continue; }
+        if (rc == YB_OK) slot_unpack(ctx, d, s, results);
+    }
+    return rc;
 }
 
-void prepare_script_store(yb_ctx *ctx, int64_t n, const yb_job *jobs, const std::vector<JobInfo> &info) {
+void prepare_script_store(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
     ctx->scriptOff.assign((size_t)n, 0);
     size_t tot = 0;
     for (int64_t i = 0; i < n; ++i) {
         ctx->scriptOff[(size_t)i] = tot;
-        if (info[(size_t)i].status == YB_OK) tot += (size_t)jobs[i].M + jobs[i].N;
+        if (jobs[i].M >= 1 && jobs[i].N >= 1) tot += (size_t)jobs[i].M + jobs[i].N;
     }
-    ctx->scriptStore.resize(tot + 16);
+    if (tot + 16 > ctx->scriptStoreCap) {
+        ctx->scriptStore.reset(new uint8_t[tot + tot / 8 + 16]);
+        ctx->scriptStoreCap = tot + tot / 8 + 16;
+    }
 }
 
 template <class F>
@@ -592,14 +719,19 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     else for (int i = 0; i < avail; ++i) ids.push_back(i);
     for (int id : ids) {
         if (id < 0 || id >= avail) { delete ctx; return YB_ERR_ARG; }
-        Device d;
-        d.id = id;
-        ctx->devs.push_back(d);
+        ctx->devs.emplace_back();
+        ctx->devs.back().id = id;
     }
     for (auto &d : ctx->devs)
-        if (device_init(ctx, d) != YB_OK) { fprintf(stderr, "yama_b200: %s\n", d.err.c_str()); yb_destroy(ctx); return YB_ERR_CUDA; }
-    if (const char *e = getenv("YB_WAVE_BYTES")) ctx->waveBytes = (size_t)strtoull(e, nullptr, 10);
-    if (const char *e = getenv("YB_STAGE_BYTES")) ctx->stageBytes = (size_t)strtoull(e, nullptr, 10);
+        if (device_init(d) != YB_OK) { fprintf(stderr, "yama_b200: %s\n", d.err.c_str()); yb_destroy(ctx); return YB_ERR_CUDA; }
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    ctx->nThreads = std::min(hw, 32);
+    if (const char *e = getenv("YB_THREADS")) ctx->nThreads = std::max(1, atoi(e));
+    if (const char *e = getenv("YB_WAVE_MB")) ctx->waveInBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
+    if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
+    if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
+    for (auto &d : ctx->devs) d.helpers = std::max(1, ctx->nThreads / (int)ctx->devs.size());
     *out = ctx;
     return YB_OK;
 }
@@ -608,10 +740,12 @@ void yb_destroy(yb_ctx *ctx) {
     if (!ctx) return;
     for (auto &d : ctx->devs) {
         cudaSetDevice(d.id);
-        for (DevBuf *b : {&d.dIn, &d.dRow, &d.dCol, &d.dTb, &d.dScript, &d.dOut, &d.dOrder, &d.dQueue}) b->release();
-        for (PinBuf *b : {&d.hIn, &d.hScript, &d.hOut}) b->release();
-        for (auto &e : d.ev) if (e) cudaEventDestroy(e);
-        if (d.stream) cudaStreamDestroy(d.stream);
+        for (auto &s : d.slots) {
+            for (DevBuf *b : {&s.dIn, &s.dRow, &s.dCol, &s.dTb, &s.dScript, &s.dOut, &s.dQueue}) b->release();
+            for (PinBuf *b : {&s.hIn, &s.hScript, &s.hOut}) b->release();
+            for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
     }
     delete ctx;
 }
@@ -653,10 +787,12 @@ int yb_set_scores(yb_ctx *ctx, const int32_t *ss, const int32_t *gop, int32_t ga
         }
     }
     if (GO < 0 || GO > 32767) { set_err(ctx, "gap_open %d outside [0,32767]", GO); return YB_ERR_SCORES; }
+    if (gap_extend < 0 || gap_extend > 32767) { set_err(ctx, "gap_extend %d outside [0,32767]", gap_extend); return YB_ERR_SCORES; }
     sc.gap_open = GO;
     sc.gap_ext = gap_extend;
     ctx->sc = sc;
-    ctx->maxDepth = std::min(255, 32767 / maxabs);
+    // 16-bit weights in the kernels: sum-of-pairs weights K*max|S6| and the extension weight K*gap_extend
+    ctx->maxDepth = std::min(255, 32767 / std::max(maxabs, std::max(1, (int)gap_extend)));
     for (auto &d : ctx->devs) {
         if (cudaSetDevice(d.id) != cudaSuccess || cudaMemcpyToSymbol(c_sc, &sc, sizeof sc) != cudaSuccess) {
             set_err(ctx, "cudaMemcpyToSymbol failed on device %d", d.id);
@@ -674,29 +810,32 @@ int yb_plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cuts) {
 }
 
 int64_t yb_check_band(int32_t M, int32_t N, const int32_t *LB, const int32_t *RB, char *msg, int msglen) {
-    return check_band(M, N, LB, RB, msg, msglen, nullptr, nullptr);
+    if (M < 0 || N < 0 || !LB || !RB) return YB_ERR_ARG;
+    return check_band(M, N, LB, RB, msg, msglen, nullptr);
 }
 
 int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results, yb_stats *stats) {
     if (!ctx || n < 0 || (n > 0 && (!jobs || !results))) return YB_ERR_ARG;
     if (!ctx->scoresSet) { set_err(ctx, "yb_set_scores has not been called"); return YB_ERR_SCORES; }
-    double t0 = now_ms();
-    std::vector<JobInfo> info;
-    int arc = analyse_jobs(ctx, n, jobs, info);
-    prepare_script_store(ctx, n, jobs, info);
-    for (auto &d : ctx->devs) reset_stats(d);
-    int ndev = (int)ctx->devs.size();
-    std::vector<int64_t> cut = split_jobs(info, ndev);
-    int rc = for_each_device(ctx, [&](int d) {
-        return run_range(ctx, ctx->devs[(size_t)d], jobs, info, cut[(size_t)d], cut[(size_t)d + 1], results);
-    });
+    const double t0 = now_ms();
+    prepare_script_store(ctx, n, jobs);
+    for (auto &d : ctx->devs) { reset_stats(d); d.hasResident = false; }
+    Dispatcher disp;
+    disp.jobs = jobs; disp.n = n;
+    disp.maxBytes = ctx->waveInBytes; disp.maxPairs = ctx->wavePairs;
+    int rc = for_each_device(ctx, [&](int d) { return device_run(ctx, ctx->devs[(size_t)d], disp, results); });
     int64_t cells = 0;
-    for (auto &ji : info) if (ji.status == YB_OK) cells += ji.cells;
+    for (auto &d : ctx->devs) cells += d.cells;
     collect_stats(ctx, stats, now_ms() - t0, cells, n);
     if (rc != YB_OK) return rc;
-    if (arc != YB_OK) return arc;
+    // per-pair failures: report the first in job order, in the reference's wording where it has one
     for (int64_t i = 0; i < n; ++i)
-        if (results[i].status != YB_OK) { set_err(ctx, "Error generating edit script."); return results[i].status; }
+        if (results[i].status != YB_OK) {
+            bool have = false;
+            for (auto &d : ctx->devs) if (!d.err.empty()) { ctx->err = d.err; have = true; break; }
+            if (!have || results[i].status == YB_ERR_TRACEBACK) set_err(ctx, "Error generating edit script.");
+            return results[i].status;
+        }
     return YB_OK;
 }
 
@@ -704,19 +843,39 @@ int yb_resident_load(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
     if (!ctx || n < 1 || !jobs) return YB_ERR_ARG;
     if (!ctx->scoresSet) { set_err(ctx, "yb_set_scores has not been called"); return YB_ERR_SCORES; }
     ctx->resJobs.assign(jobs, jobs + n);
-    int arc = analyse_jobs(ctx, n, jobs, ctx->resInfo);
-    if (arc != YB_OK) return arc;
-    prepare_script_store(ctx, n, jobs, ctx->resInfo);
-    for (auto &d : ctx->devs) reset_stats(d);
-    ctx->resSplit = split_jobs(ctx->resInfo, (int)ctx->devs.size());
-    return for_each_device(ctx, [&](int di) {
+    prepare_script_store(ctx, n, jobs);
+    for (auto &d : ctx->devs) { reset_stats(d); d.hasResident = false; }
+    // static, cell-balanced split: needs every pair's cell count first
+    std::vector<int64_t> cells((size_t)n, 0);
+    std::atomic<int> bad{0};
+    parallel_for(ctx->nThreads, n, 256, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            JobInfo ji;
+            analyse_one(ctx, jobs[i], ji, nullptr, nullptr, 0);
+            cells[(size_t)i] = ji.cells;
+            if (ji.status != YB_OK) bad.store(1);
+        }
+    });
+    if (bad.load()) { set_err(ctx, "yb_resident_load: the batch holds invalid pairs (use yb_run_batch for per-pair status)"); return YB_ERR_ARG; }
+    ctx->resCells = 0;
+    for (auto c : cells) ctx->resCells += c;
+    const int ndev = (int)ctx->devs.size();
+    ctx->resSplit.assign((size_t)ndev + 1, 0);
+    plan_split(n, cells.data(), ndev, ctx->resSplit.data());
+    return for_each_device(ctx, [&](int di) -> int {
         Device &d = ctx->devs[(size_t)di];
         if (cudaSetDevice(d.id) != cudaSuccess) return (int)YB_ERR_CUDA;
-        d.hasResident = false;
-        int64_t lo = ctx->resSplit[(size_t)di], hi = ctx->resSplit[(size_t)di + 1];
-        int rc = wave_upload(ctx, d, ctx->resJobs.data(), ctx->resInfo, lo, hi - lo, d.resident);
-        if (rc == YB_OK) d.hasResident = true;
-        return rc;
+        int64_t lo = ctx->resSplit[(size_t)di], cnt = ctx->resSplit[(size_t)di + 1] - lo;
+        if (cnt <= 0) return (int)YB_OK;
+        Slot &s = d.slots[0];
+        const int64_t want = cnt;
+        int rc = slot_pack(ctx, d, s, ctx->resJobs.data(), lo, cnt, (size_t)-1);
+        if (rc != YB_OK) return rc;
+        if (cnt != want) { d.err = "resident batch does not fit"; return (int)YB_ERR_LIMIT; }
+        CUDA_TRY(d, cudaMemcpyAsync(s.dIn.p, s.hIn.p, s.blobBytes, cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(d, cudaStreamSynchronize(s.stream));
+        d.hasResident = true;
+        return (int)YB_OK;
     });
 }
 
@@ -724,25 +883,34 @@ int yb_resident_step(yb_ctx *ctx, yb_stats *stats) {
     if (!ctx) return YB_ERR_ARG;
     double t0 = now_ms();
     for (auto &d : ctx->devs) reset_stats(d);
-    int rc = for_each_device(ctx, [&](int di) {
+    int rc = for_each_device(ctx, [&](int di) -> int {
         Device &d = ctx->devs[(size_t)di];
-        if (!d.hasResident) { d.err = "no resident batch loaded"; return (int)YB_ERR_ARG; }
+        if (!d.hasResident) {
+            if (ctx->resSplit.size() > (size_t)di + 1 && ctx->resSplit[(size_t)di + 1] == ctx->resSplit[(size_t)di]) return (int)YB_OK;
+            d.err = "no resident batch loaded";
+            return (int)YB_ERR_ARG;
+        }
         if (cudaSetDevice(d.id) != cudaSuccess) return (int)YB_ERR_CUDA;
-        return wave_compute(d, d.resident);
+        int r = slot_launch(d, d.slots[0], false, false);
+        if (r != YB_OK) return r;
+        return slot_wait(d, d.slots[0]);
     });
-    int64_t cells = 0;
-    for (auto &ji : ctx->resInfo) cells += ji.cells;
-    collect_stats(ctx, stats, now_ms() - t0, cells, (int64_t)ctx->resInfo.size());
+    collect_stats(ctx, stats, now_ms() - t0, ctx->resCells, (int64_t)ctx->resJobs.size());
     return rc;
 }
 
 int yb_resident_fetch(yb_ctx *ctx, yb_result *results) {
     if (!ctx || !results) return YB_ERR_ARG;
-    return for_each_device(ctx, [&](int di) {
+    return for_each_device(ctx, [&](int di) -> int {
         Device &d = ctx->devs[(size_t)di];
-        if (!d.hasResident) { d.err = "no resident batch loaded"; return (int)YB_ERR_ARG; }
+        if (!d.hasResident) return (int)YB_OK;
         if (cudaSetDevice(d.id) != cudaSuccess) return (int)YB_ERR_CUDA;
-        return wave_download(ctx, d, d.resident, ctx->resJobs.data(), ctx->resInfo, results);
+        Slot &s = d.slots[0];
+        int r = slot_d2h(d, s);
+        if (r != YB_OK) return r;
+        CUDA_TRY(d, cudaStreamSynchronize(s.stream));
+        slot_unpack(ctx, d, s, results);
+        return (int)YB_OK;
     });
 }
 

@@ -45,14 +45,24 @@ __constant__ ScoreConst c_sc;
 struct PairMeta {
     int K, M, L, N;
     unsigned long long offA, offB;     // byte offsets into the input blob
-    unsigned long long offLB, offRB;   // byte offsets into the input blob (int32 arrays, M+1 each)
+    unsigned long long offBand;        // byte offset into the input blob: the band of rows 0..M, see bandFmt
+    unsigned long long offSched;       // byte offset into the input blob: wavefront schedule, ceil(M/32) ints
     unsigned long long rowBase;        // index of row 0's RowRec in the RowRec pool (M+1 records)
     unsigned long long colBase;        // index of column 0's ColRec in the ColRec pool (N+1 records)
     unsigned long long tbBase;         // byte offset of this pair's traceback matrix
-    unsigned long long scriptBase;     // byte offset of this pair's script (M+N bytes)
-    unsigned long long offSched;       // byte offset into the input blob: wavefront schedule, ceil(M/32) ints
+    unsigned long long scriptBase;     // 32-bit word index of this pair's packed script (ceil((M+N)/16) words)
     int nSteps;                        // wavefront steps of this pair (host computed from the schedule)
-    int pad;
+    int bandFmt;                       // 0: M+1 words LB | RB<<16 (N < 65536);  1: M+1 ints LB, then M+1 ints RB
+};
+
+// LB[r] / RB[r] of a pair, whichever way the host packed them
+struct BandView {
+    const unsigned *w;
+    int fmt, M;
+    __device__ __forceinline__ BandView(const unsigned char *blob, const PairMeta &pm)
+        : w(reinterpret_cast<const unsigned *>(blob + pm.offBand)), fmt(pm.bandFmt), M(pm.M) {}
+    __device__ __forceinline__ int lb(int r) const { return fmt ? (int)__ldg(w + r) : (int)(__ldg(w + r) & 0xffffu); }
+    __device__ __forceinline__ int rb(int r) const { return fmt ? (int)__ldg(w + M + 1 + r) : (int)(__ldg(w + r) >> 16); }
 };
 
 // Row record, 64 B (4 x 16 B).  av* are byte-count vectors matched against the column words (see
@@ -131,8 +141,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     if (M < 1) return;                                  // invalid pair (rejected on the host)
     const unsigned char *A = blob + pm.offA;
     const unsigned char *B = blob + pm.offB;
-    const int *LB = reinterpret_cast<const int *>(blob + pm.offLB);
-    const int *RB = reinterpret_cast<const int *>(blob + pm.offRB);
+    const BandView band(blob, pm);
     RowRec *rows = rowPool + pm.rowBase;
     ColRec *cols = colPool + pm.colBase;
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
@@ -169,10 +178,10 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
         RowRec rr;
         rr.avXC = rr.avYC = rr.avZC = rr.avXI = rr.avXD = rr.avYD = rr.avZD = 0u;
         rr.eD = 0; rr.w01 = rr.w23 = rr.w45 = 0u;
-        const int lb = LB[r], lbp = r > 0 ? LB[r - 1] : 0;
-        rr.LB16 = lb * 16; rr.RB16 = RB[r] * 16; rr.LBp16 = lbp * 16;
+        const int lb = band.lb(r), lbp = r > 0 ? band.lb(r - 1) : 0;
+        rr.LB16 = lb * 16; rr.RB16 = band.rb(r) * 16; rr.LBp16 = lbp * 16;
         rr.off = r >= 1 ? sched[(r - 1) >> 5] + ((r - 1) & 31) : 0;
-        rr.RBn = r < M ? RB[r + 1] : RB[r];
+        rr.RBn = r < M ? band.rb(r + 1) : band.rb(r);
         if (r >= 1) {
             const unsigned char *now = A + (size_t)(r - 1) * K;
             const unsigned char *up = now - K;    // only dereferenced when r > 1
@@ -241,14 +250,16 @@ __device__ __forceinline__ unsigned launder(unsigned x) {
 
 // Pre-shifted traceback flags (mz_yama.c:24-26,253): byte = fC | fD<<2 | fI<<4.
 // reference tie rule (mz_yama.c:138-154): x (from C) wins ties, then y (from D) only if strictly
-// greater than z (from I).  SH = bit position of this node's 2-bit field.
+// greater than z (from I).  SH = bit position of this node's 2-bit field.  A node that does not exist
+// (mz_yama.c:163-165, :202-204) keeps the flag 0 the reference leaves there, so the stored byte is the
+// reference's byte and the traceback needs no band lookups.
 template <int SH>
-__device__ __forceinline__ int pick3(int x, int y, int z, unsigned &flag) {
+__device__ __forceinline__ int pick3(int x, int y, int z, bool exists, unsigned &flag) {
     const int m = __vimax3_s32(x, y, z);
-    const bool fromC = (x == m);
+    const bool notC = (x != m) && exists;
     const bool fromD = (y > z);
     const unsigned fyz = fromD ? (unsigned)(FLAG_D << SH) : (unsigned)(FLAG_I << SH);
-    flag = fromC ? 0u : fyz;
+    flag = notC ? fyz : 0u;
     return m;
 }
 
@@ -292,6 +303,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const RowRec *rows = rowPool + pm.rowBase;
         const ColRec *cols = colPool + pm.colBase;
         unsigned char *tb = tbPool + pm.tbBase;
+        const unsigned nKGE_hi = (unsigned)(-(pm.K * c_sc.gap_ext)) << 16;   // dp2a.lo weight of byte 1 (ndB)
         const int KGE = pm.K * c_sc.gap_ext;
         const int nSteps = pm.nSteps;
         const unsigned avYI_in = (unsigned)pm.K << 8, avZI_in = (unsigned)pm.K << 24;   // K*ndB, K*b10
@@ -379,36 +391,34 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
                 unsigned fI, fC, fD;
                 int vI, vC, vD;
+                const bool hasI = c16 > LB16, hasC = c16 > LBp16;
                 {
                     int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
                     int y = Dl + dp4a_uu(cw.x, avYI, 0) * nGO;
                     int z = Il + dp4a_uu(cw.x, avZI, 0) * gIl;
-                    vI = pick3<4>(x, y, z, fI);
-                    vI -= (int)__byte_perm(cw.x, 0, 0x4441) * KGE;
+                    vI = pick3<4>(x, y, z, hasI, fI);
+                    vI = dp2a_lo_su(nKGE_hi, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
                 }
-                const bool hasI = c16 > LB16;
                 vI = hasI ? vI : MININT;
                 // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
                 {
                     int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
                     int y = Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
                     int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
-                    vC = pick3<0>(x, y, z, fC);
+                    vC = pick3<0>(x, y, z, hasC, fC);
                     vC = dp2a_lo_su(w01, cw.y, vC);
                     vC = dp2a_hi_su(w23, cw.y, vC);
                     vC = dp2a_lo_su(w45, cw.z, vC);
                 }
-                const bool hasC = c16 > LBp16;
                 vC = hasC ? vC : MININT;
                 // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
                 {
                     int x = Cu + dp4a_uu(cw.z, avXD, 0) * gCu;
                     int y = Du + dp4a_uu(cw.z, avYD, 0) * nGO;
                     int z = Iu + dp4a_uu(cw.z, avZD, 0) * gIu;
-                    vD = pick3<2>(x, y, z, fD) - eD;
+                    vD = pick3<2>(x, y, z, true, fD) - eD;
                 }
-                // traceback byte (mz_yama.c:253); the flags of nodes that do not exist are never consulted
-                // (K3 treats them as 0, which is what the reference stores)
+                // traceback byte (mz_yama.c:253), bit for bit the reference's
                 acc = __funnelshift_r(acc, fC | fD | fI, 8);
                 if (active) {
                     sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, hasI ? E_both : Efirst);
@@ -428,23 +438,22 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 
 // =================================================================================================
 // K3: traceback (mz_yama.c:257-291), one thread per pair; threads of a warp get pairs of similar size
-// (the launch order is sorted by cell count).  Per move it needs LB[r], LB[r-1], RB[r] (int arrays of
-// the input blob, 32 rows per cache line) and one traceback byte (window-major layout, ~32 moves per
-// cache line), so the dependent-load chain mostly hits L1.
+// (the launch order is sorted by cell count).  The stored bytes are the reference's own, so a move is ONE
+// dependent byte load (window-major layout: ~32 moves per cache line) plus branch-free integer work; the
+// band is not consulted.  Ops leave as 2-bit codes, 16 per 32-bit store, in the reference's (reversed)
+// order: op i sits in bits 2*(i&15) of word i>>4.
 // =================================================================================================
-__global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order,
-                                    int nPairs, const unsigned char *__restrict__ blob,
-                                    const unsigned char *__restrict__ tbPool,
-                                    unsigned char *__restrict__ scriptPool, PairOut *__restrict__ outs) {
+__global__ void __launch_bounds__(128)
+yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+                    const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
+                    unsigned *__restrict__ scriptPool, PairOut *__restrict__ outs) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nPairs) return;
     const int p = order[idx];
     const PairMeta pm = metas[p];
-    const int *LB = reinterpret_cast<const int *>(blob + pm.offLB);
-    const int *RB = reinterpret_cast<const int *>(blob + pm.offRB);
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
     const unsigned char *tb = tbPool + pm.tbBase;
-    unsigned char *script = scriptPool + pm.scriptBase;
+    unsigned *script = scriptPool + pm.scriptBase;
     PairOut o = outs[p];
     int node;
     if (o.C >= o.D && o.C >= o.I) node = FLAG_C;         // mz_yama.c:262-267
@@ -452,28 +461,29 @@ __global__ void yb_traceback_kernel(const PairMeta *__restrict__ metas, const in
     else node = FLAG_I;
     int r = pm.M, c = pm.N, n = 0, status = 0;
     const int limit = pm.M + pm.N;
+    const unsigned tmax = (unsigned)pm.nSteps - 1u;
     int blk = -1, offBlk = 0;
+    unsigned accw = 0;
     while (r > 0 || c > 0) {
-        if (r < 0 || c < 0 || n >= limit) { status = -5; break; }           // mz_yama.c:274-276
+        if (r < 0 || c < 0 || n >= limit || node == 3) { status = -5; break; }   // mz_yama.c:274-276, :289-290
         unsigned st;
         if (r == 0) {
-            st = (c == 0) ? 0u : (unsigned)(FLAG_I << 4);                   // row 0, mz_yama.c:80,91
+            st = (unsigned)(FLAG_I << 4);                                   // row 0, mz_yama.c:91
         } else {
             if (((r - 1) >> 5) != blk) { blk = (r - 1) >> 5; offBlk = __ldg(sched + blk); }
-            // all four loads are independent of each other: one round trip per move
-            const int lb = __ldg(LB + r), lbp = __ldg(LB + r - 1), rb = __ldg(RB + r);
-            st = __ldg(tb + tb_index(r, min(c, pm.N), offBlk + ((r - 1) & 31)));
-            if (c < lb || c > rb) { status = -5; break; }                   // left the band (reference: undefined)
-            // flags of nodes that do not exist are stored as 0 by the reference (mz_yama.c:165,204)
-            if (c <= lb) st &= 0x0fu;
-            if (c <= lbp) st &= 0xfcu;
+            const unsigned t = min((unsigned)(c + offBlk + ((r - 1) & 31)), tmax);   // clamp: stay inside this pair
+            st = __ldg(tb + ((size_t)(t >> 2) * 128u + (unsigned)(((r - 1) & 31) << 2) + (t & 3u)));
         }
-        script[n++] = (unsigned char)node;
-        if (node == FLAG_I) { c--; node = st >> 4; }
-        else if (node == FLAG_D) { r--; node = (st >> 2) & 3; }
-        else if (node == FLAG_C) { r--; c--; node = st & 3; }
-        else { status = -5; break; }                                        // mz_yama.c:289-290
+        accw |= (unsigned)node << (2 * (n & 15));
+        if ((n & 15) == 15) { script[n >> 4] = accw; accw = 0; }
+        ++n;
+        // I: left, field 4 | D: up, field 2 | C: diagonal, field 0
+        const int shift = node == FLAG_I ? 4 : (node == FLAG_D ? 2 : 0);
+        r -= (node != FLAG_I);
+        c -= (node != FLAG_D);
+        node = (int)((st >> shift) & 3u);
     }
+    if (n & 15) script[n >> 4] = accw;
     o.m_new = n;
     o.status = status;
     outs[p] = o;
