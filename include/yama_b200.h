@@ -106,6 +106,13 @@ int yb_assemble(const yb_job *job, const yb_result *res, uint8_t *out);
  * wording. */
 int64_t yb_check_band(int32_t M, int32_t N, const int32_t *LB, const int32_t *RB, char *msg, int msglen);
 
+/* Host-only facts about one pair, as the library derives them before packing: DP cells (tback_size of
+ * mz_yama.c:60-66), widest band row and the number of wavefront steps of the fill kernel (the pair's
+ * traceback matrix takes 32 bytes per step).  Runs the vectorised band scan AND the scalar restatement of
+ * mz_yama.c:58-71 and returns YB_ERR_LIMIT should they ever disagree; YB_ERR_BAND (msg in the reference's
+ * wording) for an invalid band. */
+int yb_pair_facts(const yb_job *job, int64_t *cells, int32_t *wmax, int32_t *nsteps, char *msg, int msglen);
+
 /* ---- sharding plan (the reference has no counterpart: it is single-process) ------ */
 /* Cuts jobs 0..n-1, kept in reference order, into nparts contiguous ranges of near-equal cost, where
  * cost(job) = cells[job] + a fixed per-pair overhead.  cuts receives nparts+1 boundaries

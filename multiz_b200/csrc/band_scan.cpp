@@ -1,0 +1,76 @@
+// band_scan.cpp -- host-side scan of one pair's band, written branch-free so that the compiler vectorises it.
+// Compiled twice by the Makefile: once with -mavx2 (-DYB_BAND_SCAN_NAME=yb_band_scan_avx2) and once for the
+// x86-64 baseline (yb_band_scan_generic, which also holds the run-time dispatcher yb_band_scan).
+//
+// One pass computes what mz_yama.c:58-71 validates (LB[0]==0, RB[M]==N, width >= min(N,10), LB and RB
+// non-decreasing), the cell count `tback_size` of mz_yama.c:60-66, the widest row, and the wavefront schedule
+// of the fill kernel (see make_schedule in yama_b200.cu).  A violation only sets a flag: the caller re-runs the
+// scalar check, which words the message exactly as the reference does.
+#include <cstdint>
+
+#ifndef YB_BAND_SCAN_NAME
+#error "compile with -DYB_BAND_SCAN_NAME=..."
+#endif
+
+extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ LB, const int32_t *__restrict__ RB,
+                                     int32_t *wmax, int32_t *__restrict__ sched, int32_t *nSteps) {
+    const int need = N < 10 ? N : 10;
+    int bad = (LB[0] != 0) | (RB[M] != N);
+    int64_t cells = 0;
+    int wm = 0;
+    {
+        int badw = 0, sum = 0, r = 0;
+        // int32 partial sums cannot overflow within 4096 rows of width < 2^19; flush into the int64 total
+        while (r <= M) {
+            const int end = (r + 4096 <= M + 1) ? r + 4096 : M + 1;
+            sum = 0;
+            for (; r < end; ++r) {
+                const int w = RB[r] - LB[r];
+                badw |= (w < need);
+                sum += w + 1;
+                wm = w > wm ? w : wm;
+            }
+            cells += sum;
+            if (wm >= (1 << 19)) bad |= 2;      // beyond any kernel limit; the caller rejects it anyway
+        }
+        bad |= badw;
+    }
+    {
+        int badm = 0;
+        for (int r = 1; r <= M; ++r) badm |= (LB[r] < LB[r - 1]) | (RB[r] < RB[r - 1]);
+        bad |= badm;
+    }
+    if (bad) return -1;
+    *wmax = wm + 1;
+    // schedule: rows 32b+1..32b+32 run on lanes 0..31 with column = step - (OFF_b + lane)
+    int off = 0, steps = 4;
+    const int nblk = (M + 31) >> 5;
+    for (int b = 0; b < nblk; ++b) {
+        if (sched) sched[b] = off;
+        if (b == nblk - 1) {
+            const int last = off + ((M - 1) & 31) + RB[M];
+            steps = ((last + 2) + 3) & ~3;
+            break;
+        }
+        int nd = 32;
+        const int r0 = 32 * b + 1;
+        const int r1 = (M - 32 < 32 * b + 32) ? M - 32 : 32 * b + 32;
+        for (int r = r0; r <= r1; ++r) {
+            const int v = RB[r + 1] - LB[r + 32] + 3;
+            nd = v > nd ? v : nd;
+        }
+        off += nd;
+    }
+    *nSteps = steps;
+    return cells;
+}
+
+#ifdef YB_BAND_SCAN_DISPATCH
+extern "C" int64_t yb_band_scan_avx2(int, int, const int32_t *, const int32_t *, int32_t *, int32_t *, int32_t *);
+extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
+                                int32_t *nSteps) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    return avx2 ? yb_band_scan_avx2(M, N, LB, RB, wmax, sched, nSteps)
+                : YB_BAND_SCAN_NAME(M, N, LB, RB, wmax, sched, nSteps);
+}
+#endif

@@ -14,9 +14,14 @@
 #include "../../include/yama_b200.h"
 #include "yama_kernels.cuh"
 
+#include <emmintrin.h>
+
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +33,9 @@
 #include <vector>
 
 using namespace yb;
+
+extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
+                                int32_t *nSteps);   // band_scan.cpp
 
 namespace {
 
@@ -61,6 +69,71 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// Persistent helper threads of one device: run(n, chunk, fn) calls fn(lo, hi) over [0,n) in dynamic chunks on
+// the helpers plus the calling thread, and returns when all of [0,n) is done.
+class Pool {
+  public:
+    explicit Pool(int helpers) {
+        for (int t = 0; t < helpers; ++t) th_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    template <class F>
+    void run(int64_t n, int64_t chunk, F &&fn) {
+        if (n <= 0) return;
+        if (chunk < 1) chunk = 1;
+        const int64_t nchunks = (n + chunk - 1) / chunk;
+        if (th_.empty() || nchunks == 1) { fn((int64_t)0, n); return; }
+        std::function<void(int64_t, int64_t)> f = std::ref(fn);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &f; n_ = n; chunk_ = chunk; nchunks_ = nchunks;
+            next_.store(0); pending_ = (int)th_.size();
+            ++gen_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work() {
+        for (;;) {
+            int64_t c = next_.fetch_add(1);
+            if (c >= nchunks_) break;
+            (*fn_)(c * chunk_, std::min(n_, (c + 1) * chunk_));
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work();
+            std::lock_guard<std::mutex> g(mu_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::function<void(int64_t, int64_t)> *fn_ = nullptr;
+    int64_t n_ = 0, chunk_ = 1, nchunks_ = 0;
+    std::atomic<int64_t> next_{0};
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
 constexpr int NBINS = 4;
 const int kRingOf[NBINS] = {128, 512, 2048, 4096};
 constexpr int NSLOTS = 3;
@@ -71,8 +144,6 @@ struct JobInfo {           // host-side facts about one pair
     int wmax = 0;          // widest band row
     int status = YB_OK;
 };
-
-struct Need { size_t blob, rows, cols, tb, scriptWords, sched; };
 
 // One staging slot = one wave in flight.
 struct Slot {
@@ -85,8 +156,9 @@ struct Slot {
     int64_t first = 0, count = 0;
     std::vector<JobInfo> info;
     std::vector<uint32_t> scriptOff;       // per pair, word offset in the wave's script pool
-    std::vector<int> schedTmp;             // schedules of the wave's pairs, back to back
-    std::vector<size_t> schedOff;
+    struct Off { size_t blob, row, col; uint32_t script; };
+    std::vector<Off> off;                  // per pair, dimension-only offsets into the pools
+    std::vector<int> bucketCount;
     size_t blobBytes = 0, metaBytes = 0, orderOff = 0, scriptWords = 0;
     int nValid = 0;
     int binStart[NBINS + 1] = {0, 0, 0, 0, 0};
@@ -98,12 +170,15 @@ struct Device {
     Slot slots[NSLOTS];
     int fillBlocks[NBINS] = {0, 0, 0, 0};
     int helpers = 1;
+    std::unique_ptr<Pool> pool;
     // accumulated stats of the current call
     double kernel_ms = 0, fill_ms = 0, profile_ms = 0, tb_ms = 0, h2d_ms = 0, d2h_ms = 0, pack_ms = 0, unpack_ms = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0, cells = 0;
     int launches = 0, waves = 0;
     std::string err;
+    int64_t errJob = 0;
     bool hasResident = false;
+    double t_layout = 0, t_par = 0, t_post = 0, t_reserve = 0, t_wait = 0, t_launch = 0;   // YB_PROFILE breakdown
 };
 
 }  // namespace
@@ -115,7 +190,9 @@ struct yb_ctx {
     ScoreConst sc{};
     int maxDepth = 255;
     int nThreads = 1;
-    size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave
+    size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave (steady state)
+    size_t waveMinBytes = (size_t)64 << 20; // first / last waves of a batch (measured: ramping does not pay on cfg2)
+    size_t batchBlobBytes = 0;              // input bytes of the current batch (dimension-only estimate)
     size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
     int64_t wavePairs = 1 << 20;
     // results of the last batch
@@ -163,27 +240,23 @@ double now_ms() {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// fn(lo, hi) over [0,n) in dynamic chunks on `threads` host threads (the caller is one of them)
+// band rows as LB | RB<<16 (both < 65536).  (Non-temporal stores were tried for the staging copies and lost:
+// the sections are small and rarely cache-line aligned, so write-combining buffers flush partially filled.)
+inline void pack_band(uint32_t *dst, const int32_t *lb, const int32_t *rb, int rowsTotal) {
+    int r = 0;
+    for (; r + 4 <= rowsTotal; r += 4) {
+        __m128i l = _mm_loadu_si128(reinterpret_cast<const __m128i *>(lb + r));
+        __m128i h = _mm_loadu_si128(reinterpret_cast<const __m128i *>(rb + r));
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + r), _mm_or_si128(l, _mm_slli_epi32(h, 16)));
+    }
+    for (; r < rowsTotal; ++r) dst[r] = (uint32_t)lb[r] | ((uint32_t)rb[r] << 16);
+}
+
+// one-off variant for work outside a device's pipeline
 template <class F>
 void parallel_for(int threads, int64_t n, int64_t chunk, F &&fn) {
-    if (n <= 0) return;
-    if (chunk < 1) chunk = 1;
-    const int64_t nchunks = (n + chunk - 1) / chunk;
-    threads = (int)std::min<int64_t>(threads, nchunks);
-    if (threads <= 1) { fn((int64_t)0, n); return; }
-    std::atomic<int64_t> next{0};
-    auto body = [&] {
-        for (;;) {
-            int64_t c = next.fetch_add(1);
-            if (c >= nchunks) break;
-            fn(c * chunk, std::min(n, (c + 1) * chunk));
-        }
-    };
-    std::vector<std::thread> th;
-    th.reserve((size_t)threads - 1);
-    for (int t = 1; t < threads; ++t) th.emplace_back(body);
-    body();
-    for (auto &t : th) t.join();
+    Pool pool(std::max(0, threads - 1));
+    pool.run(n, chunk, fn);
 }
 
 int bin_of(int wmax) {
@@ -302,8 +375,15 @@ void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, ch
         if (msg) snprintf(msg, msglen, "bad dimensions K=%d M=%d L=%d N=%d", j.K, j.M, j.L, j.N);
         return;
     }
-    int64_t cells = check_band(j.M, j.N, j.LB, j.RB, msg, msglen, &ji.wmax);
-    if (cells < 0) { ji.status = YB_ERR_BAND; return; }
+    // vectorised scan (band_scan.cpp): validation + cells + widest row + schedule in one pass; on a violation
+    // the scalar loop below words the message as the reference does
+    int nSteps = 0;
+    int64_t cells = yb_band_scan(j.M, j.N, j.LB, j.RB, &ji.wmax, sched, &nSteps);
+    if (cells < 0) {
+        cells = check_band(j.M, j.N, j.LB, j.RB, msg, msglen, &ji.wmax);
+        if (cells < 0) { ji.status = YB_ERR_BAND; return; }
+        nSteps = make_schedule(j.M, j.LB, j.RB, sched);       // (unreachable unless the two scans disagree)
+    }
     ji.cells = cells;
     if (j.K > ctx->maxDepth || j.L > 255) {
         ji.status = YB_ERR_LIMIT;
@@ -315,7 +395,7 @@ void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, ch
         if (msg) snprintf(msg, msglen, "band row of %d cells exceeds the kernel limit (%d)", ji.wmax, kRingOf[NBINS - 1] - 32);
         return;
     }
-    ji.nSteps = make_schedule(j.M, j.LB, j.RB, sched);
+    ji.nSteps = nSteps;
 }
 
 inline int band_fmt(const yb_job &j) { return j.N < 65536 ? 0 : 1; }
@@ -326,68 +406,138 @@ inline size_t blob_bytes(const yb_job &j) {
     return align_up((size_t)j.K * j.M, 16) + align_up((size_t)j.L * j.N, 16) +
            align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 16) + align_up(sched_ints(j) * 4, 16);
 }
-inline Need need_of(const yb_job &j, const JobInfo &ji) {
-    Need n;
-    n.blob = blob_bytes(j);
-    n.rows = (size_t)j.M + 1;
-    n.cols = (size_t)j.N + 1;
-    n.tb = align_up((size_t)ji.nSteps * 32, 128);
-    n.scriptWords = ((size_t)j.M + j.N + 15) / 16;
-    n.sched = sched_ints(j);
-    return n;
-}
-
-// Analyse + pack jobs [first, first+count) into the slot's pinned buffer.  `maxTb` caps the wave's
-// traceback bytes: the wave is cut short (count shrinks, at least one job stays) when it would not fit.
+// Analyse + pack jobs [first, first+count) into the slot's pinned buffer, one pass over the caller's data:
+// everything but the traceback size of a pair follows from its dimensions, so blob / record / script offsets
+// are prefix sums taken up front and each helper validates the band (mz_yama.c:58-71), writes the schedule
+// and copies A, B and the band while they are hot in its cache.  Traceback offsets are assigned afterwards.
+// `maxTb` caps the wave's traceback bytes: the wave is cut short (count shrinks, at least one job stays).
 int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t &count, size_t maxTb) {
     const double t0 = now_ms();
-    const int T = d.helpers;
-    // ---- analysis (parallel): band validation, cells, schedule -----------------------------------------
-    s.info.assign((size_t)count, JobInfo());
-    s.schedOff.assign((size_t)count + 1, 0);
+    // ---- dimension-only layout (serial, a few ns per job) ------------------------------------------------------
+    struct Off { size_t blob, row, col; uint32_t script; };
+    s.off.resize((size_t)count);
+    size_t blob = 0, rows = 0, cols = 0, words = 0;
     for (int64_t i = 0; i < count; ++i) {
         const yb_job &j = jobs[first + i];
-        s.schedOff[(size_t)i + 1] = s.schedOff[(size_t)i] + (j.M >= 1 ? sched_ints(j) : 0);
+        s.off[(size_t)i] = Slot::Off{blob, rows, cols, (uint32_t)words};
+        if (j.K < 1 || j.L < 1 || j.M < 1 || j.N < 1 || !j.A || !j.B || !j.LB || !j.RB) continue;
+        blob += blob_bytes(j); rows += (size_t)j.M + 1; cols += (size_t)j.N + 1;
+        words += ((size_t)j.M + j.N + 15) / 16;
     }
-    s.schedTmp.resize(s.schedOff[(size_t)count] + 1);
-    std::mutex errMu;
-    parallel_for(T, count, 256, [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            char msg[256];
-            msg[0] = 0;
-            analyse_one(ctx, jobs[first + i], s.info[(size_t)i], s.schedTmp.data() + s.schedOff[(size_t)i], msg, sizeof msg);
-            if (s.info[(size_t)i].status != YB_OK) {
-                std::lock_guard<std::mutex> g(errMu);
-                if (d.err.empty()) {
-                    char b[400];
-                    if (s.info[(size_t)i].status == YB_ERR_BAND) snprintf(b, sizeof b, "%s", msg);   // reference wording
-                    else snprintf(b, sizeof b, "job %lld: %s", (long long)(first + i), msg);
-                    d.err = b;
-                }
-            }
-        }
-    });
-    // ---- offsets (serial prefix sums); cut the wave where the traceback pool would overflow ---------------
-    struct Off { size_t blob, row, col, tb; uint32_t script; };
-    std::vector<Off> off((size_t)count);
-    size_t blob = 0, rows = 0, cols = 0, tb = 0, words = 0;
-    int64_t kept = count;
-    for (int64_t i = 0; i < count; ++i) {
-        const JobInfo &ji = s.info[(size_t)i];
-        off[(size_t)i] = Off{blob, rows, cols, tb, (uint32_t)words};
-        if (ji.status != YB_OK) continue;
-        Need n = need_of(jobs[first + i], ji);
-        if (i > 0 && tb + n.tb > maxTb) { kept = i; break; }
-        blob += n.blob; rows += n.rows; cols += n.cols; tb += n.tb; words += n.scriptWords;
-    }
-    count = kept;
-    s.first = first; s.count = count;
+    s.first = first;
     s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
     s.orderOff = s.metaBytes;
     const size_t dataOff = s.metaBytes + align_up((size_t)count * 4, 256);
+    CUDA_TRY(d, s.hIn.reserve(dataOff + blob));
+    s.info.resize((size_t)count);
+    s.scriptOff.resize((size_t)count);
+    unsigned char *h = static_cast<unsigned char *>(s.hIn.p);
+    PairMeta *metas = reinterpret_cast<PairMeta *>(h);
+
+    const double t1 = now_ms();
+    d.t_layout += t1 - t0;
+    // ---- analyse + pack (parallel) -----------------------------------------------------------------------------
+    std::mutex errMu;
+    d.pool->run(count, 32, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const yb_job &j = jobs[first + i];
+            JobInfo &ji = s.info[(size_t)i];
+            const Slot::Off &of = s.off[(size_t)i];
+            PairMeta pm;
+            memset(&pm, 0, sizeof pm);
+            s.scriptOff[(size_t)i] = of.script;
+            char msg[256];
+            msg[0] = 0;
+            // the schedule goes straight to its place in the blob (after A, B and the band)
+            size_t o = dataOff + of.blob;
+            const bool dimsOk = j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1 && j.A && j.B && j.LB && j.RB;
+            size_t oA = o, oB = 0, oBand = 0, oSched = 0;
+            if (dimsOk) {
+                oB = oA + align_up((size_t)j.K * j.M, 16);
+                oBand = oB + align_up((size_t)j.L * j.N, 16);
+                oSched = oBand + align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 16);
+            }
+            analyse_one(ctx, j, ji, dimsOk ? reinterpret_cast<int *>(h + oSched) : nullptr, msg, sizeof msg);
+            if (ji.status != YB_OK) {
+                metas[i] = pm;
+                std::lock_guard<std::mutex> g(errMu);
+                if (d.err.empty() || first + i < d.errJob) {
+                    char b[400];
+                    if (ji.status == YB_ERR_BAND) snprintf(b, sizeof b, "%s", msg);   // reference wording
+                    else snprintf(b, sizeof b, "job %lld: %s", (long long)(first + i), msg);
+                    d.err = b;
+                    d.errJob = first + i;
+                }
+                continue;
+            }
+            pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
+            pm.offA = oA; memcpy(h + oA, j.A, (size_t)j.K * j.M);
+            pm.offB = oB; memcpy(h + oB, j.B, (size_t)j.L * j.N);
+            pm.offBand = oBand;
+            pm.bandFmt = band_fmt(j);
+            if (pm.bandFmt == 0) {
+                pack_band(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
+            } else {
+                memcpy(h + oBand, j.LB, (size_t)(j.M + 1) * 4);
+                memcpy(h + oBand + (size_t)(j.M + 1) * 4, j.RB, (size_t)(j.M + 1) * 4);
+            }
+            pm.offSched = oSched;
+            pm.nSteps = ji.nSteps;
+            pm.rowBase = of.row;
+            pm.colBase = of.col;
+            pm.scriptBase = of.script;
+            metas[i] = pm;
+        }
+    });
+
+    // ---- traceback offsets, wave cut, launch order (serial, O(count)) -----------------------------------------------
+    // launch order: per ring bin, big pairs first (longest-processing-time-first on the warp queue); quarter-octave
+    // buckets of the cell count instead of a comparison sort
+    const double t2 = now_ms();
+    d.t_par += t2 - t1;
+    constexpr int NB = 160;
+    s.bucketCount.assign((size_t)NBINS * NB, 0);
+    auto bucket_of = [](int64_t cells) {
+        int lg = 63 - __builtin_clzll((unsigned long long)std::max<int64_t>(cells, 1));
+        int frac = lg >= 2 ? (int)((cells >> (lg - 2)) & 3) : 0;
+        return NB - 1 - std::min(NB - 1, lg * 4 + frac);          // descending
+    };
+    size_t tb = 0;
+    int64_t kept = count;
+    for (int64_t i = 0; i < count; ++i) {
+        const JobInfo &ji = s.info[(size_t)i];
+        if (ji.status != YB_OK) continue;
+        const size_t need = align_up((size_t)ji.nSteps * 32, 128);
+        if (i > 0 && tb + need > maxTb) { kept = i; break; }
+        metas[i].tbBase = tb;
+        tb += need;
+        s.bucketCount[(size_t)bin_of(ji.wmax) * NB + bucket_of(ji.cells)]++;
+    }
+    count = kept;
+    s.count = count;
+    if (count < (int64_t)s.off.size()) {           // wave cut short: sizes of the kept prefix
+        const Slot::Off &of = s.off[(size_t)count];
+        blob = of.blob; rows = of.row; cols = of.col; words = of.script;
+    }
     s.blobBytes = dataOff + blob;
     s.scriptWords = words;
-    CUDA_TRY(d, s.hIn.reserve(s.blobBytes));
+    {
+        int *order = reinterpret_cast<int *>(h + s.orderOff);
+        int acc = 0;
+        for (int b = 0; b < NBINS; ++b) {
+            s.binStart[b] = acc;
+            for (int q = 0; q < NB; ++q) { int c = s.bucketCount[(size_t)b * NB + q]; s.bucketCount[(size_t)b * NB + q] = acc; acc += c; }
+        }
+        s.binStart[NBINS] = acc;
+        s.nValid = acc;
+        for (int64_t i = 0; i < count; ++i) {
+            const JobInfo &ji = s.info[(size_t)i];
+            if (ji.status != YB_OK) continue;
+            order[s.bucketCount[(size_t)bin_of(ji.wmax) * NB + bucket_of(ji.cells)]++] = (int)i;
+        }
+    }
+    const double t3 = now_ms();
+    d.t_post += t3 - t2;
     CUDA_TRY(d, s.dIn.reserve(s.blobBytes));
     CUDA_TRY(d, s.dRow.reserve(rows * sizeof(RowRec) + 64));
     CUDA_TRY(d, s.dCol.reserve(cols * sizeof(ColRec) + 64));
@@ -397,59 +547,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     CUDA_TRY(d, s.dQueue.reserve(64));
     CUDA_TRY(d, s.hScript.reserve(words * 4 + 64));
     CUDA_TRY(d, s.hOut.reserve((size_t)count * sizeof(PairOut) + 64));
-
-    unsigned char *h = static_cast<unsigned char *>(s.hIn.p);
-    PairMeta *metas = reinterpret_cast<PairMeta *>(h);
-    s.scriptOff.resize((size_t)count);
-    // ---- pack (parallel) -----------------------------------------------------------------------------------
-    parallel_for(T, count, 64, [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            const yb_job &j = jobs[first + i];
-            const JobInfo &ji = s.info[(size_t)i];
-            PairMeta pm;
-            memset(&pm, 0, sizeof pm);
-            s.scriptOff[(size_t)i] = off[(size_t)i].script;
-            if (ji.status != YB_OK) { metas[i] = pm; continue; }
-            size_t o = dataOff + off[(size_t)i].blob;
-            pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
-            pm.offA = o; memcpy(h + o, j.A, (size_t)j.K * j.M); o += align_up((size_t)j.K * j.M, 16);
-            pm.offB = o; memcpy(h + o, j.B, (size_t)j.L * j.N); o += align_up((size_t)j.L * j.N, 16);
-            pm.offBand = o;
-            pm.bandFmt = band_fmt(j);
-            if (pm.bandFmt == 0) {
-                uint32_t *w = reinterpret_cast<uint32_t *>(h + o);
-                for (int r = 0; r <= j.M; ++r) w[r] = (uint32_t)j.LB[r] | ((uint32_t)j.RB[r] << 16);
-                o += align_up((size_t)(j.M + 1) * 4, 16);
-            } else {
-                memcpy(h + o, j.LB, (size_t)(j.M + 1) * 4);
-                memcpy(h + o + (size_t)(j.M + 1) * 4, j.RB, (size_t)(j.M + 1) * 4);
-                o += align_up((size_t)(j.M + 1) * 8, 16);
-            }
-            pm.offSched = o;
-            memcpy(h + o, s.schedTmp.data() + s.schedOff[(size_t)i], sched_ints(j) * 4);
-            pm.nSteps = ji.nSteps;
-            pm.rowBase = off[(size_t)i].row;
-            pm.colBase = off[(size_t)i].col;
-            pm.tbBase = off[(size_t)i].tb;
-            pm.scriptBase = off[(size_t)i].script;
-            metas[i] = pm;
-        }
-    });
-    // ---- launch order: per ring bin, largest pairs first (longest-processing-time-first on the warp queue)
-    std::vector<std::pair<int64_t, int>> binned[NBINS];
-    for (int64_t i = 0; i < count; ++i)
-        if (s.info[(size_t)i].status == YB_OK) binned[bin_of(s.info[(size_t)i].wmax)].push_back({s.info[(size_t)i].cells, (int)i});
-    int *order = reinterpret_cast<int *>(h + s.orderOff);
-    int k = 0;
-    for (int b = 0; b < NBINS; ++b) {
-        s.binStart[b] = k;
-        std::sort(binned[b].begin(), binned[b].end(), [](const std::pair<int64_t, int> &x, const std::pair<int64_t, int> &y) {
-            return x.first != y.first ? x.first > y.first : x.second < y.second;
-        });
-        for (auto &pr : binned[b]) order[k++] = pr.second;
-    }
-    s.binStart[NBINS] = k;
-    s.nValid = k;
+    d.t_reserve += now_ms() - t3;
     d.pack_ms += now_ms() - t0;
     return YB_OK;
 }
@@ -466,6 +564,7 @@ int slot_launch(Device &d, Slot &s, bool h2d, bool d2h) {
     const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
     int *queue = static_cast<int *>(s.dQueue.p);
     cudaStream_t st = s.stream;
+    const double tl = now_ms();
 
     CUDA_TRY(d, cudaEventRecord(s.ev[0], st));
     if (h2d) CUDA_TRY(d, cudaMemcpyAsync(s.dIn.p, s.hIn.p, s.blobBytes, cudaMemcpyHostToDevice, st));
@@ -502,6 +601,7 @@ int slot_launch(Device &d, Slot &s, bool h2d, bool d2h) {
     d.waves++;
     if (h2d) d.h2d_bytes += (int64_t)s.blobBytes;
     if (d2h) d.d2h_bytes += (int64_t)((size_t)s.count * sizeof(PairOut) + s.scriptWords * 4);
+    d.t_launch += now_ms() - tl;
     return YB_OK;
 }
 
@@ -515,7 +615,9 @@ int slot_d2h(Device &d, Slot &s) {
 
 // Wait for the slot's wave and add its device times to the statistics.
 int slot_wait(Device &d, Slot &s) {
+    const double tw = now_ms();
     CUDA_TRY(d, cudaStreamSynchronize(s.stream));
+    d.t_wait += now_ms() - tw;
     CUDA_TRY(d, cudaGetLastError());
     float h = 0, a = 0, b = 0, c = 0, e = 0;
     cudaEventElapsedTime(&h, s.ev[0], s.ev[1]);
@@ -534,7 +636,13 @@ void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
     const double t0 = now_ms();
     const PairOut *outs = static_cast<const PairOut *>(s.hOut.p);
     const uint32_t *hs = static_cast<const uint32_t *>(s.hScript.p);
-    parallel_for(d.helpers, s.count, 128, [&](int64_t lo, int64_t hi) {
+    static const std::array<uint32_t, 256> lut = [] {      // one packed byte (4 ops) -> 4 script bytes
+        std::array<uint32_t, 256> t{};
+        for (unsigned v = 0; v < 256; ++v)
+            t[v] = (v & 3u) | (((v >> 2) & 3u) << 8) | (((v >> 4) & 3u) << 16) | (((v >> 6) & 3u) << 24);
+        return t;
+    }();
+    d.pool->run(s.count, 128, [&](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             const int64_t g = s.first + i;
             yb_result &r = results[g];
@@ -547,17 +655,11 @@ void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
             r.status = o.status;
             r.m_new = o.m_new; r.C = o.C; r.D = o.D; r.I = o.I;
             uint8_t *dst = ctx->scriptStore.get() + ctx->scriptOff[(size_t)g];
-            const uint32_t *src = hs + s.scriptOff[(size_t)i];
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(hs + s.scriptOff[(size_t)i]);
             const int n = o.m_new;
             int k = 0;
-            for (; k + 16 <= n; k += 16) {
-                uint32_t w = src[k >> 4];
-                for (int q = 0; q < 16; ++q) dst[k + q] = (uint8_t)((w >> (2 * q)) & 3u);
-            }
-            if (k < n) {
-                uint32_t w = src[k >> 4];
-                for (int q = 0; k + q < n; ++q) dst[k + q] = (uint8_t)((w >> (2 * q)) & 3u);
-            }
+            for (; k + 4 <= n; k += 4) { uint32_t w = lut[src[k >> 2]]; memcpy(dst + k, &w, 4); }
+            if (k < n) { uint32_t w = lut[src[k >> 2]]; memcpy(dst + k, &w, (size_t)(n - k)); }
             r.script = dst;
         }
     });
@@ -571,6 +673,8 @@ void reset_stats(Device &d) {
     d.h2d_bytes = d.d2h_bytes = d.cells = 0;
     d.launches = d.waves = 0;
     d.err.clear();
+    d.errJob = 0;
+    d.t_layout = d.t_par = d.t_post = d.t_reserve = d.t_wait = d.t_launch = 0;
 }
 
 void collect_stats(yb_ctx *ctx, yb_stats *st, double total_ms, int64_t cells, int64_t pairs) {
@@ -617,27 +721,38 @@ void plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cut) {
 }
 
 // Hands out waves: contiguous job ranges whose input fits one staging slot (sizes known from dimensions).
+// Waves start small (the device idles while the first one is packed), grow to maxBytes, and shrink again
+// towards the end of the batch (the host idles while the last one is on the device).
 struct Dispatcher {
     const yb_job *jobs = nullptr;
     int64_t n = 0, cursor = 0;
-    size_t maxBytes = 0;
+    size_t maxBytes = 0, minBytes = 0, remaining = 0;
     int64_t maxPairs = 0;
+    int ndev = 1, handed = 0;
     std::mutex mu;
+    static size_t bytes_of(const yb_job &j) {
+        size_t b = sizeof(PairMeta) + 4;
+        if (j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1) b += blob_bytes(j);
+        return b;
+    }
     bool grab(int64_t &lo, int64_t &hi) {
         std::lock_guard<std::mutex> g(mu);
         if (cursor >= n) return false;
         lo = cursor;
+        const int round = handed / ndev;
+        size_t target = std::min(maxBytes, minBytes << std::min(round, 16));           // ramp up
+        target = std::min(target, std::max(minBytes, remaining / (size_t)(2 * ndev))); // ramp down
         size_t bytes = 0;
         int64_t i = lo;
         while (i < n && i - lo < maxPairs) {
-            const yb_job &j = jobs[i];
-            size_t b = sizeof(PairMeta) + 4;
-            if (j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1) b += blob_bytes(j);
-            if (i > lo && bytes + b > maxBytes) break;
+            size_t b = bytes_of(jobs[i]);
+            if (i > lo && bytes + b > target) break;
             bytes += b;
             ++i;
         }
         hi = cursor = i;
+        remaining -= std::min(remaining, bytes);
+        ++handed;
         return true;
     }
 };
@@ -672,11 +787,13 @@ int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
 
 void prepare_script_store(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
     ctx->scriptOff.assign((size_t)n, 0);
-    size_t tot = 0;
+    size_t tot = 0, blob = 0;
     for (int64_t i = 0; i < n; ++i) {
         ctx->scriptOff[(size_t)i] = tot;
         if (jobs[i].M >= 1 && jobs[i].N >= 1) tot += (size_t)jobs[i].M + jobs[i].N;
+        blob += Dispatcher::bytes_of(jobs[i]);
     }
+    ctx->batchBlobBytes = blob;
     if (tot + 16 > ctx->scriptStoreCap) {
         ctx->scriptStore.reset(new uint8_t[tot + tot / 8 + 16]);
         ctx->scriptStoreCap = tot + tot / 8 + 16;
@@ -729,9 +846,13 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     ctx->nThreads = std::min(hw, 32);
     if (const char *e = getenv("YB_THREADS")) ctx->nThreads = std::max(1, atoi(e));
     if (const char *e = getenv("YB_WAVE_MB")) ctx->waveInBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
+    if (const char *e = getenv("YB_WAVE_MIN_MB")) ctx->waveMinBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
-    for (auto &d : ctx->devs) d.helpers = std::max(1, ctx->nThreads / (int)ctx->devs.size());
+    for (auto &d : ctx->devs) {
+        d.helpers = std::max(1, ctx->nThreads / (int)ctx->devs.size());
+        d.pool.reset(new Pool(d.helpers - 1));
+    }
     *out = ctx;
     return YB_OK;
 }
@@ -803,6 +924,22 @@ int yb_set_scores(yb_ctx *ctx, const int32_t *ss, const int32_t *gop, int32_t ga
     return YB_OK;
 }
 
+int yb_pair_facts(const yb_job *job, int64_t *cells, int32_t *wmax, int32_t *nsteps, char *msg, int msglen) {
+    if (!job || job->M < 1 || job->N < 1 || !job->LB || !job->RB) return YB_ERR_ARG;
+    const int nblk = (job->M + 31) >> 5;
+    std::vector<int> s1((size_t)nblk + 1, -1), s2((size_t)nblk + 1, -1);
+    int w1 = 0, w2 = 0, n1 = 0;
+    const int64_t c1 = yb_band_scan(job->M, job->N, job->LB, job->RB, &w1, s1.data(), &n1);
+    const int64_t c2 = check_band(job->M, job->N, job->LB, job->RB, msg, msglen, &w2);
+    if (c2 < 0) return c1 < 0 ? YB_ERR_BAND : YB_ERR_LIMIT;
+    const int n2 = make_schedule(job->M, job->LB, job->RB, s2.data());
+    if (c1 != c2 || w1 != w2 || n1 != n2 || s1 != s2) return YB_ERR_LIMIT;
+    if (cells) *cells = c2;
+    if (wmax) *wmax = w2;
+    if (nsteps) *nsteps = n2;
+    return YB_OK;
+}
+
 int yb_plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cuts) {
     if (n < 0 || nparts < 1 || !cuts || (n > 0 && !cells)) return YB_ERR_ARG;
     plan_split(n, cells, nparts, cuts);
@@ -823,10 +960,18 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     Dispatcher disp;
     disp.jobs = jobs; disp.n = n;
     disp.maxBytes = ctx->waveInBytes; disp.maxPairs = ctx->wavePairs;
+    disp.minBytes = std::min(ctx->waveInBytes, ctx->waveMinBytes);
+    disp.ndev = (int)ctx->devs.size();
+    disp.remaining = ctx->batchBlobBytes;
     int rc = for_each_device(ctx, [&](int d) { return device_run(ctx, ctx->devs[(size_t)d], disp, results); });
     int64_t cells = 0;
     for (auto &d : ctx->devs) cells += d.cells;
     collect_stats(ctx, stats, now_ms() - t0, cells, n);
+    if (getenv("YB_PROFILE"))
+        for (auto &d : ctx->devs)
+            fprintf(stderr, "yama_b200[profile] dev %d: waves %d total %.2f ms | pack %.2f (layout %.2f, analyse+copy %.2f, order %.2f, reserve %.2f) "
+                    "launch %.2f wait %.2f unpack %.2f | device: h2d %.2f kernels %.2f d2h %.2f\n", d.id, d.waves, now_ms() - t0, d.pack_ms,
+                    d.t_layout, d.t_par, d.t_post, d.t_reserve, d.t_launch, d.t_wait, d.unpack_ms, d.h2d_ms, d.kernel_ms, d.d2h_ms);
     if (rc != YB_OK) return rc;
     // per-pair failures: report the first in job order, in the reference's wording where it has one
     for (int64_t i = 0; i < n; ++i)

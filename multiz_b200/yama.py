@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ABI_SYMBOLS = (
     "yb_create", "yb_destroy", "yb_last_error", "yb_device_count", "yb_set_scores",
     "yb_run_batch", "yb_resident_load", "yb_resident_step", "yb_resident_fetch",
-    "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band", "yb_plan_split",
+    "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band", "yb_plan_split", "yb_pair_facts",
 )
 
 
@@ -105,6 +105,8 @@ def load_library():
     lib.yb_assemble.restype = C.c_int
     lib.yb_check_band.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
     lib.yb_check_band.restype = C.c_int64
+    lib.yb_pair_facts.argtypes = [P(yb_job), P(C.c_int64), P(C.c_int32), P(C.c_int32), C.c_char_p, C.c_int]
+    lib.yb_pair_facts.restype = C.c_int
     lib.yb_plan_split.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.yb_plan_split.restype = C.c_int
     _LIB = lib

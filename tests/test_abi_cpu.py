@@ -112,3 +112,45 @@ def test_plan_split_properties():
             cost = np.where(np.diff(cuts) > 0, cost, 0)
             assert cost.max() <= cost.sum() / parts + (cells.max() + 2000)      # within one pair of ideal
     assert list(multiz_b200.plan_split([100, 200, 50000, 30, 40, 50, 60000], 3)) == [0, 3, 6, 7]
+
+
+def test_pair_facts_simd_scan_equals_scalar(oracle):
+    """yb_pair_facts cross-checks the vectorised host scan (band_scan.cpp) against the scalar restatement of
+    mz_yama.c:58-71 and the schedule builder; cells must also equal the oracle's tback_size."""
+    from tools.synth import random_band, SynthBatch
+    lib = multiz_b200.load_library()
+    rng = np.random.default_rng(11)
+    msg = C.create_string_buffer(256)
+    cells, wmax, nsteps = C.c_int64(), C.c_int32(), C.c_int32()
+
+    def facts(M, N, LB, RB):
+        LB, RB = np.ascontiguousarray(LB, np.int32), np.ascontiguousarray(RB, np.int32)
+        job = ymod.yb_job(1, M, 1, N, None, None, LB.ctypes.data, RB.ctypes.data)
+        return lib.yb_pair_facts(C.byref(job), C.byref(cells), C.byref(wmax), C.byref(nsteps), msg, 256)
+
+    n_bad = 0
+    for it in range(600):
+        M, N = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        LB, RB = random_band(rng, M, N, ("smooth", "ragged", "full")[it % 3])
+        if it % 4 == 3:                       # corrupt: narrow row, non-monotone step or bad terminator
+            RB, LB = RB.copy(), LB.copy()
+            k = int(rng.integers(0, M + 1))
+            which = int(rng.integers(0, 3))
+            if which == 0: RB[k] = max(0, int(RB[k]) - int(rng.integers(1, 30)))
+            elif which == 1: LB[k] = int(LB[k]) + int(rng.integers(1, 30))
+            else: LB[0] = 1
+        rc = facts(M, N, LB, RB)
+        omsg = C.create_string_buffer(256)
+        want = oracle.lib.oracle_check_band(M, N, np.ascontiguousarray(LB, np.int32).ctypes.data,
+                                            np.ascontiguousarray(RB, np.int32).ctypes.data, omsg, 256)
+        if want < 0:
+            n_bad += 1
+            assert rc == -2 and msg.value == omsg.value, (it, rc, msg.value, omsg.value)
+        else:
+            assert rc == 0 and cells.value == want, (it, rc)
+            assert wmax.value == int((RB.astype(np.int64) - LB + 1).max()) and nsteps.value % 4 == 0
+    assert n_bad > 20
+    sb = SynthBatch(8, [3] * 6, [1] * 6, [5000, 4097, 4096, 8193, 33, 64], R=30)     # across the 4096-row flush
+    for i in range(sb.n):
+        A, B, LB, RB = sb.problem(i)
+        assert facts(A.shape[0], B.shape[0], LB, RB) == 0 and cells.value == int((RB.astype(np.int64) - LB + 1).sum())
