@@ -43,13 +43,13 @@ extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ L
     if (bad) return -1;
     *wmax = wm + 1;
     // schedule: rows 32b+1..32b+32 run on lanes 0..31 with column = step - (OFF_b + lane)
-    int off = 0, steps = 4;
+    int off = 0, steps = 8;
     const int nblk = (M + 31) >> 5;
     for (int b = 0; b < nblk; ++b) {
         if (sched) sched[b] = off;
         if (b == nblk - 1) {
             const int last = off + ((M - 1) & 31) + RB[M];
-            steps = ((last + 2) + 3) & ~3;
+            steps = ((last + 2) + 7) & ~7;
             break;
         }
         int nd = 32;

@@ -360,11 +360,11 @@ int make_schedule(int M, const int *LB, const int *RB, int *sched) {
         if (b == nblk - 1) {
             int lane = (M - 1) & 31;
             int last = off + lane + RB[M];                 // step of the last cell
-            return ((last + 2) + 3) & ~3;                  // +1 step to publish the final scores, whole windows
+            return ((last + 2) + 7) & ~7;                  // +1 step to publish the final scores, whole 8-step groups
         }
         off += need;
     }
-    return 4;
+    return 8;
 }
 
 // Everything the host needs to know about one job; msg (optional) gets the reference's wording.

@@ -78,13 +78,14 @@ struct __align__(16) RowRec {
     int RBn;                           //     RB[r+1] (RB[r] on the last row): how far the row below reads us
 };
 
-// Traceback matrix layout ("window-major"): the warp advances one anti-diagonal per step; the byte of
-// the cell that lane l computed at step t lives at  (t>>2)*128 + 4*l + (t&3).  Every 4 steps the warp
-// stores one fully coalesced 128-B line, and a traceback path (which walks anti-diagonals backwards)
-// stays inside one line for ~32 moves.  Cell (r,c) was computed by lane (r-1)&31 at step c + off[r].
-__device__ __forceinline__ unsigned long long tb_index(int r, int c, int off) {
-    const unsigned t = (unsigned)(c + off);
-    return (unsigned long long)(t >> 2) * 128ull + (unsigned)(((r - 1) & 31) << 2) + (t & 3u);
+// Traceback matrix layout: the warp advances one anti-diagonal per step; lane l computes one cell per step t
+// (cell (r,c) with l = (r-1)&31 and t = c + off[r]).  The byte of (l,t) lives at  (t>>3)*256 + 8*l + (t&7):
+// every 4 steps a lane stores one 32-bit word, and two consecutive stores of the warp fill 256 contiguous
+// bytes.  A 32-B sector then holds 4 lanes x 8 steps -- the shape a traceback path likes: a diagonal move is
+// (l-1, t-2), an up move (l-1, t-1), a left move (l, t-1), so a path spends >= 4 moves in a sector before it
+// drops into the sector of (l-4, t-8), 288 bytes below.
+__device__ __forceinline__ unsigned long long tb_byte(unsigned lane, unsigned t) {
+    return (unsigned long long)(t >> 3) * 256ull + (lane << 3) + (t & 7u);
 }
 
 // Column record, 16 B.
@@ -423,8 +424,8 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 if (active) {
                     sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, hasI ? E_both : Efirst);
                 }
-                // one coalesced 128-B line of traceback bytes per 4 steps (see tb_index)
-                if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)t4 * 8 + lane] = acc;
+                // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
+                if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * 64 + lane * 2 + ((t4 >> 2) & 1)] = acc;
                 Cl = vC; Dl = vD; Il = vI;
                 gCl = hasC ? nGO : 0; gIl = hasI ? nGO : 0;
                 Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
@@ -439,7 +440,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 // =================================================================================================
 // K3: traceback (mz_yama.c:257-291), one thread per pair; threads of a warp get pairs of similar size
 // (the launch order is sorted by cell count).  The stored bytes are the reference's own, so a move is ONE
-// dependent byte load (window-major layout: ~32 moves per cache line) plus branch-free integer work; the
+// dependent byte load (>= 4 moves per 32-B sector, see tb_byte) plus branch-free integer work; the
 // band is not consulted.  Ops leave as 2-bit codes, 16 per 32-bit store, in the reference's (reversed)
 // order: op i sits in bits 2*(i&15) of word i>>4.
 // =================================================================================================
@@ -463,7 +464,9 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
     const int limit = pm.M + pm.N;
     const unsigned tmax = (unsigned)pm.nSteps - 1u;
     int blk = -1, offBlk = 0;
+    long long lastSec = -1;
     unsigned accw = 0;
+    constexpr int TB_AHEAD = 4;
     while (r > 0 || c > 0) {
         if (r < 0 || c < 0 || n >= limit || node == 3) { status = -5; break; }   // mz_yama.c:274-276, :289-290
         unsigned st;
@@ -471,8 +474,19 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
             st = (unsigned)(FLAG_I << 4);                                   // row 0, mz_yama.c:91
         } else {
             if (((r - 1) >> 5) != blk) { blk = (r - 1) >> 5; offBlk = __ldg(sched + blk); }
-            const unsigned t = min((unsigned)(c + offBlk + ((r - 1) & 31)), tmax);   // clamp: stay inside this pair
-            st = __ldg(tb + ((size_t)(t >> 2) * 128u + (unsigned)(((r - 1) & 31) << 2) + (t & 3u)));
+            const unsigned lane = (unsigned)(r - 1) & 31u;
+            const unsigned t = min((unsigned)(c + offBlk) + lane, tmax);              // clamp: stay inside this pair
+            const unsigned long long at = tb_byte(lane, t);
+            // The bytes were written a whole fill kernel ago: every new 32-B sector is a dependent miss to HBM.  A path
+            // is mostly diagonal, so when it enters a sector the one it will need TB_AHEAD sectors later is known:
+            // pull it into L2 now and the chain runs at L2 latency.
+            const long long sec = (long long)(at >> 5);
+            if (sec != lastSec) {
+                lastSec = sec;
+                const long long ahead = (long long)at - (long long)TB_AHEAD * 288;
+                if (ahead >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + ahead));
+            }
+            st = __ldg(tb + at);
         }
         accw |= (unsigned)node << (2 * (n & 15));
         if ((n & 15) == 15) { script[n >> 4] = accw; accw = 0; }

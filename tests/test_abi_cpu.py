@@ -148,7 +148,7 @@ def test_pair_facts_simd_scan_equals_scalar(oracle):
             assert rc == -2 and msg.value == omsg.value, (it, rc, msg.value, omsg.value)
         else:
             assert rc == 0 and cells.value == want, (it, rc)
-            assert wmax.value == int((RB.astype(np.int64) - LB + 1).max()) and nsteps.value % 4 == 0
+            assert wmax.value == int((RB.astype(np.int64) - LB + 1).max()) and nsteps.value % 8 == 0
     assert n_bad > 20
     sb = SynthBatch(8, [3] * 6, [1] * 6, [5000, 4097, 4096, 8193, 33, 64], R=30)     # across the 4096-row flush
     for i in range(sb.n):
