@@ -32,7 +32,30 @@ if ROOT not in sys.path:
 from tools.synth import SynthBatch  # noqa: E402
 
 OPS_PER_CELL = 38          # canonical int32 ops per DP cell
-INT32_PEAK_FALLBACK_GOPS = 148 * 128 * 1.965   # 128 int lanes/SM/clk at 1965 MHz, used if not measured
+INT32_PEAK_FALLBACK_GOPS = 148 * 128 * 1.965   # issue limit: 4 warp-instructions/SM/clk at 1965 MHz
+
+
+def measured_int_peak():
+    """Integer issue peak measured on this pool's B200 by tools/int_peak.cu (profiles/r1_int_peak.jsonl): the best
+    sustained mix of an FMA-pipe op (IMAD/IDP) with an ALU-pipe op (LOP3), G thread-ops/s."""
+    try:
+        rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "r1_int_peak.jsonl")) if l.strip()]
+        ops = {r["op"]: r["gops"] for r in rows if "op" in r}
+        return max(ops.values()), "measured (tools/int_peak.cu, best two-pipe mix)"
+    except Exception:
+        return INT32_PEAK_FALLBACK_GOPS, "nominal issue limit"
+
+
+def measured_traffic(workload, cells):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE fill-kernel launch from the committed `ncu --set full`
+    capture (profiles/r1_fill_traffic.json), if it was taken on this workload at this size; else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_fill_traffic.json")))
+        if t.get("workload") == workload and abs(t.get("cells", 0) - cells) <= 0.001 * cells:
+            return int(t["dram_bytes_read"] + t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -143,7 +166,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -280,12 +303,12 @@ def main():
         launches += st.kernel_launches
     barrier()
     tw1 = time.perf_counter()
-    clocks = sampler.stop(tw0, tw1) if sampler else None
     kern_ms_max = allmax(kern_ms)
     wall_ms_max = allmax((tw1 - tw0) * 1e3)
     total_cells = allsum(float(sb.cells))
     total_pairs = allsum(float(sb.n))
-    value = total_cells * args.steps / (kern_ms_max * 1e-3) / 1e9
+    # the timed region: K steps between barrier+synchronize, max over ranks (device-event total kept beside it)
+    value = total_cells * args.steps / (wall_ms_max * 1e-3) / 1e9
 
     # end to end through the C ABI with host buffers
     for _ in range(2):
@@ -300,6 +323,7 @@ def main():
         h2d += st.h2d_bytes; d2h += st.d2h_bytes; e_launch += st.kernel_launches
     barrier()
     te1 = time.perf_counter()
+    clocks = sampler.stop(tw0, te1) if sampler else None      # clocks over both timed regions (kernels, then e2e)
     e_ms_max = allmax((te1 - te0) * 1e3)
     e2e_val = total_cells * esteps / (e_ms_max * 1e-3) / 1e9
     bad = int((res["status"] != 0).sum())
@@ -309,23 +333,27 @@ def main():
         alg = algorithmic_bytes(sb)
         fill_avg_s = fill_ms / args.steps * 1e-3
         ach = alg / fill_avg_s / 1e9
-        int_peak = float(peaks.get("int32_gops", INT32_PEAK_FALLBACK_GOPS))
+        int_peak, int_how = measured_int_peak()
         line = {
             "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": kern_ms_max / args.steps, "higher_is_better": True,
+            "warmup": max(3, args.warmup), "ms_per_step": wall_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "pairs_per_s": total_pairs * args.steps / (kern_ms_max * 1e-3),
+            "pairs_per_s": total_pairs * args.steps / (wall_ms_max * 1e-3),
             "config": {"workload": desc, "pairs_per_gpu": int(sb.n), "cells_per_gpu": int(sb.cells),
                        "l2": "no flush needed: each step writes %.1f GB of traceback + row/column records, far above the 126 MB L2" % (sb.cells / 1e9),
                        "parallelism": f"{world} GPU(s), independent pair shards, no collective"},
-            "wall_ms_per_step": wall_ms_max / args.steps,
+            "device_event_ms_per_step": kern_ms_max / args.steps,
             "kernel_split_ms": {"profile": prof_ms / args.steps, "fill": fill_ms / args.steps, "traceback": tb_ms / args.steps},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
-                         "kernel": "yb_fill_kernel (dominant)",
+                         "frac": ach / peaks["hbm_gbs"], "traffic": measured_traffic(args.workload, sb.cells),
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback 6650 GB/s",
+                         "kernel": "yb_fill_kernel_w (dominant; one launch per ring-size bin)",
+                         "algorithmic_bytes_per_launch": alg,
                          "int32": {"achieved_gops": sb.cells / fill_avg_s / 1e9 * OPS_PER_CELL, "peak_gops": int_peak,
                                    "frac": sb.cells / fill_avg_s / 1e9 * OPS_PER_CELL / int_peak, "ops_per_cell": OPS_PER_CELL,
-                                   "note": "binding limit is the integer pipes, not HBM (SURVEY §8d)"}},
+                                   "peak_source": int_how,
+                                   "note": "the fill kernel is bound by integer instruction issue, not by HBM (SURVEY 8d); "
+                                           "ncu evidence in profiles/"}},
             "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d / esteps), "d2h_bytes_per_step": int(d2h / esteps),
                     "pairs_per_s": total_pairs * esteps / (e_ms_max * 1e-3), "steps": esteps, "failed_pairs": bad},
             "gpu_launches": int(launches),

@@ -148,6 +148,8 @@ struct JobInfo {           // host-side facts about one pair
 // One staging slot = one wave in flight.
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t binStream[NBINS] = {};    // fill kernels of the wider ring bins run beside the main one
+    cudaEvent_t binDone[NBINS] = {};
     cudaEvent_t ev[8] = {};
     DevBuf dIn, dRow, dCol, dTb, dScript, dOut, dQueue;
     PinBuf hIn, hScript, hOut;
@@ -308,6 +310,10 @@ int device_init(Device &d) {
     for (auto &s : d.slots) {
         CUDA_TRY(d, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         for (auto &e : s.ev) CUDA_TRY(d, cudaEventCreate(&e));
+        for (int b = 1; b < NBINS; ++b) {
+            CUDA_TRY(d, cudaStreamCreateWithFlags(&s.binStream[b], cudaStreamNonBlocking));
+            CUDA_TRY(d, cudaEventCreateWithFlags(&s.binDone[b], cudaEventDisableTiming));
+        }
     }
     for (int b = 0; b < NBINS; ++b) {
         FillFn fn = fill_fn(b);
@@ -576,14 +582,21 @@ int slot_launch(Device &d, Slot &s, bool h2d, bool d2h) {
         d.launches++;
     }
     CUDA_TRY(d, cudaEventRecord(s.ev[2], st));
-    for (int b = 0; b < NBINS; ++b) {
+    // The wide-ring bins hold few, long pairs (one warp each): they start first, on their own streams, and the
+    // bulk bin fills the machine around them -- launched back to back they would be a serial tail.
+    for (int b = NBINS - 1; b >= 0; --b) {
         int n = s.binStart[b + 1] - s.binStart[b];
         if (n <= 0) continue;
         int wpc = warps_of(b);
         int blocks = std::min((n + wpc - 1) / wpc, d.fillBlocks[b]);
-        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), st>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb, outs);
+        cudaStream_t bs = b == 0 ? st : s.binStream[b];
+        if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
+        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb, outs);
+        if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
         d.launches++;
     }
+    for (int b = 1; b < NBINS; ++b)
+        if (s.binStart[b + 1] - s.binStart[b] > 0) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[b], 0));
     CUDA_TRY(d, cudaEventRecord(s.ev[3], st));
     if (s.nValid > 0) {
         yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(metas, order, s.nValid, blob, tb, script, outs);
@@ -865,6 +878,8 @@ void yb_destroy(yb_ctx *ctx) {
             for (DevBuf *b : {&s.dIn, &s.dRow, &s.dCol, &s.dTb, &s.dScript, &s.dOut, &s.dQueue}) b->release();
             for (PinBuf *b : {&s.hIn, &s.hScript, &s.hOut}) b->release();
             for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+            for (auto &e : s.binDone) if (e) cudaEventDestroy(e);
+            for (auto &b : s.binStream) if (b) cudaStreamDestroy(b);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
     }
