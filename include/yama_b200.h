@@ -52,9 +52,10 @@ typedef struct {
     int32_t C, D, I;     /* the three node scores at grid point (M,N) (mz_yama.c:262-267)       */
     int32_t reserved;
     int64_t cells;       /* DP cells of this pair == tback_size of mz_yama.c:60-66              */
-    const uint8_t *script; /* m_new ops in the reference's own (reversed) order, mz_yama.c:278:
-                              0=C (both columns) 1=I (B column) 2=D (A column).  Owned by ctx,
-                              valid until the next yb_run_batch/yb_flush/yb_destroy.          */
+    const uint8_t *script; /* m_new ops in the reference's own (reversed) order, mz_yama.c:278, PACKED 2 bits
+                              per op: op i sits in bits 2*(i&3) of byte i>>2; codes 0=C (both columns)
+                              1=I (B column) 2=D (A column).  (m_new+3)/4 bytes.  Owned by ctx, valid until
+                              the next yb_run_batch/yb_flush/yb_destroy.  yb_script_unpack() expands it.   */
 } yb_result;
 
 typedef struct {
@@ -97,6 +98,9 @@ int64_t yb_submit(yb_ctx *ctx, const yb_job *job);            /* returns job id 
 int yb_flush(yb_ctx *ctx, yb_stats *stats);                   /* runs everything submitted      */
 int yb_fetch(yb_ctx *ctx, int64_t id, yb_result *out);
 void yb_clear(yb_ctx *ctx);
+
+/* Expands res->script into one byte per op (the reference's `script[]`, mz_yama.c:257-291): ops[i], i < m_new. */
+int yb_script_unpack(const yb_result *res, uint8_t *ops);
 
 /* ---- column assembly (mz_yama.c:293-313), host side ----------------------------------------- */
 /* Writes m_new*(K+L) bytes to out (caller-allocated). */

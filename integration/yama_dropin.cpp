@@ -64,7 +64,7 @@ struct KeyHash {
     size_t operator()(const Key &k) const { return (size_t)(k.a ^ (k.b * 0x9e3779b97f4a7c15ull)); }
 };
 
-struct Entry {            // one aligned job: its edit script in the reference's (reversed) order
+struct Entry {            // one aligned job: its edit script (packed 2 bits per op, see yama_b200.h)
     int32_t m_new = 0;
     size_t off = 0;       // into G.scripts
 };
@@ -364,7 +364,7 @@ void align_pending() {
         Entry e;
         e.m_new = res[i].m_new;
         e.off = G.scripts.size();
-        G.scripts.insert(G.scripts.end(), res[i].script, res[i].script + res[i].m_new);
+        G.scripts.insert(G.scripts.end(), res[i].script, res[i].script + (res[i].m_new + 3) / 4);   // packed, 2 bits per op
         G.table.emplace(G.pending[i].key, e);
     }
     G.pending.clear();

@@ -135,14 +135,17 @@ class Pool {
 };
 
 constexpr int NBINS = 4;
+constexpr int NB = 160;                    // launch-order buckets per ring bin
 const int kRingOf[NBINS] = {128, 512, 2048, 4096};
-constexpr int NSLOTS = 3;
+constexpr int TB_GROUP = 3;               // waves per traceback launch group
+constexpr int NSLOTS = 2 * TB_GROUP;      // one group filling while the previous one drains
 
 struct JobInfo {           // host-side facts about one pair
     int64_t cells = 0;     // tback_size of the reference
     int nSteps = 0;        // wavefront steps (schedule below); traceback bytes = 32 * nSteps
     int wmax = 0;          // widest band row
     int status = YB_OK;
+    int bucket = 0;        // launch-order bucket: ring bin * NB + quarter-octave of the cell count, descending
 };
 
 // One staging slot = one wave in flight.
@@ -152,8 +155,10 @@ struct Slot {
     cudaEvent_t binDone[NBINS] = {};
     cudaEvent_t ev[8] = {};
     DevBuf dIn, dRow, dCol, dTb, dScript, dOut, dQueue;
-    PinBuf hIn, hScript, hOut;
-    bool busy = false;
+    PinBuf hIn, hOut;
+    uint8_t *scriptDst = nullptr;          // where this wave's packed scripts go in the context's pinned store
+    bool filled = false;                   // H2D + K1 + K2 queued, K3 not yet
+    bool busy = false;                     // K3 + D2H queued, results not yet unpacked
     // the wave it holds
     int64_t first = 0, count = 0;
     std::vector<JobInfo> info;
@@ -161,7 +166,7 @@ struct Slot {
     struct Off { size_t blob, row, col; uint32_t script; };
     std::vector<Off> off;                  // per pair, dimension-only offsets into the pools
     std::vector<int> bucketCount;
-    size_t blobBytes = 0, metaBytes = 0, orderOff = 0, scriptWords = 0;
+    size_t blobBytes = 0, metaBytes = 0, orderOff = 0, tbBaseOff = 0, scriptWords = 0;
     int nValid = 0;
     int binStart[NBINS + 1] = {0, 0, 0, 0, 0};
 };
@@ -197,8 +202,9 @@ struct yb_ctx {
     size_t batchBlobBytes = 0;              // input bytes of the current batch (dimension-only estimate)
     size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
     int64_t wavePairs = 1 << 20;
+    bool ntStores = true;                   // full-line non-temporal staging stores (YB_NT=0 turns them off)
     // results of the last batch
-    std::unique_ptr<uint8_t[]> scriptStore;
+    uint8_t *scriptStore = nullptr;         // pinned (portable): the D2H copies of the waves land here directly
     size_t scriptStoreCap = 0;
     std::vector<uint64_t> scriptOff;
     // record/replay queue
@@ -242,6 +248,43 @@ double now_ms() {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Non-temporal copy of n bytes to a 64-byte aligned destination whose section is padded to whole 64-byte lines:
+// only full lines are streamed (the tail goes through a zero-padded line buffer), so write-combining buffers never
+// flush partially and the staging buffer is never read for ownership.
+inline void copy_nt64(unsigned char *dst, const unsigned char *src, size_t n) {
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+        __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+        __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+    }
+    if (i < n) {
+        alignas(64) unsigned char line[64] = {0};
+        memcpy(line, src + i, n - i);
+        for (int k = 0; k < 64; k += 16)
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + k), _mm_load_si128(reinterpret_cast<const __m128i *>(line + k)));
+    }
+}
+inline void pack_band_nt64(uint32_t *dst, const int32_t *lb, const int32_t *rb, int rowsTotal) {
+    int r = 0;
+    for (; r + 16 <= rowsTotal; r += 16)
+        for (int k = 0; k < 16; k += 4) {
+            __m128i l = _mm_loadu_si128(reinterpret_cast<const __m128i *>(lb + r + k));
+            __m128i h = _mm_loadu_si128(reinterpret_cast<const __m128i *>(rb + r + k));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + r + k), _mm_or_si128(l, _mm_slli_epi32(h, 16)));
+        }
+    if (r < rowsTotal) {
+        alignas(64) uint32_t line[16] = {0};
+        for (int k = 0; r + k < rowsTotal; ++k) line[k] = (uint32_t)lb[r + k] | ((uint32_t)rb[r + k] << 16);
+        for (int k = 0; k < 16; k += 4)
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + r + k), _mm_load_si128(reinterpret_cast<const __m128i *>(line + k)));
+    }
+}
 // band rows as LB | RB<<16 (both < 65536).  (Non-temporal stores were tried for the staging copies and lost:
 // the sections are small and rarely cache-line aligned, so write-combining buffers flush partially filled.)
 inline void pack_band(uint32_t *dst, const int32_t *lb, const int32_t *rb, int rowsTotal) {
@@ -284,15 +327,15 @@ __global__ void __launch_bounds__(WARPS * 32)
 yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                  const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
-                 PairOut *__restrict__ outs) {
-    fill_body<RING, WARPS>(metas, order, nPairs, queue, rowPool, colPool, tbPool, outs);
+                 const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs) {
+    fill_body<RING, WARPS>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs);
 }
 }  // namespace yb
 
 namespace {
 
 typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *, const ColRec *,
-                       unsigned char *, PairOut *);
+                       unsigned char *, const unsigned long long *, PairOut *);
 FillFn fill_fn(int bin) {
     switch (bin) {
         case 0: return yb_fill_kernel_w<128, 8>;
@@ -404,13 +447,14 @@ void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, ch
     ji.nSteps = nSteps;
 }
 
+inline bool dims_ok(const yb_job &j) { return j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1 && j.A && j.B && j.LB && j.RB; }
 inline int band_fmt(const yb_job &j) { return j.N < 65536 ? 0 : 1; }
 inline size_t sched_ints(const yb_job &j) { return (size_t)((j.M + 31) >> 5); }
 
 // bytes a job takes in the input blob: known from its dimensions alone (wave planning needs no band read)
 inline size_t blob_bytes(const yb_job &j) {
-    return align_up((size_t)j.K * j.M, 16) + align_up((size_t)j.L * j.N, 16) +
-           align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 16) + align_up(sched_ints(j) * 4, 16);
+    return align_up((size_t)j.K * j.M, 64) + align_up((size_t)j.L * j.N, 64) +
+           align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 64) + align_up(sched_ints(j) * 4, 64);
 }
 // Analyse + pack jobs [first, first+count) into the slot's pinned buffer, one pass over the caller's data:
 // everything but the traceback size of a pair follows from its dimensions, so blob / record / script offsets
@@ -426,14 +470,15 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     for (int64_t i = 0; i < count; ++i) {
         const yb_job &j = jobs[first + i];
         s.off[(size_t)i] = Slot::Off{blob, rows, cols, (uint32_t)words};
-        if (j.K < 1 || j.L < 1 || j.M < 1 || j.N < 1 || !j.A || !j.B || !j.LB || !j.RB) continue;
+        if (!dims_ok(j)) continue;
         blob += blob_bytes(j); rows += (size_t)j.M + 1; cols += (size_t)j.N + 1;
         words += ((size_t)j.M + j.N + 15) / 16;
     }
     s.first = first;
     s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
     s.orderOff = s.metaBytes;
-    const size_t dataOff = s.metaBytes + align_up((size_t)count * 4, 256);
+    s.tbBaseOff = s.orderOff + align_up((size_t)count * 4, 256);
+    const size_t dataOff = s.tbBaseOff + align_up((size_t)count * 8, 256);   // 64-B aligned: every section is
     CUDA_TRY(d, s.hIn.reserve(dataOff + blob));
     s.info.resize((size_t)count);
     s.scriptOff.resize((size_t)count);
@@ -456,12 +501,12 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
             msg[0] = 0;
             // the schedule goes straight to its place in the blob (after A, B and the band)
             size_t o = dataOff + of.blob;
-            const bool dimsOk = j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1 && j.A && j.B && j.LB && j.RB;
+            const bool dimsOk = dims_ok(j);
             size_t oA = o, oB = 0, oBand = 0, oSched = 0;
             if (dimsOk) {
-                oB = oA + align_up((size_t)j.K * j.M, 16);
-                oBand = oB + align_up((size_t)j.L * j.N, 16);
-                oSched = oBand + align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 16);
+                oB = oA + align_up((size_t)j.K * j.M, 64);
+                oBand = oB + align_up((size_t)j.L * j.N, 64);
+                oSched = oBand + align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 64);
             }
             analyse_one(ctx, j, ji, dimsOk ? reinterpret_cast<int *>(h + oSched) : nullptr, msg, sizeof msg);
             if (ji.status != YB_OK) {
@@ -477,12 +522,19 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
                 continue;
             }
             pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
-            pm.offA = oA; memcpy(h + oA, j.A, (size_t)j.K * j.M);
-            pm.offB = oB; memcpy(h + oB, j.B, (size_t)j.L * j.N);
+            pm.offA = oA; pm.offB = oB;
+            if (ctx->ntStores) {
+                copy_nt64(h + oA, j.A, (size_t)j.K * j.M);
+                copy_nt64(h + oB, j.B, (size_t)j.L * j.N);
+            } else {
+                memcpy(h + oA, j.A, (size_t)j.K * j.M);
+                memcpy(h + oB, j.B, (size_t)j.L * j.N);
+            }
             pm.offBand = oBand;
             pm.bandFmt = band_fmt(j);
             if (pm.bandFmt == 0) {
-                pack_band(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
+                if (ctx->ntStores) pack_band_nt64(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
+                else pack_band(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
             } else {
                 memcpy(h + oBand, j.LB, (size_t)(j.M + 1) * 4);
                 memcpy(h + oBand + (size_t)(j.M + 1) * 4, j.RB, (size_t)(j.M + 1) * 4);
@@ -493,6 +545,12 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
             pm.colBase = of.col;
             pm.scriptBase = of.script;
             metas[i] = pm;
+            if (ctx->ntStores) _mm_sfence();
+            {
+                const int lg = 63 - __builtin_clzll((unsigned long long)std::max<int64_t>(ji.cells, 1));
+                const int frac = lg >= 2 ? (int)((ji.cells >> (lg - 2)) & 3) : 0;
+                ji.bucket = bin_of(ji.wmax) * NB + (NB - 1 - std::min(NB - 1, lg * 4 + frac));
+            }
         }
     });
 
@@ -501,23 +559,18 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     // buckets of the cell count instead of a comparison sort
     const double t2 = now_ms();
     d.t_par += t2 - t1;
-    constexpr int NB = 160;
     s.bucketCount.assign((size_t)NBINS * NB, 0);
-    auto bucket_of = [](int64_t cells) {
-        int lg = 63 - __builtin_clzll((unsigned long long)std::max<int64_t>(cells, 1));
-        int frac = lg >= 2 ? (int)((cells >> (lg - 2)) & 3) : 0;
-        return NB - 1 - std::min(NB - 1, lg * 4 + frac);          // descending
-    };
     size_t tb = 0;
     int64_t kept = count;
+    unsigned long long *tbBase = reinterpret_cast<unsigned long long *>(h + s.tbBaseOff);
     for (int64_t i = 0; i < count; ++i) {
         const JobInfo &ji = s.info[(size_t)i];
         if (ji.status != YB_OK) continue;
         const size_t need = align_up((size_t)ji.nSteps * 32, 128);
         if (i > 0 && tb + need > maxTb) { kept = i; break; }
-        metas[i].tbBase = tb;
+        tbBase[i] = tb;
         tb += need;
-        s.bucketCount[(size_t)bin_of(ji.wmax) * NB + bucket_of(ji.cells)]++;
+        s.bucketCount[(size_t)ji.bucket]++;
     }
     count = kept;
     s.count = count;
@@ -539,7 +592,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
         for (int64_t i = 0; i < count; ++i) {
             const JobInfo &ji = s.info[(size_t)i];
             if (ji.status != YB_OK) continue;
-            order[s.bucketCount[(size_t)bin_of(ji.wmax) * NB + bucket_of(ji.cells)]++] = (int)i;
+            order[s.bucketCount[(size_t)ji.bucket]++] = (int)i;
         }
     }
     const double t3 = now_ms();
@@ -551,7 +604,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     CUDA_TRY(d, s.dScript.reserve(words * 4 + 64));
     CUDA_TRY(d, s.dOut.reserve((size_t)count * sizeof(PairOut) + 64));
     CUDA_TRY(d, s.dQueue.reserve(64));
-    CUDA_TRY(d, s.hScript.reserve(words * 4 + 64));
+    s.scriptDst = ctx->scriptStore + ctx->scriptOff[(size_t)first];   // the wave's scripts, in job order, in the batch store
     CUDA_TRY(d, s.hOut.reserve((size_t)count * sizeof(PairOut) + 64));
     d.t_reserve += now_ms() - t3;
     d.pack_ms += now_ms() - t0;
@@ -559,13 +612,13 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
 }
 
 // Enqueue one wave on its slot's stream.  Nothing here waits for the device.
-int slot_launch(Device &d, Slot &s, bool h2d, bool d2h) {
+// Enqueue H2D, K1 and K2 of one wave on its slot's stream.  Nothing here waits for the device.
+int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     const PairMeta *metas = static_cast<const PairMeta *>(s.dIn.p);
     const unsigned char *blob = static_cast<const unsigned char *>(s.dIn.p);
     RowRec *rows = static_cast<RowRec *>(s.dRow.p);
     ColRec *cols = static_cast<ColRec *>(s.dCol.p);
     unsigned char *tb = static_cast<unsigned char *>(s.dTb.p);
-    unsigned *script = static_cast<unsigned *>(s.dScript.p);
     PairOut *outs = static_cast<PairOut *>(s.dOut.p);
     const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
     int *queue = static_cast<int *>(s.dQueue.p);
@@ -591,28 +644,51 @@ int slot_launch(Device &d, Slot &s, bool h2d, bool d2h) {
         int blocks = std::min((n + wpc - 1) / wpc, d.fillBlocks[b]);
         cudaStream_t bs = b == 0 ? st : s.binStream[b];
         if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
-        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb, outs);
+        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
+                                                            reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs);
         if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
         d.launches++;
     }
     for (int b = 1; b < NBINS; ++b)
         if (s.binStart[b + 1] - s.binStart[b] > 0) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[b], 0));
     CUDA_TRY(d, cudaEventRecord(s.ev[3], st));
+    CUDA_TRY(d, cudaGetLastError());
+    s.filled = true;
+    d.waves++;
+    if (h2d) d.h2d_bytes += (int64_t)s.blobBytes;
+    d.t_launch += now_ms() - tl;
+    return YB_OK;
+}
+
+// Enqueue K3 and the D2H copies of a wave whose fill is already queued.  K3 is bound by the latency of the
+// longest pair's pointer chase, not by throughput, and the fill kernels leave it no registers to co-reside with:
+// launching it once per GROUP of waves, on their own streams at the same time, keeps that latency from being
+// paid once per wave.
+int slot_launch_traceback(Device &d, Slot &s, bool d2h) {
+    const PairMeta *metas = static_cast<const PairMeta *>(s.dIn.p);
+    const unsigned char *blob = static_cast<const unsigned char *>(s.dIn.p);
+    unsigned char *tb = static_cast<unsigned char *>(s.dTb.p);
+    unsigned *script = static_cast<unsigned *>(s.dScript.p);
+    PairOut *outs = static_cast<PairOut *>(s.dOut.p);
+    const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
+    cudaStream_t st = s.stream;
+    const double tl = now_ms();
+    CUDA_TRY(d, cudaEventRecord(s.ev[6], st));
     if (s.nValid > 0) {
-        yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(metas, order, s.nValid, blob, tb, script, outs);
+        yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(
+            metas, order, s.nValid, blob, tb, reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs);
         d.launches++;
     }
     CUDA_TRY(d, cudaEventRecord(s.ev[4], st));
     if (d2h) {
         CUDA_TRY(d, cudaMemcpyAsync(s.hOut.p, s.dOut.p, (size_t)s.count * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
         if (s.scriptWords)
-            CUDA_TRY(d, cudaMemcpyAsync(s.hScript.p, s.dScript.p, s.scriptWords * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(d, cudaMemcpyAsync(s.scriptDst, s.dScript.p, s.scriptWords * 4, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(d, cudaEventRecord(s.ev[5], st));
     CUDA_TRY(d, cudaGetLastError());
+    s.filled = false;
     s.busy = true;
-    d.waves++;
-    if (h2d) d.h2d_bytes += (int64_t)s.blobBytes;
     if (d2h) d.d2h_bytes += (int64_t)((size_t)s.count * sizeof(PairOut) + s.scriptWords * 4);
     d.t_launch += now_ms() - tl;
     return YB_OK;
@@ -621,7 +697,7 @@ int slot_launch(Device &d, Slot &s, bool h2d, bool d2h) {
 int slot_d2h(Device &d, Slot &s) {
     CUDA_TRY(d, cudaMemcpyAsync(s.hOut.p, s.dOut.p, (size_t)s.count * sizeof(PairOut), cudaMemcpyDeviceToHost, s.stream));
     if (s.scriptWords)
-        CUDA_TRY(d, cudaMemcpyAsync(s.hScript.p, s.dScript.p, s.scriptWords * 4, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(d, cudaMemcpyAsync(s.scriptDst, s.dScript.p, s.scriptWords * 4, cudaMemcpyDeviceToHost, s.stream));
     d.d2h_bytes += (int64_t)((size_t)s.count * sizeof(PairOut) + s.scriptWords * 4);
     return YB_OK;
 }
@@ -636,7 +712,7 @@ int slot_wait(Device &d, Slot &s) {
     cudaEventElapsedTime(&h, s.ev[0], s.ev[1]);
     cudaEventElapsedTime(&a, s.ev[1], s.ev[2]);
     cudaEventElapsedTime(&b, s.ev[2], s.ev[3]);
-    cudaEventElapsedTime(&c, s.ev[3], s.ev[4]);
+    cudaEventElapsedTime(&c, s.ev[6], s.ev[4]);
     cudaEventElapsedTime(&e, s.ev[4], s.ev[5]);
     d.h2d_ms += h; d.profile_ms += a; d.fill_ms += b; d.tb_ms += c; d.d2h_ms += e;
     d.kernel_ms += a + b + c;
@@ -648,14 +724,7 @@ int slot_wait(Device &d, Slot &s) {
 void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
     const double t0 = now_ms();
     const PairOut *outs = static_cast<const PairOut *>(s.hOut.p);
-    const uint32_t *hs = static_cast<const uint32_t *>(s.hScript.p);
-    static const std::array<uint32_t, 256> lut = [] {      // one packed byte (4 ops) -> 4 script bytes
-        std::array<uint32_t, 256> t{};
-        for (unsigned v = 0; v < 256; ++v)
-            t[v] = (v & 3u) | (((v >> 2) & 3u) << 8) | (((v >> 4) & 3u) << 16) | (((v >> 6) & 3u) << 24);
-        return t;
-    }();
-    d.pool->run(s.count, 128, [&](int64_t lo, int64_t hi) {
+    d.pool->run(s.count, 256, [&](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             const int64_t g = s.first + i;
             yb_result &r = results[g];
@@ -667,13 +736,8 @@ void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
             const PairOut &o = outs[i];
             r.status = o.status;
             r.m_new = o.m_new; r.C = o.C; r.D = o.D; r.I = o.I;
-            uint8_t *dst = ctx->scriptStore.get() + ctx->scriptOff[(size_t)g];
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(hs + s.scriptOff[(size_t)i]);
-            const int n = o.m_new;
-            int k = 0;
-            for (; k + 4 <= n; k += 4) { uint32_t w = lut[src[k >> 2]]; memcpy(dst + k, &w, 4); }
-            if (k < n) { uint32_t w = lut[src[k >> 2]]; memcpy(dst + k, &w, (size_t)(n - k)); }
-            r.script = dst;
+            // the device's 2-bit codes are the ABI's script format and the D2H copy put them in place
+            r.script = ctx->scriptStore + ctx->scriptOff[(size_t)g];
         }
     });
     for (int64_t i = 0; i < s.count; ++i)
@@ -744,7 +808,7 @@ struct Dispatcher {
     int ndev = 1, handed = 0;
     std::mutex mu;
     static size_t bytes_of(const yb_job &j) {
-        size_t b = sizeof(PairMeta) + 4;
+        size_t b = sizeof(PairMeta) + 12;
         if (j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1) b += blob_bytes(j);
         return b;
     }
@@ -770,15 +834,26 @@ struct Dispatcher {
     }
 };
 
-// One device's share of a batch: grab waves until none are left, keeping up to NSLOTS in flight.
+// One device's share of a batch: grab waves until none are left.  A wave's fill (H2D, K1, K2) is queued as soon as
+// it is packed; tracebacks and D2H copies are queued for TB_GROUP waves at a time; a slot is unpacked when the
+// ring comes back to it (NSLOTS waves later) or at the end.
 int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
     if (cudaSetDevice(d.id) != cudaSuccess) { d.err = "cudaSetDevice failed"; return YB_ERR_CUDA; }
-    int rc = YB_OK, next = 0;
+    int rc = YB_OK, next = 0, nFilled = 0;
+    int filledSlots[NSLOTS];
     int64_t lo = 0, hi = 0;                      // jobs grabbed but not yet packed
+    auto flush_group = [&]() -> int {
+        for (int k = 0; k < nFilled; ++k) {
+            int r2 = slot_launch_traceback(d, d.slots[filledSlots[k]], true);
+            if (r2 != YB_OK) return r2;
+        }
+        nFilled = 0;
+        return YB_OK;
+    };
     for (;;) {
         if (lo >= hi && !disp.grab(lo, hi)) break;
         Slot &s = d.slots[next];
-        next = (next + 1) % NSLOTS;
+        if (s.filled && (rc = flush_group()) != YB_OK) break;     // (only if NSLOTS < 2*TB_GROUP)
         if (s.busy) {                            // the wave launched NSLOTS rounds ago
             if ((rc = slot_wait(d, s)) != YB_OK) break;
             slot_unpack(ctx, d, s, results);
@@ -786,10 +861,15 @@ int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
         int64_t count = hi - lo;
         if ((rc = slot_pack(ctx, d, s, disp.jobs, lo, count, ctx->waveTbBytes)) != YB_OK) break;
         lo += count;
-        if ((rc = slot_launch(d, s, true, true)) != YB_OK) break;
+        if ((rc = slot_launch_fill(d, s, true)) != YB_OK) break;
+        filledSlots[nFilled++] = next;
+        next = (next + 1) % NSLOTS;
+        if (nFilled == TB_GROUP && (rc = flush_group()) != YB_OK) break;
     }
+    if (rc == YB_OK) rc = flush_group();
     for (int k = 0; k < NSLOTS; ++k) {           // drain, oldest first
         Slot &s = d.slots[(next + k) % NSLOTS];
+        if (s.filled) { cudaStreamSynchronize(s.stream); s.filled = false; }
         if (!s.busy) continue;
         int r2 = slot_wait(d, s);
         if (r2 != YB_OK) { if (rc == YB_OK) rc = r2; continue; }
@@ -798,19 +878,27 @@ int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
     return rc;
 }
 
-void prepare_script_store(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
+int prepare_script_store(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
     ctx->scriptOff.assign((size_t)n, 0);
     size_t tot = 0, blob = 0;
     for (int64_t i = 0; i < n; ++i) {
         ctx->scriptOff[(size_t)i] = tot;
-        if (jobs[i].M >= 1 && jobs[i].N >= 1) tot += (size_t)jobs[i].M + jobs[i].N;
+        if (dims_ok(jobs[i])) tot += (((size_t)jobs[i].M + jobs[i].N + 15) / 16) * 4;   // packed, whole words: the layout
+                                                                                       // of the waves' device script pools
         blob += Dispatcher::bytes_of(jobs[i]);
     }
     ctx->batchBlobBytes = blob;
-    if (tot + 16 > ctx->scriptStoreCap) {
-        ctx->scriptStore.reset(new uint8_t[tot + tot / 8 + 16]);
-        ctx->scriptStoreCap = tot + tot / 8 + 16;
+    if (tot + 64 > ctx->scriptStoreCap) {
+        if (ctx->scriptStore) cudaFreeHost(ctx->scriptStore);
+        ctx->scriptStore = nullptr;
+        ctx->scriptStoreCap = 0;
+        const size_t want = tot + tot / 4 + (1u << 20);
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return YB_ERR_CUDA; }
+        ctx->scriptStore = static_cast<uint8_t *>(p);
+        ctx->scriptStoreCap = want;
     }
+    return YB_OK;
 }
 
 template <class F>
@@ -861,6 +949,7 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_WAVE_MB")) ctx->waveInBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_MIN_MB")) ctx->waveMinBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
+    if (const char *e = getenv("YB_NT")) ctx->ntStores = atoi(e) != 0;
     if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
     for (auto &d : ctx->devs) {
         d.helpers = std::max(1, ctx->nThreads / (int)ctx->devs.size());
@@ -876,13 +965,14 @@ void yb_destroy(yb_ctx *ctx) {
         cudaSetDevice(d.id);
         for (auto &s : d.slots) {
             for (DevBuf *b : {&s.dIn, &s.dRow, &s.dCol, &s.dTb, &s.dScript, &s.dOut, &s.dQueue}) b->release();
-            for (PinBuf *b : {&s.hIn, &s.hScript, &s.hOut}) b->release();
+            for (PinBuf *b : {&s.hIn, &s.hOut}) b->release();
             for (auto &e : s.ev) if (e) cudaEventDestroy(e);
             for (auto &e : s.binDone) if (e) cudaEventDestroy(e);
             for (auto &b : s.binStream) if (b) cudaStreamDestroy(b);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
     }
+    if (ctx->scriptStore) cudaFreeHost(ctx->scriptStore);
     delete ctx;
 }
 
@@ -970,7 +1060,7 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     if (!ctx || n < 0 || (n > 0 && (!jobs || !results))) return YB_ERR_ARG;
     if (!ctx->scoresSet) { set_err(ctx, "yb_set_scores has not been called"); return YB_ERR_SCORES; }
     const double t0 = now_ms();
-    prepare_script_store(ctx, n, jobs);
+    if (prepare_script_store(ctx, n, jobs) != YB_OK) { set_err(ctx, "cudaHostAlloc failed for the script store"); return YB_ERR_CUDA; }
     for (auto &d : ctx->devs) { reset_stats(d); d.hasResident = false; }
     Dispatcher disp;
     disp.jobs = jobs; disp.n = n;
@@ -1003,7 +1093,7 @@ int yb_resident_load(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
     if (!ctx || n < 1 || !jobs) return YB_ERR_ARG;
     if (!ctx->scoresSet) { set_err(ctx, "yb_set_scores has not been called"); return YB_ERR_SCORES; }
     ctx->resJobs.assign(jobs, jobs + n);
-    prepare_script_store(ctx, n, jobs);
+    if (prepare_script_store(ctx, n, jobs) != YB_OK) { set_err(ctx, "cudaHostAlloc failed for the script store"); return YB_ERR_CUDA; }
     for (auto &d : ctx->devs) { reset_stats(d); d.hasResident = false; }
     // static, cell-balanced split: needs every pair's cell count first
     std::vector<int64_t> cells((size_t)n, 0);
@@ -1051,7 +1141,8 @@ int yb_resident_step(yb_ctx *ctx, yb_stats *stats) {
             return (int)YB_ERR_ARG;
         }
         if (cudaSetDevice(d.id) != cudaSuccess) return (int)YB_ERR_CUDA;
-        int r = slot_launch(d, d.slots[0], false, false);
+        int r = slot_launch_fill(d, d.slots[0], false);
+        if (r == YB_OK) r = slot_launch_traceback(d, d.slots[0], false);
         if (r != YB_OK) return r;
         return slot_wait(d, d.slots[0]);
     });
@@ -1123,12 +1214,18 @@ void yb_clear(yb_ctx *ctx) {
     ctx->arena.clear();
 }
 
+int yb_script_unpack(const yb_result *res, uint8_t *ops) {
+    if (!res || !ops || (res->m_new > 0 && !res->script)) return YB_ERR_ARG;
+    for (int i = 0; i < res->m_new; ++i) ops[i] = (uint8_t)((res->script[i >> 2] >> (2 * (i & 3))) & 3);
+    return YB_OK;
+}
+
 int yb_assemble(const yb_job *job, const yb_result *res, uint8_t *out) {
     if (!job || !res || !out || !res->script) return YB_ERR_ARG;
     const int K = job->K, L = job->L, W = K + L;
     int i = 0, j = 0, m = 0;
     for (int e = res->m_new - 1; e >= 0; --e) {             // mz_yama.c:300-309
-        int op = res->script[e];
+        const int op = (res->script[e >> 2] >> (2 * (e & 3))) & 3;
         uint8_t *dst = out + (size_t)m * W;
         if (op == FLAG_C) { ++i; ++j; }
         else if (op == FLAG_I) ++j;

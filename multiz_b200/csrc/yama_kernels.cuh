@@ -49,8 +49,9 @@ struct PairMeta {
     unsigned long long offSched;       // byte offset into the input blob: wavefront schedule, ceil(M/32) ints
     unsigned long long rowBase;        // index of row 0's RowRec in the RowRec pool (M+1 records)
     unsigned long long colBase;        // index of column 0's ColRec in the ColRec pool (N+1 records)
-    unsigned long long tbBase;         // byte offset of this pair's traceback matrix
     unsigned long long scriptBase;     // 32-bit word index of this pair's packed script (ceil((M+N)/16) words)
+    // (the byte offset of the pair's traceback matrix depends on the band, not only on the dimensions: it lives in a
+    //  separate per-wave array so that the host can fill the metas in parallel, before those offsets are known)
     int nSteps;                        // wavefront steps of this pair (host computed from the schedule)
     int bandFmt;                       // 0: M+1 words LB | RB<<16 (N < 65536);  1: M+1 ints LB, then M+1 ints RB
 };
@@ -270,7 +271,7 @@ __device__ __forceinline__ void
 fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
           const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
-          PairOut *__restrict__ outs) {
+          const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout per warp: [ RING ring records | 32 lanes x 2 mailbox records ]; ring is RING*16-aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -303,7 +304,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const int M = pm.M;
         const RowRec *rows = rowPool + pm.rowBase;
         const ColRec *cols = colPool + pm.colBase;
-        unsigned char *tb = tbPool + pm.tbBase;
+        unsigned char *tb = tbPool + __ldg(tbBase + p);
         const unsigned nKGE_hi = (unsigned)(-(pm.K * c_sc.gap_ext)) << 16;   // dp2a.lo weight of byte 1 (ndB)
         const int KGE = pm.K * c_sc.gap_ext;
         const int nSteps = pm.nSteps;
@@ -447,13 +448,14 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 __global__ void __launch_bounds__(128)
 yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                     const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
-                    unsigned *__restrict__ scriptPool, PairOut *__restrict__ outs) {
+                    const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
+                    PairOut *__restrict__ outs) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nPairs) return;
     const int p = order[idx];
     const PairMeta pm = metas[p];
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
-    const unsigned char *tb = tbPool + pm.tbBase;
+    const unsigned char *tb = tbPool + __ldg(tbBase + p);
     unsigned *script = scriptPool + pm.scriptBase;
     PairOut o = outs[p];
     int node;

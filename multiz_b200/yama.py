@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ABI_SYMBOLS = (
     "yb_create", "yb_destroy", "yb_last_error", "yb_device_count", "yb_set_scores",
     "yb_run_batch", "yb_resident_load", "yb_resident_step", "yb_resident_fetch",
-    "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band", "yb_plan_split", "yb_pair_facts",
+    "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band", "yb_plan_split", "yb_pair_facts", "yb_script_unpack",
 )
 
 
@@ -105,6 +105,8 @@ def load_library():
     lib.yb_assemble.restype = C.c_int
     lib.yb_check_band.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
     lib.yb_check_band.restype = C.c_int64
+    lib.yb_script_unpack.argtypes = [P(yb_result), C.c_void_p]
+    lib.yb_script_unpack.restype = C.c_int
     lib.yb_pair_facts.argtypes = [P(yb_job), P(C.c_int64), P(C.c_int32), P(C.c_int32), C.c_char_p, C.c_int]
     lib.yb_pair_facts.restype = C.c_int
     lib.yb_plan_split.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
@@ -242,10 +244,13 @@ class YamaB200:
 
     @staticmethod
     def script_of(res_row) -> np.ndarray:
+        """The edit script as one byte per op (the reference's script[], reversed order), from the packed result."""
         n = int(res_row["m_new"])
         if n == 0 or not int(res_row["script"]):
             return np.zeros(0, dtype=np.uint8)
-        return np.ctypeslib.as_array(C.cast(int(res_row["script"]), C.POINTER(C.c_uint8)), shape=(n,)).copy()
+        packed = np.ctypeslib.as_array(C.cast(int(res_row["script"]), C.POINTER(C.c_uint8)), shape=((n + 3) // 4,))
+        ops = (packed[:, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)[None, :]) & 3
+        return ops.reshape(-1)[:n].astype(np.uint8)
 
     def assemble(self, job_row, res_row) -> np.ndarray:
         """Column assembly of mz_yama.c:293-313 -> array [m_new, K+L]."""

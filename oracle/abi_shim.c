@@ -54,9 +54,15 @@ int yb_run_batch(yb_ctx *c, int64_t n, const yb_job *jobs, yb_result *res, yb_st
         memset(&res[i], 0, sizeof res[i]);
         long nc = oracle_check_band(j->M, j->N, j->LB, j->RB, c->err, sizeof c->err);
         if (nc < 0) { res[i].status = YB_ERR_BAND; rc = YB_ERR_BAND; continue; }
+        uint8_t *ops = c->scripts + off;
         int m = oracle_yama(j->A, j->K, j->M, j->B, j->L, j->N, j->LB, j->RB, c->ss, c->gop, c->gap_ext, NULL, NULL,
-                            cdi, c->scripts + off, c->err, sizeof c->err);
+                            cdi, ops, c->err, sizeof c->err);
         if (m < 0) { res[i].status = YB_ERR_TRACEBACK; rc = YB_ERR_TRACEBACK; continue; }
+        for (int k = 0; k < m; k++) {             /* pack in place, 2 bits per op (yama_b200.h) */
+            uint8_t op = ops[k];
+            if ((k & 3) == 0) ops[k >> 2] = 0;
+            ops[k >> 2] |= (uint8_t)(op << (2 * (k & 3)));
+        }
         res[i].m_new = m; res[i].C = cdi[0]; res[i].D = cdi[1]; res[i].I = cdi[2];
         res[i].cells = nc; res[i].script = c->scripts + off;
         cells += nc;
@@ -69,7 +75,7 @@ int yb_assemble(const yb_job *job, const yb_result *res, uint8_t *out) {
     const int K = job->K, L = job->L, W = K + L;
     int i = 0, j = 0, m = 0;
     for (int e = res->m_new - 1; e >= 0; --e, ++m) {
-        int op = res->script[e];
+        int op = (res->script[e >> 2] >> (2 * (e & 3))) & 3;
         uint8_t *dst = out + (size_t)m * W;
         if (op != 1) i++;
         if (op != 2) j++;

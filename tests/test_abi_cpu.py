@@ -85,7 +85,8 @@ def test_assemble_matches_reference_columns():
     for i in range(g.n):
         A, B, LB, RB = (np.ascontiguousarray(x) for x in g.problem(i))
         e = g.expected(i)
-        script = np.ascontiguousarray(e["script"])
+        ops = np.concatenate([e["script"], np.zeros((-len(e["script"])) % 4, np.uint8)]).reshape(-1, 4)
+        script = np.ascontiguousarray((ops << np.array([0, 2, 4, 6], np.uint8)).sum(axis=1).astype(np.uint8))   # 2 bits/op
         job = ymod.yb_job(A.shape[1], A.shape[0], B.shape[1], B.shape[0], A.ctypes.data, B.ctypes.data,
                           LB.ctypes.data, RB.ctypes.data)
         res = ymod.yb_result(0, e["m_new"], 0, 0, 0, 0, e["cells"], script.ctypes.data)
@@ -93,6 +94,9 @@ def test_assemble_matches_reference_columns():
         assert lib.yb_assemble(C.byref(job), C.byref(res), out.ctypes.data) == 0
         assert np.array_equal(out, e["al"]), i
     # a script that does not consume both alignments is refused (mz_yama.c:310-312)
+    unpacked = np.zeros(e["m_new"], np.uint8)
+    res = ymod.yb_result(0, e["m_new"], 0, 0, 0, 0, e["cells"], script.ctypes.data)
+    assert lib.yb_script_unpack(C.byref(res), unpacked.ctypes.data) == 0 and np.array_equal(unpacked, e["script"])
     bad = np.zeros(1, np.uint8)
     res = ymod.yb_result(0, 1, 0, 0, 0, 0, 0, bad.ctypes.data)
     if A.shape[0] + B.shape[0] > 2:
