@@ -250,18 +250,18 @@ __device__ __forceinline__ unsigned launder(unsigned x) {
     return x;
 }
 
-// Pre-shifted traceback flags (mz_yama.c:24-26,253): byte = fC | fD<<2 | fI<<4.
-// reference tie rule (mz_yama.c:138-154): x (from C) wins ties, then y (from D) only if strictly
-// greater than z (from I).  SH = bit position of this node's 2-bit field.  A node that does not exist
-// (mz_yama.c:163-165, :202-204) keeps the flag 0 the reference leaves there, so the stored byte is the
-// reference's byte and the traceback needs no band lookups.
+// Traceback byte of a cell: three 2-bit fields (C node at bit 0, D node at bit 2, I node at bit 4, like
+// mz_yama.c:24-26,253), each holding  e = notC | gt<<1  with  notC = "the from-C candidate is not the maximum"
+// and gt = "from-D is strictly greater than from-I" -- the two comparisons of the reference's tie rule
+// (mz_yama.c:138-154): e even -> came from C, e == 1 -> from I, e == 3 -> from D.  A node that does not exist
+// (mz_yama.c:163-165, :202-204) gets notC = 0, i.e. reads as "from C" = 0, the value the reference leaves there,
+// so the traceback needs no band lookups.  Every comparison becomes ONE predicated add of an immediate into the
+// running 32-bit word (4 cells per word), instead of a select chain.
 template <int SH>
-__device__ __forceinline__ int pick3(int x, int y, int z, bool exists, unsigned &flag) {
+__device__ __forceinline__ int pick3(int x, int y, int z, bool exists, unsigned &acc) {
     const int m = __vimax3_s32(x, y, z);
-    const bool notC = (x != m) && exists;
-    const bool fromD = (y > z);
-    const unsigned fyz = fromD ? (unsigned)(FLAG_D << SH) : (unsigned)(FLAG_I << SH);
-    flag = notC ? fyz : 0u;
+    if ((x != m) && exists) acc += 1u << (24 + SH);
+    if (y > z) acc += 2u << (24 + SH);
     return m;
 }
 
@@ -305,7 +305,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const RowRec *rows = rowPool + pm.rowBase;
         const ColRec *cols = colPool + pm.colBase;
         unsigned char *tb = tbPool + __ldg(tbBase + p);
-        const unsigned nKGE_hi = (unsigned)(-(pm.K * c_sc.gap_ext)) << 16;   // dp2a.lo weight of byte 1 (ndB)
+        const unsigned nKGE_hi = launder((unsigned)(-(pm.K * c_sc.gap_ext)) << 16);   // dp2a.lo weight of byte 1 (ndB)
         const int KGE = pm.K * c_sc.gap_ext;
         const int nSteps = pm.nSteps;
         const unsigned avYI_in = (unsigned)pm.K << 8, avZI_in = (unsigned)pm.K << 24;   // K*ndB, K*b10
@@ -391,14 +391,14 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 if (active) cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) + c16));
 
                 // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
-                unsigned fI, fC, fD;
                 int vI, vC, vD;
+                acc >>= 8;                                   // make room for this cell's byte (bits 24..31)
                 const bool hasI = c16 > LB16, hasC = c16 > LBp16;
                 {
                     int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
                     int y = Dl + dp4a_uu(cw.x, avYI, 0) * nGO;
                     int z = Il + dp4a_uu(cw.x, avZI, 0) * gIl;
-                    vI = pick3<4>(x, y, z, hasI, fI);
+                    vI = pick3<4>(x, y, z, hasI, acc);
                     vI = dp2a_lo_su(nKGE_hi, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
                 }
                 vI = hasI ? vI : MININT;
@@ -407,7 +407,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
                     int y = Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
                     int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
-                    vC = pick3<0>(x, y, z, hasC, fC);
+                    vC = pick3<0>(x, y, z, hasC, acc);
                     vC = dp2a_lo_su(w01, cw.y, vC);
                     vC = dp2a_hi_su(w23, cw.y, vC);
                     vC = dp2a_lo_su(w45, cw.z, vC);
@@ -418,10 +418,8 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     int x = Cu + dp4a_uu(cw.z, avXD, 0) * gCu;
                     int y = Du + dp4a_uu(cw.z, avYD, 0) * nGO;
                     int z = Iu + dp4a_uu(cw.z, avZD, 0) * gIu;
-                    vD = pick3<2>(x, y, z, true, fD) - eD;
+                    vD = pick3<2>(x, y, z, true, acc) - eD;
                 }
-                // traceback byte (mz_yama.c:253), bit for bit the reference's
-                acc = __funnelshift_r(acc, fC | fD | fI, 8);
                 if (active) {
                     sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, hasI ? E_both : Efirst);
                 }
@@ -473,7 +471,7 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
         if (r < 0 || c < 0 || n >= limit || node == 3) { status = -5; break; }   // mz_yama.c:274-276, :289-290
         unsigned st;
         if (r == 0) {
-            st = (unsigned)(FLAG_I << 4);                                   // row 0, mz_yama.c:91
+            st = 1u << 4;                                                   // row 0: from I (mz_yama.c:91), e = 1
         } else {
             if (((r - 1) >> 5) != blk) { blk = (r - 1) >> 5; offBlk = __ldg(sched + blk); }
             const unsigned lane = (unsigned)(r - 1) & 31u;
@@ -497,7 +495,7 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
         const int shift = node == FLAG_I ? 4 : (node == FLAG_D ? 2 : 0);
         r -= (node != FLAG_I);
         c -= (node != FLAG_D);
-        node = (int)((st >> shift) & 3u);
+        node = (int)((0x84u >> (2u * ((st >> shift) & 3u))) & 3u);      // e = notC | gt<<1  ->  0,2: C   1: I   3: D
     }
     if (n & 15) script[n >> 4] = accw;
     o.m_new = n;
