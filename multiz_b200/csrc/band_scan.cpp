@@ -12,8 +12,10 @@
 #error "compile with -DYB_BAND_SCAN_NAME=..."
 #endif
 
+// lanesOf(wmax, M) -> wavefront width B (32, 128, 256 ...) the pair will run with; the schedule depends on it
 extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ LB, const int32_t *__restrict__ RB,
-                                     int32_t *wmax, int32_t *__restrict__ sched, int32_t *nSteps) {
+                                     int32_t *wmax, int32_t *__restrict__ sched, int32_t *nSteps,
+                                     int (*lanesOf)(int, int), int32_t *lanes) {
     const int need = N < 10 ? N : 10;
     int bad = (LB[0] != 0) | (RB[M] != N);
     int64_t cells = 0;
@@ -42,21 +44,24 @@ extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ L
     }
     if (bad) return -1;
     *wmax = wm + 1;
-    // schedule: rows 32b+1..32b+32 run on lanes 0..31 with column = step - (OFF_b + lane)
+    // schedule: rows Bb+1..Bb+B run on lanes 0..B-1 with column = step - (OFF_b + lane)
+    const int B = lanesOf(wm + 1, M);
+    *lanes = B;
+    if (B <= 0) { *nSteps = 0; return cells; }             // wider than any kernel: the caller reports the limit
     int off = 0, steps = 8;
-    const int nblk = (M + 31) >> 5;
+    const int nblk = (M + B - 1) / B;
     for (int b = 0; b < nblk; ++b) {
         if (sched) sched[b] = off;
         if (b == nblk - 1) {
-            const int last = off + ((M - 1) & 31) + RB[M];
+            const int last = off + ((M - 1) % B) + RB[M];
             steps = ((last + 2) + 7) & ~7;
             break;
         }
-        int nd = 32;
-        const int r0 = 32 * b + 1;
-        const int r1 = (M - 32 < 32 * b + 32) ? M - 32 : 32 * b + 32;
+        int nd = B;
+        const int r0 = B * b + 1;
+        const int r1 = (M - B < B * b + B) ? M - B : B * b + B;
         for (int r = r0; r <= r1; ++r) {
-            const int v = RB[r + 1] - LB[r + 32] + 3;
+            const int v = RB[r + 1] - LB[r + B] + 3;
             nd = v > nd ? v : nd;
         }
         off += nd;
@@ -66,11 +71,12 @@ extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ L
 }
 
 #ifdef YB_BAND_SCAN_DISPATCH
-extern "C" int64_t yb_band_scan_avx2(int, int, const int32_t *, const int32_t *, int32_t *, int32_t *, int32_t *);
+extern "C" int64_t yb_band_scan_avx2(int, int, const int32_t *, const int32_t *, int32_t *, int32_t *, int32_t *,
+                                     int (*)(int, int), int32_t *);
 extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
-                                int32_t *nSteps) {
+                                int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes) {
     static const bool avx2 = __builtin_cpu_supports("avx2");
-    return avx2 ? yb_band_scan_avx2(M, N, LB, RB, wmax, sched, nSteps)
-                : YB_BAND_SCAN_NAME(M, N, LB, RB, wmax, sched, nSteps);
+    return avx2 ? yb_band_scan_avx2(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes)
+                : YB_BAND_SCAN_NAME(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes);
 }
 #endif

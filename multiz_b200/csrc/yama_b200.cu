@@ -35,7 +35,7 @@
 using namespace yb;
 
 extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
-                                int32_t *nSteps);   // band_scan.cpp
+                                int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes);   // band_scan.cpp
 
 namespace {
 
@@ -134,9 +134,12 @@ class Pool {
     bool stop_ = false;
 };
 
-constexpr int NBINS = 4;
+constexpr int NBINS = 5;
 constexpr int NB = 160;                    // launch-order buckets per ring bin
-const int kRingOf[NBINS] = {128, 512, 2048, 4096};
+// Kernel bins: ring entries (>= widest band row + 32), warps per pair G, pairs per CTA P.  Narrow bands and short
+// pairs run one warp per pair; wide bands on long pairs run one CTA per pair (one ring per pair -> full occupancy).
+struct BinCfg { int ring, G, P, minRows; };
+const BinCfg kBin[NBINS] = {{128, 1, 8, 0}, {512, 1, 8, 0}, {512, 4, 1, 192}, {2048, 8, 1, 0}, {4096, 8, 1, 0}};
 constexpr int TB_GROUP = 3;               // waves per traceback launch group
 constexpr int NSLOTS = 2 * TB_GROUP;      // one group filling while the previous one drains
 
@@ -145,6 +148,7 @@ struct JobInfo {           // host-side facts about one pair
     int nSteps = 0;        // wavefront steps (schedule below); traceback bytes = 32 * nSteps
     int wmax = 0;          // widest band row
     int status = YB_OK;
+    int bin = 0;           // kernel bin (ring size, warps per pair)
     int bucket = 0;        // launch-order bucket: ring bin * NB + quarter-octave of the cell count, descending
 };
 
@@ -168,14 +172,14 @@ struct Slot {
     std::vector<int> bucketCount;
     size_t blobBytes = 0, metaBytes = 0, orderOff = 0, tbBaseOff = 0, scriptWords = 0;
     int nValid = 0;
-    int binStart[NBINS + 1] = {0, 0, 0, 0, 0};
+    int binStart[NBINS + 1] = {};
 };
 
 struct Device {
     int id = -1;
     int sms = 0;
     Slot slots[NSLOTS];
-    int fillBlocks[NBINS] = {0, 0, 0, 0};
+    int fillBlocks[NBINS] = {};
     int helpers = 1;
     std::unique_ptr<Pool> pool;
     // accumulated stats of the current call
@@ -304,31 +308,36 @@ void parallel_for(int threads, int64_t n, int64_t chunk, F &&fn) {
     pool.run(n, chunk, fn);
 }
 
-int bin_of(int wmax) {
-    for (int b = 0; b < NBINS; ++b)
-        if (wmax + 32 <= kRingOf[b]) return b;
+int bin_of(int wmax, int M) {
+    if (wmax + 32 <= kBin[0].ring) return 0;
+    if (wmax + 32 <= kBin[1].ring) return M >= kBin[2].minRows ? 2 : 1;
+    if (wmax + 32 <= kBin[3].ring) return 3;
+    if (wmax + 32 <= kBin[4].ring) return 4;
     return -1;
 }
-
-// warps per CTA follow from the shared memory a ring of that size needs
-constexpr int warps_of(int bin) { return bin <= 1 ? 8 : (bin == 2 ? 4 : 1); }
+int lanes_of(int wmax, int M) {          // wavefront width of the pair's bin (0: no kernel takes it)
+    const int b = bin_of(wmax, M);
+    return b < 0 ? 0 : 32 * kBin[b].G;
+}
+inline int lg_of(int lanes) { return 31 - __builtin_clz((unsigned)lanes); }
 
 size_t fill_smem(int bin) {
-    // rings (RING*16-aligned, hence the slack) + 1 KB of mailboxes per warp
-    return (size_t)warps_of(bin) * ((size_t)kRingOf[bin] * 16 + 1024) + (size_t)kRingOf[bin] * 16;
+    // rings (RING*16-aligned, hence the slack) + 32 B of mailbox per lane + the queue slot
+    const BinCfg &c = kBin[bin];
+    return (size_t)c.P * ((size_t)c.ring * 16 + (size_t)c.G * 1024) + (size_t)c.ring * 16 + 16;
 }
 
 }  // namespace
 
 // ---- kernels with a runtime warps-per-CTA: thin wrappers around the template ---------------------
 namespace yb {
-template <int RING, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int RING, int G, int P>
+__global__ void __launch_bounds__(G * P * 32)
 yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                  const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
                  const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs) {
-    fill_body<RING, WARPS>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs);
+    fill_body<RING, G, P>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs);
 }
 }  // namespace yb
 
@@ -338,10 +347,11 @@ typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *
                        unsigned char *, const unsigned long long *, PairOut *);
 FillFn fill_fn(int bin) {
     switch (bin) {
-        case 0: return yb_fill_kernel_w<128, 8>;
-        case 1: return yb_fill_kernel_w<512, 8>;
-        case 2: return yb_fill_kernel_w<2048, 4>;
-        default: return yb_fill_kernel_w<4096, 1>;
+        case 0: return yb_fill_kernel_w<128, 1, 8>;
+        case 1: return yb_fill_kernel_w<512, 1, 8>;
+        case 2: return yb_fill_kernel_w<512, 4, 1>;
+        case 3: return yb_fill_kernel_w<2048, 8, 1>;
+        default: return yb_fill_kernel_w<4096, 8, 1>;
     }
 }
 
@@ -363,7 +373,7 @@ int device_init(Device &d) {
         size_t sm = fill_smem(b);
         CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         int occ = 0;
-        CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, warps_of(b) * 32, sm));
+        CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBin[b].G * kBin[b].P * 32, sm));
         if (occ < 1) occ = 1;
         d.fillBlocks[b] = occ * d.sms;
     }
@@ -394,20 +404,20 @@ int64_t check_band(int M, int N, const int *LB, const int *RB, char *msg, int ms
     return cells;
 }
 
-// Wavefront schedule (see K2): rows 32b+1..32b+32 run on lanes 0..31 with column = step - (OFF_b + lane).
-// OFF grows per block by at least 32 (lane 0 stays behind lane 31 of the previous block) and by enough
+// Wavefront schedule (see K2): rows Bb+1..Bb+B run on lanes 0..B-1 with column = step - (OFF_b + lane).
+// OFF grows per block by at least B (lane 0 stays behind the last lane of the previous block) and by enough
 // that a lane starts its next row only after the row below its current one has stopped reading it.
-// Returns the step count; sched (may be null) receives ceil(M/32) block offsets.
-int make_schedule(int M, const int *LB, const int *RB, int *sched) {
+// Returns the step count; sched (may be null) receives ceil(M/B) block offsets.
+int make_schedule(int M, const int *LB, const int *RB, int B, int *sched) {
     int off = 0;
-    const int nblk = (M + 31) >> 5;
+    const int nblk = (M + B - 1) / B;
     for (int b = 0; b < nblk; ++b) {
         if (sched) sched[b] = off;
-        int need = 32;
-        const int r0 = 32 * b + 1, r1 = std::min(M - 32, 32 * b + 32);
-        for (int r = r0; r <= r1; ++r) need = std::max(need, RB[r + 1] - LB[r + 32] + 3);
+        int need = B;
+        const int r0 = B * b + 1, r1 = std::min(M - B, B * b + B);
+        for (int r = r0; r <= r1; ++r) need = std::max(need, RB[r + 1] - LB[r + B] + 3);
         if (b == nblk - 1) {
-            int lane = (M - 1) & 31;
+            int lane = (M - 1) % B;
             int last = off + lane + RB[M];                 // step of the last cell
             return ((last + 2) + 7) & ~7;                  // +1 step to publish the final scores, whole 8-step groups
         }
@@ -426,12 +436,13 @@ void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, ch
     }
     // vectorised scan (band_scan.cpp): validation + cells + widest row + schedule in one pass; on a violation
     // the scalar loop below words the message as the reference does
-    int nSteps = 0;
-    int64_t cells = yb_band_scan(j.M, j.N, j.LB, j.RB, &ji.wmax, sched, &nSteps);
+    int nSteps = 0, lanes = 0;
+    int64_t cells = yb_band_scan(j.M, j.N, j.LB, j.RB, &ji.wmax, sched, &nSteps, lanes_of, &lanes);
     if (cells < 0) {
         cells = check_band(j.M, j.N, j.LB, j.RB, msg, msglen, &ji.wmax);
         if (cells < 0) { ji.status = YB_ERR_BAND; return; }
-        nSteps = make_schedule(j.M, j.LB, j.RB, sched);       // (unreachable unless the two scans disagree)
+        lanes = lanes_of(ji.wmax, j.M);                        // (unreachable unless the two scans disagree)
+        if (lanes > 0) nSteps = make_schedule(j.M, j.LB, j.RB, lanes, sched);
     }
     ji.cells = cells;
     if (j.K > ctx->maxDepth || j.L > 255) {
@@ -439,17 +450,18 @@ void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, ch
         if (msg) snprintf(msg, msglen, "profile depth K=%d L=%d exceeds the kernel limit (%d/255 rows)", j.K, j.L, ctx->maxDepth);
         return;
     }
-    if (bin_of(ji.wmax) < 0) {
+    if (lanes <= 0) {
         ji.status = YB_ERR_LIMIT;
-        if (msg) snprintf(msg, msglen, "band row of %d cells exceeds the kernel limit (%d)", ji.wmax, kRingOf[NBINS - 1] - 32);
+        if (msg) snprintf(msg, msglen, "band row of %d cells exceeds the kernel limit (%d)", ji.wmax, kBin[NBINS - 1].ring - 32);
         return;
     }
+    ji.bin = bin_of(ji.wmax, j.M);
     ji.nSteps = nSteps;
 }
 
 inline bool dims_ok(const yb_job &j) { return j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1 && j.A && j.B && j.LB && j.RB; }
 inline int band_fmt(const yb_job &j) { return j.N < 65536 ? 0 : 1; }
-inline size_t sched_ints(const yb_job &j) { return (size_t)((j.M + 31) >> 5); }
+inline size_t sched_ints(const yb_job &j) { return (size_t)((j.M + 31) >> 5); }   // upper bound (B >= 32)
 
 // bytes a job takes in the input blob: known from its dimensions alone (wave planning needs no band read)
 inline size_t blob_bytes(const yb_job &j) {
@@ -541,6 +553,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
             }
             pm.offSched = oSched;
             pm.nSteps = ji.nSteps;
+            pm.lgLanes = lg_of(32 * kBin[ji.bin].G);
             pm.rowBase = of.row;
             pm.colBase = of.col;
             pm.scriptBase = of.script;
@@ -549,7 +562,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
             {
                 const int lg = 63 - __builtin_clzll((unsigned long long)std::max<int64_t>(ji.cells, 1));
                 const int frac = lg >= 2 ? (int)((ji.cells >> (lg - 2)) & 3) : 0;
-                ji.bucket = bin_of(ji.wmax) * NB + (NB - 1 - std::min(NB - 1, lg * 4 + frac));
+                ji.bucket = ji.bin * NB + (NB - 1 - std::min(NB - 1, lg * 4 + frac));
             }
         }
     });
@@ -566,7 +579,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     for (int64_t i = 0; i < count; ++i) {
         const JobInfo &ji = s.info[(size_t)i];
         if (ji.status != YB_OK) continue;
-        const size_t need = align_up((size_t)ji.nSteps * 32, 128);
+        const size_t need = (size_t)ji.nSteps * 32 * kBin[ji.bin].G;       // one byte per lane and step
         if (i > 0 && tb + need > maxTb) { kept = i; break; }
         tbBase[i] = tb;
         tb += need;
@@ -640,12 +653,12 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     for (int b = NBINS - 1; b >= 0; --b) {
         int n = s.binStart[b + 1] - s.binStart[b];
         if (n <= 0) continue;
-        int wpc = warps_of(b);
-        int blocks = std::min((n + wpc - 1) / wpc, d.fillBlocks[b]);
+        const BinCfg &bc = kBin[b];
+        int blocks = std::min((n + bc.P - 1) / bc.P, d.fillBlocks[b]);
         cudaStream_t bs = b == 0 ? st : s.binStream[b];
         if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
-        fill_fn(b)<<<blocks, wpc * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
-                                                            reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs);
+        fill_fn(b)<<<blocks, bc.G * bc.P * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
+                                                                  reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs);
         if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
         d.launches++;
     }
@@ -1034,11 +1047,15 @@ int yb_pair_facts(const yb_job *job, int64_t *cells, int32_t *wmax, int32_t *nst
     const int nblk = (job->M + 31) >> 5;
     std::vector<int> s1((size_t)nblk + 1, -1), s2((size_t)nblk + 1, -1);
     int w1 = 0, w2 = 0, n1 = 0;
-    const int64_t c1 = yb_band_scan(job->M, job->N, job->LB, job->RB, &w1, s1.data(), &n1);
+    int lanes1 = 0;
+    const int64_t c1 = yb_band_scan(job->M, job->N, job->LB, job->RB, &w1, s1.data(), &n1, lanes_of, &lanes1);
     const int64_t c2 = check_band(job->M, job->N, job->LB, job->RB, msg, msglen, &w2);
     if (c2 < 0) return c1 < 0 ? YB_ERR_BAND : YB_ERR_LIMIT;
-    const int n2 = make_schedule(job->M, job->LB, job->RB, s2.data());
-    if (c1 != c2 || w1 != w2 || n1 != n2 || s1 != s2) return YB_ERR_LIMIT;
+    const int lanes2 = lanes_of(w2, job->M);
+    if (lanes2 <= 0) return YB_ERR_LIMIT;                      // wider than any kernel bin
+    const int n2 = make_schedule(job->M, job->LB, job->RB, lanes2, s2.data());
+    for (int b = (job->M + lanes2 - 1) / lanes2; b <= nblk; ++b) s1[(size_t)b] = s2[(size_t)b] = -1;
+    if (c1 != c2 || w1 != w2 || n1 != n2 || lanes1 != lanes2 || s1 != s2) return YB_ERR_LIMIT;
     if (cells) *cells = c2;
     if (wmax) *wmax = w2;
     if (nsteps) *nsteps = n2;

@@ -54,6 +54,8 @@ struct PairMeta {
     //  separate per-wave array so that the host can fill the metas in parallel, before those offsets are known)
     int nSteps;                        // wavefront steps of this pair (host computed from the schedule)
     int bandFmt;                       // 0: M+1 words LB | RB<<16 (N < 65536);  1: M+1 ints LB, then M+1 ints RB
+    int lgLanes;                       // log2 of the wavefront width: 32 lanes (one warp) ... 256 lanes (a CTA) per pair
+    int pad;
 };
 
 // LB[r] / RB[r] of a pair, whichever way the host packed them
@@ -79,14 +81,13 @@ struct __align__(16) RowRec {
     int RBn;                           //     RB[r+1] (RB[r] on the last row): how far the row below reads us
 };
 
-// Traceback matrix layout: the warp advances one anti-diagonal per step; lane l computes one cell per step t
-// (cell (r,c) with l = (r-1)&31 and t = c + off[r]).  The byte of (l,t) lives at  (t>>3)*256 + 8*l + (t&7):
-// every 4 steps a lane stores one 32-bit word, and two consecutive stores of the warp fill 256 contiguous
-// bytes.  A 32-B sector then holds 4 lanes x 8 steps -- the shape a traceback path likes: a diagonal move is
-// (l-1, t-2), an up move (l-1, t-1), a left move (l, t-1), so a path spends >= 4 moves in a sector before it
-// drops into the sector of (l-4, t-8), 288 bytes below.
-__device__ __forceinline__ unsigned long long tb_byte(unsigned lane, unsigned t) {
-    return (unsigned long long)(t >> 3) * 256ull + (lane << 3) + (t & 7u);
+// Traceback matrix layout: the wavefront (B = 32 << (lgLanes-5) lanes: one warp, or the warps of a CTA) advances one
+// anti-diagonal per step; lane l computes one cell per step t (cell (r,c) with l = (r-1) mod B and t = c + off[r]).
+// The byte of (l,t) lives at  (t>>3)*8B + 8*l + (t&7):  every 4 steps a lane stores one 32-bit word, and two
+// consecutive stores of a warp fill 256 contiguous bytes.  A 32-B sector holds 4 lanes x 8 steps -- the shape a
+// traceback path likes: a diagonal move is (l-1, t-2), an up move (l-1, t-1), a left move (l, t-1).
+__device__ __forceinline__ unsigned long long tb_byte(unsigned lane, unsigned t, int lgLanes) {
+    return ((unsigned long long)(t >> 3) << (lgLanes + 3)) + (lane << 3) + (t & 7u);
 }
 
 // Column record, 16 B.
@@ -182,7 +183,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
         rr.eD = 0; rr.w01 = rr.w23 = rr.w45 = 0u;
         const int lb = band.lb(r), lbp = r > 0 ? band.lb(r - 1) : 0;
         rr.LB16 = lb * 16; rr.RB16 = band.rb(r) * 16; rr.LBp16 = lbp * 16;
-        rr.off = r >= 1 ? sched[(r - 1) >> 5] + ((r - 1) & 31) : 0;
+        rr.off = r >= 1 ? sched[(r - 1) >> pm.lgLanes] + ((r - 1) & ((1 << pm.lgLanes) - 1)) : 0;
         rr.RBn = r < M ? band.rb(r + 1) : band.rb(r);
         if (r >= 1) {
             const unsigned char *now = A + (size_t)(r - 1) * K;
@@ -265,39 +266,53 @@ __device__ __forceinline__ int pick3(int x, int y, int z, bool exists, unsigned 
     return m;
 }
 
-// RING: ring entries, power of two, >= widest band row + 32.  WARPS: warps (= pairs in flight) per CTA.
-template <int RING, int WARPS>
+// RING: ring entries, power of two, >= widest band row + 32.
+// G:    warps per pair.  The 32*G lanes of a group form ONE wavefront (lane l owns rows l+1, l+1+32G, ...): G = 1 is a
+//       warp per pair, synchronised with __syncwarp(); G > 1 is a CTA per pair, synchronised with __syncthreads() --
+//       the form for wide bands, where one ring per PAIR (instead of per warp) keeps the shared-memory footprint small
+//       enough for full occupancy, and long pairs get 32*G cells per step.
+// P:    groups (= pairs in flight) per CTA; P > 1 only with G = 1.
+template <int RING, int G, int P>
 __device__ __forceinline__ void
 fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
           const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
           const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs) {
+    static_assert(G == 1 || P == 1, "several groups per CTA only for warp-sized groups");
+    constexpr int B = 32 * G;                                     // lanes of the wavefront
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout per warp: [ RING ring records | 32 lanes x 2 mailbox records ]; ring is RING*16-aligned
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr unsigned PER_WARP = (RING + 64) * 16;
+    // layout: [ P rings of RING records | P x B lanes x 2 mailbox records | queue slot ]; rings are RING*16-aligned
+    const int grp = (G == 1) ? (int)(threadIdx.x >> 5) : 0;
+    const int lane = (G == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;   // lane within the group's wavefront
     // dynamic smem base is at least 16-aligned; rings need RING*16 alignment for the (a&b)^c addressing
     const unsigned smem0 = (smem_u32(smem_raw) + RING * 16 - 1) & ~(unsigned)(RING * 16 - 1);
-    const unsigned ringAddr = smem0 + warp * RING * 16;
-    const unsigned boxAddr = smem0 + WARPS * RING * 16 + warp * 1024;
-    (void)PER_WARP;
+    const unsigned ringAddr = smem0 + grp * RING * 16;
+    const unsigned boxAddr = smem0 + P * RING * 16 + grp * B * 32;
+    const unsigned slotAddr = smem0 + P * RING * 16 + P * B * 32;
+    auto group_sync = [&]() { if (G == 1) __syncwarp(); else __syncthreads(); };
     const int GO = c_sc.gap_open;
     const int nGO = -GO;
     const unsigned E_both = pack16(nGO, nGO);
 
     // Mailbox of lane l: 32 B at boxAddr + 32*l, two 16-B slots; slot of column c is (c&1) ^ ((l>>2)&1)
     // (the swizzle keeps 128-bit accesses of a quarter-warp on distinct banks).  Lane l reads what lane
-    // l-1 wrote (lane 0 reads the ring), writes its own mailbox (lane 31 writes the ring).
+    // l-1 wrote (lane 0 reads the ring), writes its own mailbox (the last lane writes the ring).
     auto boxOf = [&](int l) { return boxAddr + 32u * l + (((unsigned)l >> 2) & 1u) * 16u; };
     const unsigned rdBase = launder((lane == 0) ? ringAddr : boxOf(lane - 1));
     const unsigned rdMask = (lane == 0) ? (unsigned)(RING * 16 - 16) : 16u;
-    const unsigned wrBase = launder((lane == 31) ? ringAddr : boxOf(lane));
-    const unsigned wrMask = (lane == 31) ? (unsigned)(RING * 16 - 16) : 16u;
+    const unsigned wrBase = launder((lane == B - 1) ? ringAddr : boxOf(lane));
+    const unsigned wrMask = (lane == B - 1) ? (unsigned)(RING * 16 - 16) : 16u;
 
     for (;;) {
         int slot = 0;
-        if (lane == 0) slot = atomicAdd(queue, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (G == 1) {
+            if (lane == 0) slot = atomicAdd(queue, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+        } else {
+            if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(slotAddr), "r"(atomicAdd(queue, 1)) : "memory");
+            __syncthreads();
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(slot) : "r"(slotAddr) : "memory");
+        }
         if (slot >= nPairs) break;
         const int p = order[slot];
         const PairMeta pm = metas[p];
@@ -311,8 +326,8 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const unsigned avYI_in = (unsigned)pm.K << 8, avZI_in = (unsigned)pm.K << 24;   // K*ndB, K*b10
         const unsigned E_c0 = pack16(nGO, 0);
 
-        // ---- row 0 (mz_yama.c:83-94) into the ring + its traceback bytes ------------------------
-        {
+        // ---- row 0 (mz_yama.c:83-94) into the ring (first warp of the group) ----------------------
+        if (G == 1 || lane < 32) {
             const int RB0 = rows[0].RB16 >> 4;
             const int RB1 = rows[0].RBn;
             int carry = 0;
@@ -360,9 +375,10 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         };
         if (r <= M) load_row(0);
         unsigned acc = 0;
+        const size_t tbWord = (size_t)lane * 2;               // this lane's word inside an 8-step group (see tb_byte)
         int Cl = MININT, Dl = MININT, Il = MININT, gCl = 0, gIl = 0;     // grid point (r, c-1)
         int Cd = MININT, Dd = MININT, Id = MININT, gCd = 0, gId = 0;     // grid point (r-1, c-1)
-        __syncwarp();
+        group_sync();
 
         for (int t4 = 0; t4 < nSteps; t4 += 4) {
 #pragma unroll
@@ -377,9 +393,9 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                         sts128(and_xor((unsigned)cc << 4, wrMask, wrBase), MININT, MININT, MININT, E_both);
                     // (b) final scores
                     if (r == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
-                    // (c) move 32 rows down
-                    r += 32;
-                    rp += 32 * (sizeof(RowRec) / 16);
+                    // (c) move one wavefront width down
+                    r += B;
+                    rp += B * (sizeof(RowRec) / 16);
                     if (r <= M) load_row(t4 + u);
                     else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; RBn = 0; }
                 }
@@ -424,15 +440,15 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, hasI ? E_both : Efirst);
                 }
                 // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
-                if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * 64 + lane * 2 + ((t4 >> 2) & 1)] = acc;
+                if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * (2 * B) + tbWord + ((t4 >> 2) & 1)] = acc;
                 Cl = vC; Dl = vD; Il = vI;
                 gCl = hasC ? nGO : 0; gIl = hasI ? nGO : 0;
                 Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
                 c16 += 16;
-                __syncwarp();
+                group_sync();
             }
         }
-        __syncwarp();
+        group_sync();
     }
 }
 
@@ -463,6 +479,8 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
     int r = pm.M, c = pm.N, n = 0, status = 0;
     const int limit = pm.M + pm.N;
     const unsigned tmax = (unsigned)pm.nSteps - 1u;
+    const int lg = pm.lgLanes;
+    const unsigned laneMask = (1u << lg) - 1u;
     int blk = -1, offBlk = 0;
     long long lastSec = -1;
     unsigned accw = 0;
@@ -473,17 +491,17 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
         if (r == 0) {
             st = 1u << 4;                                                   // row 0: from I (mz_yama.c:91), e = 1
         } else {
-            if (((r - 1) >> 5) != blk) { blk = (r - 1) >> 5; offBlk = __ldg(sched + blk); }
-            const unsigned lane = (unsigned)(r - 1) & 31u;
+            if (((r - 1) >> lg) != blk) { blk = (r - 1) >> lg; offBlk = __ldg(sched + blk); }
+            const unsigned lane = (unsigned)(r - 1) & laneMask;
             const unsigned t = min((unsigned)(c + offBlk) + lane, tmax);              // clamp: stay inside this pair
-            const unsigned long long at = tb_byte(lane, t);
+            const unsigned long long at = tb_byte(lane, t, lg);
             // The bytes were written a whole fill kernel ago: every new 32-B sector is a dependent miss to HBM.  A path
             // is mostly diagonal, so when it enters a sector the one it will need TB_AHEAD sectors later is known:
             // pull it into L2 now and the chain runs at L2 latency.
             const long long sec = (long long)(at >> 5);
             if (sec != lastSec) {
                 lastSec = sec;
-                const long long ahead = (long long)at - (long long)TB_AHEAD * 288;
+                const long long ahead = (long long)at - (long long)TB_AHEAD * ((8ll << lg) + 32);   // (l-4, t-8) per sector
                 if (ahead >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + ahead));
             }
             st = __ldg(tb + at);

@@ -87,3 +87,16 @@ def test_golden_fixtures(yama_ctx, name):
         assert r["status"] == 0
         g.check(i, dict(cdi=(r["C"], r["D"], r["I"]), m_new=r["m_new"], script=yama_ctx.script_of(r),
                         al=yama_ctx.assemble(jobs[i], r), cells=r["cells"]))
+
+
+def test_wide_bands_cta_per_pair(yama_ctx, oracle):
+    """Wide bands run one CTA per pair (4 or 8 warps form one wavefront, bins 2-4 of yama_b200.cu); short wide pairs
+    stay one warp per pair on the 512-entry ring (bin 1).  Rows straddle the 128- and 256-lane block sizes."""
+    cases = [  # (K, L, M, R)
+        (2, 1, 600, 150), (3, 2, 191, 150), (2, 1, 192, 150), (1, 1, 257, 120), (4, 1, 129, 200),    # bins 1 / 2
+        (2, 1, 1200, 400), (3, 1, 255, 400), (2, 2, 513, 380),                                       # bin 3
+        (2, 1, 2300, 1100), (1, 1, 1030, 1500),                                                      # bin 4
+    ]
+    for seed, (K, L, M, R) in enumerate(cases):
+        sb = SynthBatch(40 + seed, [K, K], [L, L], [M, max(1, M - 37)], R=R, indel=0.02)
+        _check(yama_ctx, oracle, [sb.problem(i) for i in range(sb.n)], f"wide K={K} L={L} M={M} R={R}")
