@@ -170,7 +170,8 @@ struct Slot {
     struct Off { size_t blob, row, col; uint32_t script; };
     std::vector<Off> off;                  // per pair, dimension-only offsets into the pools
     std::vector<int> bucketCount;
-    size_t blobBytes = 0, metaBytes = 0, orderOff = 0, tbBaseOff = 0, scriptWords = 0;
+    size_t blobBytes = 0, metaBytes = 0, orderOff = 0, longOff = 0, tbBaseOff = 0, scriptWords = 0;
+    int nLong = 0;                         // pairs whose traceback path gets a warp of its own
     int nValid = 0;
     int binStart[NBINS + 1] = {};
 };
@@ -489,7 +490,8 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     s.first = first;
     s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
     s.orderOff = s.metaBytes;
-    s.tbBaseOff = s.orderOff + align_up((size_t)count * 4, 256);
+    s.longOff = s.orderOff + align_up((size_t)count * 4, 256);
+    s.tbBaseOff = s.longOff + align_up((size_t)count * 4, 256);
     const size_t dataOff = s.tbBaseOff + align_up((size_t)count * 8, 256);   // 64-B aligned: every section is
     CUDA_TRY(d, s.hIn.reserve(dataOff + blob));
     s.info.resize((size_t)count);
@@ -602,10 +604,13 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
         }
         s.binStart[NBINS] = acc;
         s.nValid = acc;
+        int *longList = reinterpret_cast<int *>(h + s.longOff);
+        s.nLong = 0;
         for (int64_t i = 0; i < count; ++i) {
             const JobInfo &ji = s.info[(size_t)i];
             if (ji.status != YB_OK) continue;
             order[s.bucketCount[(size_t)ji.bucket]++] = (int)i;
+            if (jobs[first + i].M + jobs[first + i].N >= TB_LONG) longList[s.nLong++] = (int)i;
         }
     }
     const double t3 = now_ms();
@@ -687,7 +692,13 @@ int slot_launch_traceback(Device &d, Slot &s, bool d2h) {
     cudaStream_t st = s.stream;
     const double tl = now_ms();
     CUDA_TRY(d, cudaEventRecord(s.ev[6], st));
-    if (s.nValid > 0) {
+    if (s.nLong > 0) {
+        yb_traceback_long_kernel<<<(unsigned)((s.nLong + 3) / 4), 128, 0, st>>>(
+            metas, reinterpret_cast<const int *>(blob + s.longOff), s.nLong, blob, tb,
+            reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs);
+        d.launches++;
+    }
+    if (s.nValid > s.nLong) {
         yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(
             metas, order, s.nValid, blob, tb, reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs);
         d.launches++;
@@ -821,7 +832,7 @@ struct Dispatcher {
     int ndev = 1, handed = 0;
     std::mutex mu;
     static size_t bytes_of(const yb_job &j) {
-        size_t b = sizeof(PairMeta) + 12;
+        size_t b = sizeof(PairMeta) + 16;
         if (j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1) b += blob_bytes(j);
         return b;
     }
