@@ -286,6 +286,9 @@ def main():
         return float(t.item())
 
     sb, desc = make_batch(args.workload, seed + rank, args.scale)     # weak scaling: same work per GPU
+    if world > 1 and "YB_THREADS" not in os.environ:                   # the ranks of one box share its host cores
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        os.environ["YB_THREADS"] = str(max(2, (os.cpu_count() or 1) // max(1, local_world)))
     ctx = YamaB200(devices=[local])
     ctx.resident_load(sb.jobs)
 

@@ -100,3 +100,64 @@ def test_wide_bands_cta_per_pair(yama_ctx, oracle):
     for seed, (K, L, M, R) in enumerate(cases):
         sb = SynthBatch(40 + seed, [K, K], [L, L], [M, max(1, M - 37)], R=R, indel=0.02)
         _check(yama_ctx, oracle, [sb.problem(i) for i in range(sb.n)], f"wide K={K} L={L} M={M} R={R}")
+
+
+def test_batch_api_edges(yama_ctx, oracle):
+    """Empty batch, per-pair status for an invalid band / an over-deep profile inside a good batch (the good pairs
+    still align), and the queue form yb_submit / yb_flush / yb_fetch giving the same answers as yb_run_batch."""
+    import ctypes as C
+    from multiz_b200 import yama as ym
+    res, st = yama_ctx.run_batch(np.zeros(0, dtype=ym.JOB_DTYPE))
+    assert len(res) == 0 and st.pairs == 0
+
+    rng = np.random.default_rng(77)
+    good = [random_problem(rng, 2, 1, 40, 44, band="smooth"), random_problem(rng, 3, 2, 25, 30, band="ragged")]
+    A, B, LB, RB = random_problem(rng, 2, 1, 30, 35, band="smooth")
+    bad_band = (A, B, LB, RB.copy())
+    bad_band[3][10] = max(0, int(bad_band[2][10]) + 2)                # row narrower than min(N,10): mz_yama.c:63-65
+    deep = random_problem(rng, 300, 1, 12, 12, band="full")           # K > 255
+    jobs, keep = yama_ctx.make_jobs([good[0], bad_band, good[1], deep])
+    res, st = yama_ctx.run_batch(jobs, check=False)
+    assert [int(r["status"]) for r in res] == [0, -2, 0, -4]
+    msg = yama_ctx.lib.yb_last_error(yama_ctx.h).decode()
+    assert msg.startswith("RB[10] - LB[10] < 10"), msg                # the first failure, in the reference's wording
+    for i, k in ((0, 0), (2, 1)):
+        o = oracle.yama(*good[k], want_tback=False)
+        assert np.array_equal(yama_ctx.script_of(res[i]), o["script"])
+
+    lib = yama_ctx.lib
+    lib.yb_clear(yama_ctx.h)
+    ids = []
+    for (A, B, LB, RB) in good:
+        j, k2 = yama_ctx.make_jobs([(A, B, LB, RB)])
+        job = ym.yb_job(*[int(j[0][f]) for f in ("K", "M", "L", "N", "A", "B", "LB", "RB")])
+        ids.append(lib.yb_submit(yama_ctx.h, C.byref(job)))
+        del k2                                                        # submit copies: the inputs may go away
+    assert ids == [0, 1]
+    stq = ym.yb_stats()
+    assert lib.yb_flush(yama_ctx.h, C.byref(stq)) == 0 and stq.pairs == 2
+    for i, (A, B, LB, RB) in enumerate(good):
+        r = ym.yb_result()
+        assert lib.yb_fetch(yama_ctx.h, i, C.byref(r)) == 0
+        o = oracle.yama(A, B, LB, RB, want_tback=False)
+        assert (r.C, r.D, r.I) == tuple(int(x) for x in o["cdi"]) and r.m_new == o["m_new"]
+    lib.yb_clear(yama_ctx.h)
+
+
+def test_resident_path_matches_batch(yama_ctx, oracle):
+    """yb_resident_load/step/fetch (what bench.py times as `value`) returns exactly what yb_run_batch returns."""
+    sb = SynthBatch(321, [2, 3, 4, 5, 2, 8] * 20, [1, 1, 1, 1, 2, 8] * 20, list(np.random.default_rng(5).integers(5, 700, 120)), R=30)
+    res_b, _ = yama_ctx.run_batch(sb.jobs)
+    scripts_b = [yama_ctx.script_of(r) for r in res_b]
+    yama_ctx.resident_load(sb.jobs)
+    for _ in range(2):
+        st = yama_ctx.resident_step()
+    assert st.cells == sb.cells
+    res_r = yama_ctx.resident_fetch()
+    for i in range(sb.n):
+        assert tuple(res_r[i][f] for f in ("status", "m_new", "C", "D", "I", "cells")) == \
+               tuple(res_b[i][f] for f in ("status", "m_new", "C", "D", "I", "cells")), i
+        assert np.array_equal(yama_ctx.script_of(res_r[i]), scripts_b[i]), i
+    A, B, LB, RB = sb.problem(7)
+    o = oracle.yama(A, B, LB, RB, want_tback=False)
+    assert np.array_equal(scripts_b[7], o["script"])
