@@ -96,6 +96,7 @@ struct Globals {
     double gpu_ms = 0, kernel_ms = 0;
     int64_t cells = 0, batches = 0, jobs = 0, failed = 0;
     int passes = 0;
+    double child_ms = 0, final_ms = 0;      // wall time of the speculative passes / of the real pass
     bool debug = false;
     std::unordered_map<Key, int, KeyHash> failedKeys;   // debug: batch status of jobs that did not align
 } G;
@@ -257,17 +258,15 @@ void child_finish() {
     close(G.pipe_w);
 }
 
-// shape-valid placeholder: every column of A (gaps below), then every column of B (gaps above)
+// shape-valid placeholder: column i of A beside column i of B, the longer alignment's tail alone -- max(M,N)
+// columns, every column of A and of B exactly once and in order (the host rescoring of a placeholder block,
+// mafScoreRange, costs rows^2 * columns, so fewer columns is cheaper than "all of A, then all of B")
 void emit_dummy(const yb_job &job, uchar ***OAL, int *OM) {
-    const int m_new = job.M + job.N, W = job.K + job.L;
+    const int m_new = job.M > job.N ? job.M : job.N, W = job.K + job.L;
     uchar **al = alloc_al(m_new, W);
-    for (int i = 1; i <= job.M; ++i) {
-        memcpy(al[i], job.A + (size_t)(i - 1) * job.K, (size_t)job.K);
-        memset(al[i] + job.K, '-', (size_t)job.L);
-    }
-    for (int j = 1; j <= job.N; ++j) {
-        memset(al[job.M + j], '-', (size_t)job.K);
-        memcpy(al[job.M + j] + job.K, job.B + (size_t)(j - 1) * job.L, (size_t)job.L);
+    for (int i = 1; i <= m_new; ++i) {
+        if (i <= job.M) memcpy(al[i], job.A + (size_t)(i - 1) * job.K, (size_t)job.K); else memset(al[i], '-', (size_t)job.K);
+        if (i <= job.N) memcpy(al[i] + job.K, job.B + (size_t)(i - 1) * job.L, (size_t)job.L); else memset(al[i] + job.K, '-', (size_t)job.L);
     }
     G.lastDummy = al;
     G.lastDummyRows = W;
@@ -376,6 +375,7 @@ int run_batched(int argc, char **argv) {
     for (int pass = 1; pass <= maxPasses; ++pass) {
         int fds[2];
         if (pipe(fds) != 0) break;
+        const double tc = now_ms();
         fflush(nullptr);
         pid_t pid = fork();
         if (pid < 0) { close(fds[0]); close(fds[1]); break; }
@@ -395,21 +395,25 @@ int run_batched(int argc, char **argv) {
         int status = 0;
         while (waitpid(pid, &status, 0) < 0 && errno == EINTR) {}
         ++G.passes;
+        G.child_ms += now_ms() - tc;
         const bool any = !G.pending.empty();
         align_pending();
         if (!clean || !any || end.tainted == 0) break;
     }
     G.mode = REPLAY;
-    return ref_tool_main(argc, argv);
+    const double tf = now_ms();
+    const int rc = ref_tool_main(argc, argv);
+    G.final_ms = now_ms() - tf;
+    return rc;
 }
 
 void print_stats() {
     if (!G.stats) return;
     fprintf(stderr,
             "yama_b200: passes=%d batches=%lld jobs=%lld failed=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
-            "gpu_ms=%.2f kernel_ms=%.2f devices=%d\n",
+            "gpu_ms=%.2f kernel_ms=%.2f speculative_ms=%.0f final_ms=%.0f devices=%d\n",
             G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.failed, (long long)G.cells, (unsigned long long)G.calls,
-            (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms,
+            (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.child_ms, G.final_ms,
             G.ctx ? yb_device_count(G.ctx) : 0);
 }
 
