@@ -323,7 +323,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const unsigned nKGE_hi = launder((unsigned)(-(pm.K * c_sc.gap_ext)) << 16);   // dp2a.lo weight of byte 1 (ndB)
         const int KGE = pm.K * c_sc.gap_ext;
         const int nSteps = pm.nSteps;
-        const unsigned avYI_in = (unsigned)pm.K << 8, avZI_in = (unsigned)pm.K << 24;   // K*ndB, K*b10
+        const int KnGO = pm.K * nGO;                        // I-node y / z charge per residue / per closing gap of B
         const unsigned E_c0 = pack16(nGO, 0);
 
         // ---- row 0 (mz_yama.c:83-94) into the ring (first warp of the group) ----------------------
@@ -356,9 +356,10 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         // ---- per-lane row state --------------------------------------------------------------------
         int r = lane + 1;
         const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
-        unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avYI = 0, avZI = 0, avXD = 0, avYD = 0, avZD = 0;
+        unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avXD = 0, avYD = 0, avZD = 0;
+        int gIrow = 0;
         unsigned w01 = 0, w23 = 0, w45 = 0, Efirst = 0;
-        int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBp16 = 0, RBn = 0, c16 = 0;
+        int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBp16 = 0, c16 = 0;
         auto load_row = [&](int t) {
             uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
             avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
@@ -366,10 +367,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
             w01 = q2.x; w23 = q2.y; w45 = q2.z; LB16 = (int)q2.w;
             RB16 = (int)q3.x; LBp16 = (int)q3.y;
             c16 = (t - (int)q3.z) * 16;
-            RBn = (int)q3.w;
-            const bool inner = r < M;                               // mz_yama.c:123: no I-node gap-open on the last row
-            avYI = inner ? avYI_in : 0u;
-            avZI = inner ? avZI_in : 0u;
+            gIrow = r < M ? KnGO : 0;                               // mz_yama.c:123: no I-node gap-open on the last row
             // first cell of the row: its I node never exists, its C node only if the band moved right
             Efirst = (LB16 > LBp16) ? E_c0 : 0u;
         };
@@ -387,17 +385,26 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 const uint4 up = lds128(and_xor((unsigned)c16, rdMask, rdBase));
                 if (c16 > RB16) {
                     // ---- this lane finished its row -----------------------------------------------------
-                    // (a) the row below keeps reading us up to its own right bound: stale dp[] entries
+                    // (a) the row below keeps reading us up to its own right bound: stale dp[] entries (mz_yama.c:93-94).
+                    //     A mailbox lane of a warp-sized wavefront fills both of its slots (the reader took our last
+                    //     column at the top of this step); the ring lane, and CTA-sized wavefronts whose reader may sit
+                    //     in another warp, write them column by column.
+                    if (G == 1 && lane != B - 1) {
+                        sts128(wrBase, MININT, MININT, MININT, E_both);
+                        sts128(wrBase ^ 16u, MININT, MININT, MININT, E_both);
+                    } else {
+                        const int RBn = __ldg(reinterpret_cast<const int *>(rp) + 15);      // RowRec::RBn
 #pragma unroll 1
-                    for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
-                        sts128(and_xor((unsigned)cc << 4, wrMask, wrBase), MININT, MININT, MININT, E_both);
+                        for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
+                            sts128(and_xor((unsigned)cc << 4, wrMask, wrBase), MININT, MININT, MININT, E_both);
+                    }
                     // (b) final scores
                     if (r == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
                     // (c) move one wavefront width down
                     r += B;
                     rp += B * (sizeof(RowRec) / 16);
                     if (r <= M) load_row(t4 + u);
-                    else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; RBn = 0; }
+                    else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; }
                 }
                 const int Cu = (int)up.x, Du = (int)up.y, Iu = (int)up.z;
                 const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
@@ -412,8 +419,8 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 const bool hasI = c16 > LB16, hasC = c16 > LBp16;
                 {
                     int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
-                    int y = Dl + dp4a_uu(cw.x, avYI, 0) * nGO;
-                    int z = Il + dp4a_uu(cw.x, avZI, 0) * gIl;
+                    int y = Dl + (int)__byte_perm(cw.x, 0, 0x4441) * gIrow;       // K*ndB opens (mz_yama.c:131-134)
+                    int z = Il + (int)(cw.x >> 24) * gIl;                         // K*b10, if I(r,c-1) exists
                     vI = pick3<4>(x, y, z, hasI, acc);
                     vI = dp2a_lo_su(nKGE_hi, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
                 }
@@ -442,7 +449,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
                 if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * (2 * B) + tbWord + ((t4 >> 2) & 1)] = acc;
                 Cl = vC; Dl = vD; Il = vI;
-                gCl = hasC ? nGO : 0; gIl = hasI ? nGO : 0;
+                gCl = hasC ? nGO : 0; gIl = hasI ? gIrow : 0;
                 Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
                 c16 += 16;
                 group_sync();
