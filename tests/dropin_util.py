@@ -95,3 +95,38 @@ def check_speculation(report):
             assert st["misses"] == 0, last
         else:
             assert st["misses"] <= max(2, 0.01 * st["calls"]), last
+
+
+def run_roast(multiz_tool, workdir, tree, env=None):
+    """The reference's own roast driver (oracle/_ref/bin/roast, which exec's `multiz` and `maf_project` from PATH,
+    auto_mz.c:19-20) with `multiz_tool` first on PATH.  Returns the output MAF without '#' lines (they embed getpid())."""
+    import shutil as _sh
+    refbin = os.path.dirname(REF_MULTIZ)
+    bindir = os.path.join(workdir, "_bin")
+    os.makedirs(bindir, exist_ok=True)
+    for name, src in (("multiz", multiz_tool), ("maf_project", os.path.join(refbin, "maf_project")),
+                      ("roast", os.path.join(refbin, "roast"))):
+        dst = os.path.join(bindir, name)
+        if os.path.lexists(dst):
+            os.remove(dst)
+        os.symlink(src, dst)
+    e = dict(os.environ)
+    e.update(env or {})
+    e["PATH"] = bindir + os.pathsep + e.get("PATH", "")
+    files = sorted(f for f in os.listdir(workdir) if f.endswith(".sing.maf"))
+    out = os.path.join(workdir, "roast_out.maf")
+    if os.path.exists(out):
+        os.remove(out)
+    p = subprocess.run([os.path.join(bindir, "roast"), f"T={workdir}", "E=ref", tree] + files + [out], cwd=workdir, env=e,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    assert p.returncode == 0, p.stderr.decode()[-500:]
+    _ = _sh
+    return b"".join(l for l in open(out, "rb").read().splitlines(keepends=True) if not l.startswith(b"#"))
+
+
+def make_roast_dataset(workdir, ref_len, n_species, seed):
+    from tools.mafsynth import make_dataset
+    os.makedirs(workdir, exist_ok=True)
+    for p in make_dataset(workdir, ref_len=ref_len, n_species=n_species, seed=seed):
+        sp = os.path.basename(p).split(".")[1]
+        os.replace(p, os.path.join(workdir, f"ref.{sp}.sing.maf"))

@@ -7,7 +7,8 @@ import os
 
 import pytest
 
-from dropin_util import REF_MULTIZ, SHIM_MULTIZ, check_against_live_reference, check_golden_cases, check_speculation
+from dropin_util import (REF_MULTIZ, SHIM_MULTIZ, check_against_live_reference, check_golden_cases, check_speculation,
+                         make_roast_dataset, run_roast)
 
 pytestmark = pytest.mark.skipif(not os.path.exists(SHIM_MULTIZ),
                                 reason="integration/_ref/bin/multiz_shim not built (needs /root/reference at build time)")
@@ -24,3 +25,17 @@ def test_fresh_data_against_reference_binary(tmp_path):
                                        env={"YB_DROPIN_STATS": "1"})
     # v=1 needs one speculative pass, v=0 two (stage 2 consumes stage 1's output, mz_preyama.c:335)
     check_speculation(rep)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin not built")
+def test_roast_driver_runs_the_dropin(tmp_path):
+    """The reference's roast (auto_mz.c) exec's `multiz` from PATH; with the drop-in there its progressive alignment
+    of a 4-species tree (v=1 and v=0 merges, maf_project in between) is unchanged apart from the '#' provenance lines."""
+    import shutil
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    make_roast_dataset(a, 40_000, 3, seed=8)
+    shutil.copytree(a, b)
+    tree = "((ref sp1) (sp2 sp3))"
+    want = run_roast(REF_MULTIZ, a, tree)
+    got = run_roast(SHIM_MULTIZ, b, tree)
+    assert len(want) > 10_000 and got == want

@@ -5,7 +5,8 @@ import os
 
 import pytest
 
-from dropin_util import GPU_MULTIC, GPU_MULTIZ, REF_MULTIZ, check_against_live_reference, check_golden_cases, check_speculation, run_tool
+from dropin_util import (GPU_MULTIC, GPU_MULTIZ, REF_MULTIZ, check_against_live_reference, check_golden_cases,
+                         check_speculation, make_roast_dataset, run_roast, run_tool)
 
 pytestmark = [pytest.mark.gpu]
 
@@ -52,3 +53,17 @@ def test_multic_same_boundary(tmp_path):
     rc_o, out_o, err = run_tool(GPU_MULTIC, argv, d)
     assert rc_r == rc_o, err.decode()[-300:]
     assert out_o == out_r
+
+
+def test_roast_five_species_tree(tmp_path):
+    """configs[3] in miniature: the reference's roast driver over a 5-species tree, 300 kb, with the GPU multiz on PATH
+    (all visible GPUs); identical to the run with the reference's multiz apart from '#' lines."""
+    import shutil
+    _need(GPU_MULTIZ); _need(REF_MULTIZ)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    make_roast_dataset(a, 300_000, 4, seed=12)
+    shutil.copytree(a, b)
+    tree = "((ref sp1) ((sp2 sp3) sp4))"
+    want = run_roast(REF_MULTIZ, a, tree)
+    got = run_roast(GPU_MULTIZ, b, tree)
+    assert len(want) > 100_000 and got == want
