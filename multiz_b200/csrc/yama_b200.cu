@@ -77,7 +77,7 @@ class Pool {
         for (int t = 0; t < helpers; ++t) th_.emplace_back([this] { loop(); });
     }
     ~Pool() {
-        { std::lock_guard<std::mutex> g(mu_); stop_ = true; ++gen_; }
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; ++gen_; genFast_.store(gen_, std::memory_order_release); }
         cv_.notify_all();
         for (auto &t : th_) t.join();
     }
@@ -92,10 +92,13 @@ class Pool {
             std::lock_guard<std::mutex> g(mu_);
             fn_ = &f; n_ = n; chunk_ = chunk; nchunks_ = nchunks;
             next_.store(0); pending_ = (int)th_.size();
+            pendingFast_.store(pending_, std::memory_order_release);
             ++gen_;
+            genFast_.store(gen_, std::memory_order_release);
         }
         cv_.notify_all();
         work();
+        for (int spin = 0; spin < 20000 && pendingFast_.load(std::memory_order_acquire) != 0; ++spin) _mm_pause();
         std::unique_lock<std::mutex> g(mu_);
         done_.wait(g, [this] { return pending_ == 0; });
         fn_ = nullptr;
@@ -112,6 +115,8 @@ class Pool {
     void loop() {
         uint64_t seen = 0;
         for (;;) {
+            // runs of one batch follow each other within microseconds: poll briefly before sleeping on the condvar
+            for (int spin = 0; spin < 4000 && genFast_.load(std::memory_order_acquire) == seen; ++spin) _mm_pause();
             {
                 std::unique_lock<std::mutex> g(mu_);
                 cv_.wait(g, [&] { return gen_ != seen; });
@@ -120,6 +125,7 @@ class Pool {
             }
             work();
             std::lock_guard<std::mutex> g(mu_);
+            pendingFast_.fetch_sub(1, std::memory_order_release);
             if (--pending_ == 0) done_.notify_one();
         }
     }
@@ -131,6 +137,8 @@ class Pool {
     std::atomic<int64_t> next_{0};
     int pending_ = 0;
     uint64_t gen_ = 0;
+    std::atomic<uint64_t> genFast_{0};
+    std::atomic<int> pendingFast_{0};
     bool stop_ = false;
 };
 
@@ -172,6 +180,7 @@ struct Slot {
     std::vector<int> bucketCount;
     size_t blobBytes = 0, metaBytes = 0, orderOff = 0, longOff = 0, tbBaseOff = 0, scriptWords = 0;
     int nLong = 0;                         // pairs whose traceback path gets a warp of its own
+    int tbLong = TB_LONG;                  // ... those with at least this many moves
     int nValid = 0;
     int binStart[NBINS + 1] = {};
 };
@@ -207,6 +216,7 @@ struct yb_ctx {
     size_t batchBlobBytes = 0;              // input bytes of the current batch (dimension-only estimate)
     size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
     int64_t wavePairs = 1 << 20;
+    int tbLong = TB_LONG;                   // paths of at least this many moves: warp-per-path traceback (YB_TB_LONG)
     bool ntStores = true;                   // full-line non-temporal staging stores (YB_NT=0 turns them off)
     // results of the last batch
     uint8_t *scriptStore = nullptr;         // pinned (portable): the D2H copies of the waves land here directly
@@ -606,11 +616,12 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
         s.nValid = acc;
         int *longList = reinterpret_cast<int *>(h + s.longOff);
         s.nLong = 0;
+        s.tbLong = ctx->tbLong;
         for (int64_t i = 0; i < count; ++i) {
             const JobInfo &ji = s.info[(size_t)i];
             if (ji.status != YB_OK) continue;
             order[s.bucketCount[(size_t)ji.bucket]++] = (int)i;
-            if (jobs[first + i].M + jobs[first + i].N >= TB_LONG) longList[s.nLong++] = (int)i;
+            if (jobs[first + i].M + jobs[first + i].N >= s.tbLong) longList[s.nLong++] = (int)i;
         }
     }
     const double t3 = now_ms();
@@ -692,17 +703,23 @@ int slot_launch_traceback(Device &d, Slot &s, bool d2h) {
     cudaStream_t st = s.stream;
     const double tl = now_ms();
     CUDA_TRY(d, cudaEventRecord(s.ev[6], st));
+    // the warp-per-path kernel (issue-bound) runs beside the thread-per-pair kernel (latency-bound), on a side stream
     if (s.nLong > 0) {
-        yb_traceback_long_kernel<<<(unsigned)((s.nLong + 3) / 4), 128, 0, st>>>(
+        cudaStream_t ls = s.binStream[1];
+        CUDA_TRY(d, cudaStreamWaitEvent(ls, s.ev[6], 0));
+        yb_traceback_long_kernel<<<(unsigned)((s.nLong + 3) / 4), 128, 0, ls>>>(
             metas, reinterpret_cast<const int *>(blob + s.longOff), s.nLong, blob, tb,
             reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs);
+        CUDA_TRY(d, cudaEventRecord(s.binDone[1], ls));
         d.launches++;
     }
     if (s.nValid > s.nLong) {
         yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(
-            metas, order, s.nValid, blob, tb, reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs);
+            metas, order, s.nValid, blob, tb, reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs,
+            s.tbLong);
         d.launches++;
     }
+    if (s.nLong > 0) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[1], 0));
     CUDA_TRY(d, cudaEventRecord(s.ev[4], st));
     if (d2h) {
         CUDA_TRY(d, cudaMemcpyAsync(s.hOut.p, s.dOut.p, (size_t)s.count * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
@@ -972,8 +989,17 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_THREADS")) ctx->nThreads = std::max(1, atoi(e));
     if (const char *e = getenv("YB_WAVE_MB")) ctx->waveInBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_MIN_MB")) ctx->waveMinBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
+    {   // traceback bytes per wave: an eighth of the smallest device's free memory (NSLOTS waves can be in flight)
+        size_t cap = (size_t)24 << 30;
+        for (auto &d : ctx->devs) {
+            size_t fr = 0, tot = 0;
+            if (cudaSetDevice(d.id) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess) cap = std::min(cap, fr / 8);
+        }
+        ctx->waveTbBytes = std::max<size_t>(cap, (size_t)256 << 20);
+    }
     if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_NT")) ctx->ntStores = atoi(e) != 0;
+    if (const char *e = getenv("YB_TB_LONG")) ctx->tbLong = std::max(1, atoi(e));
     if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
     for (auto &d : ctx->devs) {
         d.helpers = std::max(1, ctx->nThreads / (int)ctx->devs.size());

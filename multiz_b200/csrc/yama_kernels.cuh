@@ -466,19 +466,19 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 // band is not consulted.  Ops leave as 2-bit codes, 16 per 32-bit store, in the reference's (reversed)
 // order: op i sits in bits 2*(i&15) of word i>>4.
 // =================================================================================================
-constexpr int TB_LONG = 6144;       // paths of at least this many moves get a warp of their own (the warp-per-path
+constexpr int TB_LONG = 2048;       // paths of at least this many moves get a warp of their own (the warp-per-path
                                     // kernel is bound by instruction issue, so only where the pointer chase is critical)
 
 __global__ void __launch_bounds__(128)
 yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                     const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
                     const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
-                    PairOut *__restrict__ outs) {
+                    PairOut *__restrict__ outs, int tbLong) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nPairs) return;
     const int p = order[idx];
     const PairMeta pm = metas[p];
-    if (pm.M + pm.N >= TB_LONG) return;                  // walked by yb_traceback_long_kernel, one warp per pair
+    if (pm.M + pm.N >= tbLong) return;                  // walked by yb_traceback_long_kernel, one warp per pair
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
     const unsigned char *tb = tbPool + __ldg(tbBase + p);
     unsigned *script = scriptPool + pm.scriptBase;
