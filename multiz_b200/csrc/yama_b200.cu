@@ -181,6 +181,7 @@ struct Slot {
     size_t blobBytes = 0, metaBytes = 0, orderOff = 0, longOff = 0, tbBaseOff = 0, scriptWords = 0;
     int nLong = 0;                         // pairs whose traceback path gets a warp of its own
     int tbLong = TB_LONG;                  // ... those with at least this many moves
+    bool y16 = false;                      // every pair has K*gap_open <= 32767: the kernels' 16-bit weight forms
     int nValid = 0;
     int binStart[NBINS + 1] = {};
 };
@@ -342,13 +343,13 @@ size_t fill_smem(int bin) {
 
 // ---- kernels with a runtime warps-per-CTA: thin wrappers around the template ---------------------
 namespace yb {
-template <int RING, int G, int P>
+template <int RING, int G, int P, bool Y16>
 __global__ void __launch_bounds__(G * P * 32)
 yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                  const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
                  const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs) {
-    fill_body<RING, G, P>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs);
+    fill_body<RING, G, P, Y16>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs);
 }
 }  // namespace yb
 
@@ -356,13 +357,13 @@ namespace {
 
 typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *, const ColRec *,
                        unsigned char *, const unsigned long long *, PairOut *);
-FillFn fill_fn(int bin) {
+FillFn fill_fn(int bin, bool y16) {
     switch (bin) {
-        case 0: return yb_fill_kernel_w<128, 1, 8>;
-        case 1: return yb_fill_kernel_w<512, 1, 8>;
-        case 2: return yb_fill_kernel_w<512, 4, 1>;
-        case 3: return yb_fill_kernel_w<2048, 8, 1>;
-        default: return yb_fill_kernel_w<4096, 8, 1>;
+        case 0: return y16 ? yb_fill_kernel_w<128, 1, 8, true> : yb_fill_kernel_w<128, 1, 8, false>;
+        case 1: return y16 ? yb_fill_kernel_w<512, 1, 8, true> : yb_fill_kernel_w<512, 1, 8, false>;
+        case 2: return y16 ? yb_fill_kernel_w<512, 4, 1, true> : yb_fill_kernel_w<512, 4, 1, false>;
+        case 3: return y16 ? yb_fill_kernel_w<2048, 8, 1, true> : yb_fill_kernel_w<2048, 8, 1, false>;
+        default: return y16 ? yb_fill_kernel_w<4096, 8, 1, true> : yb_fill_kernel_w<4096, 8, 1, false>;
     }
 }
 
@@ -380,8 +381,9 @@ int device_init(Device &d) {
         }
     }
     for (int b = 0; b < NBINS; ++b) {
-        FillFn fn = fill_fn(b);
+        FillFn fn = fill_fn(b, true);
         size_t sm = fill_smem(b);
+        CUDA_TRY(d, cudaFuncSetAttribute(fill_fn(b, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         int occ = 0;
         CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBin[b].G * kBin[b].P * 32, sm));
@@ -490,14 +492,17 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     struct Off { size_t blob, row, col; uint32_t script; };
     s.off.resize((size_t)count);
     size_t blob = 0, rows = 0, cols = 0, words = 0;
+    int maxK = 0;
     for (int64_t i = 0; i < count; ++i) {
         const yb_job &j = jobs[first + i];
         s.off[(size_t)i] = Slot::Off{blob, rows, cols, (uint32_t)words};
         if (!dims_ok(j)) continue;
+        maxK = std::max(maxK, j.K);
         blob += blob_bytes(j); rows += (size_t)j.M + 1; cols += (size_t)j.N + 1;
         words += ((size_t)j.M + j.N + 15) / 16;
     }
     s.first = first;
+    s.y16 = (int64_t)std::min(maxK, ctx->maxDepth) * ctx->sc.gap_open <= 32767;
     s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
     s.orderOff = s.metaBytes;
     s.longOff = s.orderOff + align_up((size_t)count * 4, 256);
@@ -660,7 +665,7 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)s.count * sizeof(PairOut), st));
     CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, st));
     if (s.nValid > 0) {
-        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols);
+        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0);
         d.launches++;
     }
     CUDA_TRY(d, cudaEventRecord(s.ev[2], st));
@@ -673,7 +678,7 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
         int blocks = std::min((n + bc.P - 1) / bc.P, d.fillBlocks[b]);
         cudaStream_t bs = b == 0 ? st : s.binStream[b];
         if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
-        fill_fn(b)<<<blocks, bc.G * bc.P * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
+        fill_fn(b, s.y16)<<<blocks, bc.G * bc.P * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
                                                                   reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs);
         if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
         d.launches++;

@@ -71,7 +71,8 @@ struct BandView {
 // Row record, 64 B (4 x 16 B).  av* are byte-count vectors matched against the column words (see
 // ColRec) with dp4a; everything a lane needs to run one row of the band.
 struct __align__(16) RowRec {
-    unsigned avXC, avYC, avZC, avXI;   // q0: C-node x,y,z and I-node x coefficient bytes
+    unsigned avXC, avYC, avZC, avXI;   // q0: C-node x,y,z and I-node x coefficient bytes (avYC/avYD: 16-bit pairs
+                                       //     pre-multiplied by -gap_open when the wave runs in y16 mode)
     unsigned avXD, avYD, avZD;         // q1: D-node x,y,z coefficient bytes (bytes 2,3 only)
     int eD;                            //     ndA*L*gap_ext  (mz_yama.c:239-242)
     unsigned w01, w23, w45;            // q2: S6^T * classcount(A row) as int16 pairs (sum-of-pairs weights)
@@ -91,7 +92,7 @@ __device__ __forceinline__ unsigned long long tb_byte(unsigned lane, unsigned t,
 }
 
 // Column record, 16 B.
-//  w0 = (b01, ndB, dB, b10)           raw transition / dash counts of column c against column c-1
+//  w0 = (b01, b10, ndB, dB)           raw transition / dash counts of column c against column c-1
 //  w1 = (n_A, n_C, n_G, n_T)          class counts
 //  w2 = (n_X, n_dash, ndB', dB')      ndB',dB' zeroed for c==0 and c==N  (mz_yama.c:211, end gaps free)
 //  w3 = w0 zeroed for c==1            (mz_yama.c:173, no gap-open at the start)
@@ -138,7 +139,7 @@ constexpr int K1_THREADS = 128;
 
 __global__ void __launch_bounds__(K1_THREADS)
 yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__restrict__ blob,
-                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool) {
+                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int y16) {
     const PairMeta pm = metas[blockIdx.x];
     const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
     if (M < 1) return;                                  // invalid pair (rejected on the host)
@@ -167,7 +168,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
                 b10 += t & (!v);
             }
             unsigned dB = n[5], ndB = (unsigned)L - dB;
-            cr.w0 = pack4(b01, ndB, dB, b10);
+            cr.w0 = pack4(b01, b10, ndB, dB);
             cr.w1 = pack4(n[0], n[1], n[2], n[3]);
             bool inner = (c < N);                               // mz_yama.c:211
             cr.w2 = pack4(n[4], n[5], inner ? ndB : 0u, inner ? dB : 0u);
@@ -198,19 +199,22 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
                 a00 += (!s) & (!u); a01 += (!s) & u; a10 += s & (!u); a11 += s & u;
             }
             unsigned dA = (unsigned)n[5], ndA = (unsigned)K - dA;
-            // gap-open counts as dot products with the column bytes (b01, ndB, dB, b10):
-            //   C.x: a00*b01 + a01*ndB + a10*dB + a11*b10   C.y: dA*ndB + a10*dB   C.z: ndA*dB + dA*b10
+            // gap-open counts as dot products with the column bytes (b01, b10, ndB, dB):
+            //   C.x: a00*b01 + a11*b10 + a01*ndB + a10*dB   C.y: dA*ndB + a10*dB   C.z: ndA*dB + dA*b10
             //   I.x: ndA*ndB + dA*b10    I.y: K*ndB    I.z: K*b10
             //   D.x: ndA*ndB' + a10*dB'   D.y: a10*(ndB'+dB')   D.z: ndA*(ndB'+dB')   on bytes 2,3 of w2
+            // The y candidates (from a D node) are never gated, so when K*gap_open fits 16 bits (y16) their weights are
+            // stored already multiplied by -gap_open and K2 applies them with ONE dp2a on bytes 2,3.
+            const int nGO = -c_sc.gap_open;
             if (r > 1) {                                        // mz_yama.c:180-184, :218-221 (row>1)
-                rr.avXC = pack4(a00, a01, a10, a11);
-                rr.avYC = pack4(0, dA, a10, 0);
+                rr.avXC = pack4(a00, a11, a01, a10);
+                rr.avYC = y16 ? pack16((int)dA * nGO, (int)a10 * nGO) : pack4(0, 0, dA, a10);
                 rr.avXD = pack4(0, 0, ndA, a10);
-                rr.avYD = pack4(0, 0, a10, a10);
+                rr.avYD = y16 ? pack16((int)a10 * nGO, (int)a10 * nGO) : pack4(0, 0, a10, a10);
             }
-            rr.avZC = pack4(0, 0, ndA, dA);
+            rr.avZC = pack4(0, dA, 0, ndA);
             rr.avZD = pack4(0, 0, ndA, ndA);
-            if (r < M) rr.avXI = pack4(0, ndA, 0, dA);         // mz_yama.c:123 (row<M)
+            if (r < M) rr.avXI = pack4(0, dA, ndA, 0);         // mz_yama.c:123 (row<M)
             rr.eD = (int)ndA * L * GE;
             int w[6];
 #pragma unroll
@@ -272,7 +276,9 @@ __device__ __forceinline__ int pick3(int x, int y, int z, bool exists, unsigned 
 //       the form for wide bands, where one ring per PAIR (instead of per warp) keeps the shared-memory footprint small
 //       enough for full occupancy, and long pairs get 32*G cells per step.
 // P:    groups (= pairs in flight) per CTA; P > 1 only with G = 1.
-template <int RING, int G, int P>
+// Y16:  every pair of the launch has K*gap_open <= 32767: the ungated y candidates and the I-node z candidate take
+//       one dp2a with 16-bit weights instead of dp4a/extract + imad.
+template <int RING, int G, int P, bool Y16>
 __device__ __forceinline__ void
 fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
@@ -320,7 +326,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const RowRec *rows = rowPool + pm.rowBase;
         const ColRec *cols = colPool + pm.colBase;
         unsigned char *tb = tbPool + __ldg(tbBase + p);
-        const unsigned nKGE_hi = launder((unsigned)(-(pm.K * c_sc.gap_ext)) << 16);   // dp2a.lo weight of byte 1 (ndB)
+        const unsigned nKGE_lo = launder((unsigned)(-(pm.K * c_sc.gap_ext)) & 0xffffu);   // dp2a.hi weight of byte 2 (ndB)
         const int KGE = pm.K * c_sc.gap_ext;
         const int nSteps = pm.nSteps;
         const int KnGO = pm.K * nGO;                        // I-node y / z charge per residue / per closing gap of B
@@ -334,7 +340,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
             for (int base = 0; base <= RB1; base += 32) {
                 int c = base + lane;
                 int nd = 0;
-                if (c >= 1 && c <= RB0) nd = (int)((__ldg(&cols[c].w0) >> 8) & 0xffu);
+                if (c >= 1 && c <= RB0) nd = (int)((__ldg(&cols[c].w0) >> 16) & 0xffu);
                 int inc = nd;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -367,7 +373,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
             w01 = q2.x; w23 = q2.y; w45 = q2.z; LB16 = (int)q2.w;
             RB16 = (int)q3.x; LBp16 = (int)q3.y;
             c16 = (t - (int)q3.z) * 16;
-            gIrow = r < M ? KnGO : 0;                               // mz_yama.c:123: no I-node gap-open on the last row
+            gIrow = r < M ? (Y16 ? (KnGO & 0xffff) : KnGO) : 0;     // mz_yama.c:123: no I-node gap-open on the last row
             // first cell of the row: its I node never exists, its C node only if the band moved right
             Efirst = (LB16 > LBp16) ? E_c0 : 0u;
         };
@@ -419,16 +425,22 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 const bool hasI = c16 > LB16, hasC = c16 > LBp16;
                 {
                     int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
-                    int y = Dl + (int)__byte_perm(cw.x, 0, 0x4441) * gIrow;       // K*ndB opens (mz_yama.c:131-134)
-                    int z = Il + (int)(cw.x >> 24) * gIl;                         // K*b10, if I(r,c-1) exists
+                    int y, z;
+                    if (Y16) {
+                        y = dp2a_hi_su((unsigned)gIrow, cw.x, Dl);                    // K*ndB opens (mz_yama.c:131-134)
+                        z = dp2a_lo_su((unsigned)gIl, cw.x, Il);                      // K*b10, if I(r,c-1) exists
+                    } else {
+                        y = Dl + (int)__byte_perm(cw.x, 0, 0x4442) * gIrow;
+                        z = Il + (int)__byte_perm(cw.x, 0, 0x4441) * gIl;
+                    }
                     vI = pick3<4>(x, y, z, hasI, acc);
-                    vI = dp2a_lo_su(nKGE_hi, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
+                    vI = dp2a_hi_su(nKGE_lo, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
                 }
                 vI = hasI ? vI : MININT;
                 // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
                 {
                     int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
-                    int y = Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
+                    int y = Y16 ? dp2a_hi_su(avYC, cw.w, Dd) : Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
                     int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
                     vC = pick3<0>(x, y, z, hasC, acc);
                     vC = dp2a_lo_su(w01, cw.y, vC);
@@ -439,7 +451,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
                 {
                     int x = Cu + dp4a_uu(cw.z, avXD, 0) * gCu;
-                    int y = Du + dp4a_uu(cw.z, avYD, 0) * nGO;
+                    int y = Y16 ? dp2a_hi_su(avYD, cw.z, Du) : Du + dp4a_uu(cw.z, avYD, 0) * nGO;
                     int z = Iu + dp4a_uu(cw.z, avZD, 0) * gIu;
                     vD = pick3<2>(x, y, z, true, acc) - eD;
                 }
@@ -449,7 +461,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
                 if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * (2 * B) + tbWord + ((t4 >> 2) & 1)] = acc;
                 Cl = vC; Dl = vD; Il = vI;
-                gCl = hasC ? nGO : 0; gIl = hasI ? gIrow : 0;
+                gCl = hasC ? nGO : 0; gIl = hasI ? (Y16 ? gIrow << 16 : gIrow) : 0;
                 Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
                 c16 += 16;
                 group_sync();
