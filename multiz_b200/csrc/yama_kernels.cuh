@@ -361,12 +361,12 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 
         // ---- per-lane row state --------------------------------------------------------------------
         int r = lane + 1;
-        const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
         unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avXD = 0, avYD = 0, avZD = 0;
-        int gIrow = 0;
+        int gIrow = 0, gIz = 0;
         unsigned w01 = 0, w23 = 0, w45 = 0, Efirst = 0;
         int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBp16 = 0, c16 = 0;
         auto load_row = [&](int t) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);       // (recomputed: no pointer carried by the loop)
             uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
             avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
             avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
@@ -374,6 +374,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
             RB16 = (int)q3.x; LBp16 = (int)q3.y;
             c16 = (t - (int)q3.z) * 16;
             gIrow = r < M ? (Y16 ? (KnGO & 0xffff) : KnGO) : 0;     // mz_yama.c:123: no I-node gap-open on the last row
+            gIz = Y16 ? gIrow << 16 : gIrow;                        // the z candidate's weight sits on byte 1 (b10)
             // first cell of the row: its I node never exists, its C node only if the band moved right
             Efirst = (LB16 > LBp16) ? E_c0 : 0u;
         };
@@ -399,7 +400,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                         sts128(wrBase, MININT, MININT, MININT, E_both);
                         sts128(wrBase ^ 16u, MININT, MININT, MININT, E_both);
                     } else {
-                        const int RBn = __ldg(reinterpret_cast<const int *>(rp) + 15);      // RowRec::RBn
+                        const int RBn = __ldg(reinterpret_cast<const int *>(rows + r) + 15);   // RowRec::RBn
 #pragma unroll 1
                         for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
                             sts128(and_xor((unsigned)cc << 4, wrMask, wrBase), MININT, MININT, MININT, E_both);
@@ -408,7 +409,6 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     if (r == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
                     // (c) move one wavefront width down
                     r += B;
-                    rp += B * (sizeof(RowRec) / 16);
                     if (r <= M) load_row(t4 + u);
                     else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; }
                 }
@@ -461,7 +461,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
                 if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * (2 * B) + tbWord + ((t4 >> 2) & 1)] = acc;
                 Cl = vC; Dl = vD; Il = vI;
-                gCl = hasC ? nGO : 0; gIl = hasI ? (Y16 ? gIrow << 16 : gIrow) : 0;
+                gCl = hasC ? nGO : 0; gIl = hasI ? gIz : 0;
                 Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
                 c16 += 16;
                 group_sync();
