@@ -329,6 +329,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const unsigned nKGE_lo = launder((unsigned)(-(pm.K * c_sc.gap_ext)) & 0xffffu);   // dp2a.hi weight of byte 2 (ndB)
         const int KGE = pm.K * c_sc.gap_ext;
         const int nSteps = pm.nSteps;
+        const int N16 = pm.N * 16;
         const int KnGO = pm.K * nGO;                        // I-node y / z charge per residue / per closing gap of B
         const unsigned E_c0 = pack16(nGO, 0);
 
@@ -416,8 +417,9 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
                 const bool active = (c16 >= LB16);
 
-                uint4 cw = make_uint4(0u, 0u, 0u, 0u);
-                if (active) cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) + c16));
+                // column record of column c; lanes outside their row read a clamped (valid) column and discard the result
+                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) +
+                                                                       __vimin_s32_relu(c16, N16)));
 
                 // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
                 int vI, vC, vD;
