@@ -211,10 +211,15 @@ class YamaB200:
                        A.ctypes.data, B.ctypes.data, LB.ctypes.data, RB.ctypes.data)
         return jobs, keep
 
-    def run_batch(self, jobs: np.ndarray, check: bool = True):
-        """jobs: array of JOB_DTYPE (pointers into live host memory).  Returns (results, stats)."""
+    def run_batch(self, jobs: np.ndarray, check: bool = True, out: np.ndarray | None = None):
+        """jobs: array of JOB_DTYPE (pointers into live host memory).  Returns (results, stats).  `out` lets a caller
+        reuse its result array across calls, as a C caller of yb_run_batch would."""
         assert jobs.dtype == JOB_DTYPE and jobs.flags.c_contiguous
-        res = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        if out is None:
+            res = np.zeros(len(jobs), dtype=RESULT_DTYPE)
+        else:
+            assert out.dtype == RESULT_DTYPE and out.flags.c_contiguous and len(out) == len(jobs)
+            res = out
         st = yb_stats()
         rc = self.lib.yb_run_batch(self.h, len(jobs), jobs.ctypes.data, res.ctypes.data, C.byref(st))
         if rc != 0 and check:
