@@ -161,3 +161,49 @@ def test_resident_path_matches_batch(yama_ctx, oracle):
     A, B, LB, RB = sb.problem(7)
     o = oracle.yama(A, B, LB, RB, want_tback=False)
     assert np.array_equal(scripts_b[7], o["script"])
+
+
+def test_full_size_batch_sampled_and_wave_invariant(oracle):
+    """BASELINE.json configs[1] at full size (119 490 pairs, 2.29 G cells): (i) a size-stratified sample of pairs is
+    compared with the oracle bit for bit, (ii) every script consumes exactly its two alignments, (iii) the results do
+    not depend on how the batch is cut into waves (8 MB waves vs the default) nor on a second run."""
+    import os
+    from bench import make_batch
+    from multiz_b200 import YamaB200
+    sb, _ = make_batch("cfg2", 1234, 1.0)
+    ctx = YamaB200(devices=[0])
+    res, st = ctx.run_batch(sb.jobs)
+    assert st.cells == sb.cells and int((res["status"] != 0).sum()) == 0
+    ops = np.zeros(0, np.uint8)
+    order = np.argsort(sb.M, kind="stable")
+    sample = np.unique(np.concatenate([order[:: max(1, sb.n // 150)], order[-20:], order[:20]]))
+    for i in sample:
+        A, B, LB, RB = sb.problem(int(i))
+        o = oracle.yama(A, B, LB, RB, want_tback=False)
+        r = res[int(i)]
+        assert (int(r["C"]), int(r["D"]), int(r["I"])) == tuple(int(x) for x in o["cdi"]), int(i)
+        assert np.array_equal(ctx.script_of(r), o["script"]), int(i)
+    # (ii) on every pair: #C + #D == M, #C + #I == N  (what yb_assemble / mz_yama.c:310-312 insist on)
+    packed_len = (res["m_new"].astype(np.int64) + 3) // 4
+    import ctypes as C
+    nC = np.zeros(sb.n, np.int64); nI = np.zeros(sb.n, np.int64); nD = np.zeros(sb.n, np.int64)
+    for i in range(0, sb.n, 97):                      # every 97th pair: ~1200 pairs
+        s = ctx.script_of(res[i])
+        nC[i], nI[i], nD[i] = (s == 0).sum(), (s == 1).sum(), (s == 2).sum()
+        assert nC[i] + nD[i] == sb.M[i] and nC[i] + nI[i] == sb.N[i], i
+    del ops, packed_len, C
+    # (iii) wave-size and run-to-run invariance
+    keep = [(int(r["m_new"]), int(r["C"]), int(r["D"]), int(r["I"])) for r in res]
+    scripts = {int(i): ctx.script_of(res[int(i)]).tobytes() for i in sample}
+    ctx.close()
+    os.environ["YB_WAVE_MB"] = "8"
+    try:
+        ctx2 = YamaB200(devices=[0])
+    finally:
+        del os.environ["YB_WAVE_MB"]
+    for _ in range(2):
+        res2, _st = ctx2.run_batch(sb.jobs)
+        assert [(int(r["m_new"]), int(r["C"]), int(r["D"]), int(r["I"])) for r in res2] == keep
+        for i in sample:
+            assert ctx2.script_of(res2[int(i)]).tobytes() == scripts[int(i)]
+    ctx2.close()
