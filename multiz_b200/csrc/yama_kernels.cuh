@@ -132,6 +132,43 @@ __device__ __forceinline__ unsigned pack16(int lo, int hi) {
     return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
 }
 
+// ---- 4 bytes at a time: class counts and dash transitions of one alignment column / row --------------------
+// 0x80 in every byte of x that is zero (exact, no carries across bytes)
+__device__ __forceinline__ unsigned zero_bytes80(unsigned x) {
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+__device__ __forceinline__ unsigned eq_bytes80(unsigned w, unsigned pattern) { return zero_bytes80(w ^ pattern); }
+// unaligned 32-bit read of bytes p..p+3 from two aligned words (blob sections are padded, reading past n is safe)
+__device__ __forceinline__ unsigned load4(const unsigned char *p) {
+    const unsigned *a = reinterpret_cast<const unsigned *>(reinterpret_cast<unsigned long long>(p) & ~3ull);
+    const unsigned sh = ((unsigned)reinterpret_cast<unsigned long long>(p) & 3u) * 8u;
+    return __funnelshift_r(__ldg(a), __ldg(a + 1), sh);
+}
+struct Census {
+    unsigned n[6];          // A, C, G, T, other, dash  (mz_scores.c:39-54 distinguishes nothing else)
+    unsigned t00, t01, t10, t11;   // (previous is dash, this is dash) transition counts; previous == none counts as non-dash
+};
+__device__ __forceinline__ Census census(const unsigned char *now, const unsigned char *prev, int n) {
+    Census q;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q.n[k] = 0;
+    q.t00 = q.t01 = q.t10 = q.t11 = 0;
+    for (int j = 0; j < n; j += 4) {
+        const unsigned valid = (n - j >= 4) ? 0x80808080u : (0x80808080u >> (8 * (4 - (n - j))));
+        const unsigned w = load4(now + j);
+        const unsigned lw = w | 0x20202020u;
+        const unsigned mD = eq_bytes80(w, 0x2d2d2d2du) & valid;                 // '-'
+        const unsigned mA = eq_bytes80(lw, 0x61616161u) & valid, mC = eq_bytes80(lw, 0x63636363u) & valid;
+        const unsigned mG = eq_bytes80(lw, 0x67676767u) & valid, mT = eq_bytes80(lw, 0x74747474u) & valid;
+        const unsigned pD = prev ? (eq_bytes80(load4(prev + j), 0x2d2d2d2du) & valid) : 0u;
+        q.n[0] += __popc(mA); q.n[1] += __popc(mC); q.n[2] += __popc(mG); q.n[3] += __popc(mT); q.n[5] += __popc(mD);
+        q.n[4] += __popc(valid & ~(mA | mC | mG | mT | mD));
+        q.t11 += __popc(pD & mD); q.t10 += __popc(pD & ~mD); q.t01 += __popc(valid & ~pD & mD);
+    }
+    q.t00 = (unsigned)n - q.t01 - q.t10 - q.t11;
+    return q;
+}
+
 // =================================================================================================
 // K1: column / row profiles, traceback row offsets, wavefront schedule.  One CTA per pair.
 // =================================================================================================
@@ -156,17 +193,9 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
         ColRec cr = {0u, 0u, 0u, 0u};
         if (c >= 1) {
             const unsigned char *now = B + (size_t)(c - 1) * L;
-            const unsigned char *left = now - L;   // only dereferenced when c > 1
-            unsigned n[6] = {0, 0, 0, 0, 0, 0};
-            unsigned b01 = 0, b10 = 0;
-            for (int j = 0; j < L; ++j) {
-                unsigned ch = now[j];
-                n[classify(ch)]++;
-                unsigned v = (ch == '-');
-                unsigned t = (c > 1) ? (left[j] == '-') : 0u;   // mz_yama.c:128 (t==0 when col==1)
-                b01 += (!t) & v;
-                b10 += t & (!v);
-            }
+            const Census q = census(now, c > 1 ? now - L : nullptr, L);    // mz_yama.c:128 (t==0 when col==1)
+            const unsigned *n = q.n;
+            const unsigned b01 = q.t01, b10 = q.t10;
             unsigned dB = n[5], ndB = (unsigned)L - dB;
             cr.w0 = pack4(b01, b10, ndB, dB);
             cr.w1 = pack4(n[0], n[1], n[2], n[3]);
@@ -188,16 +217,11 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
         rr.RBn = r < M ? band.rb(r + 1) : band.rb(r);
         if (r >= 1) {
             const unsigned char *now = A + (size_t)(r - 1) * K;
-            const unsigned char *up = now - K;    // only dereferenced when r > 1
-            int n[6] = {0, 0, 0, 0, 0, 0};
-            unsigned a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-            for (int i = 0; i < K; ++i) {
-                unsigned ch = now[i];
-                n[classify(ch)]++;
-                unsigned u = (ch == '-');
-                unsigned s = (r > 1) ? (up[i] == '-') : 0u;     // mz_yama.c:175,213
-                a00 += (!s) & (!u); a01 += (!s) & u; a10 += s & (!u); a11 += s & u;
-            }
+            const Census q = census(now, r > 1 ? now - K : nullptr, K);    // mz_yama.c:175,213 (s==0 when row==1)
+            int n[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) n[k] = (int)q.n[k];
+            const unsigned a00 = q.t00, a01 = q.t01, a10 = q.t10, a11 = q.t11;
             unsigned dA = (unsigned)n[5], ndA = (unsigned)K - dA;
             // gap-open counts as dot products with the column bytes (b01, b10, ndB, dB):
             //   C.x: a00*b01 + a11*b10 + a01*ndB + a10*dB   C.y: dA*ndB + a10*dB   C.z: ndA*dB + dA*b10
