@@ -5,22 +5,23 @@
 //  K1 yb_profile_kernel   one CTA per block pair.  Every alignment column is reduced to a count
 //                         vector: 6 character classes (A,C,G,T,other,'-'; mz_scores.c:39-54 only ever
 //                         distinguishes these) and the dash-transition counts between neighbouring
-//                         columns that the quasi-natural gap costs need (mz_scores.c:57-79).  With
-//                         those, each O(K*L) loop of mz_yama.c:124-137/:174-201/:212-225 collapses to
-//                         a 4-term integer dot product of byte counts (dp4a) and the sum-of-pairs
-//                         score (mz_yama.c:199-201) to a 6-term 16x8-bit dot product (dp2a).
-//                         Also produces the per-row traceback offsets and the wavefront schedule.
-//  K2 yb_fill_kernel      one warp per block pair, persistent, pairs pulled from a queue.  Lane l owns
-//                         rows l+1, l+33, ... and walks its row left to right; lane l is always one
-//                         column behind lane l-1, so at every step the warp advances one anti-diagonal
-//                         of the band.  (C,D,I) of the row above arrive through a 2-slot shared-memory
-//                         mailbox per lane; lane 31 -> lane 0 goes through a ring that holds one band
-//                         row.  One traceback byte per cell (mz_yama.c:253) is packed 4 at a time into
-//                         32-bit stores.
-//  K3 yb_traceback_kernel one thread per pair follows the packed pointers (mz_yama.c:257-291) and emits
-//                         the edit script.
+//                         columns that the quasi-natural gap costs need (mz_scores.c:57-79), four bytes
+//                         per step with zero-byte masks and popc.  With those, each O(K*L) loop of
+//                         mz_yama.c:124-137/:174-201/:212-225 collapses to a 4-term integer dot product of
+//                         byte counts (dp4a) and the sum-of-pairs score (mz_yama.c:199-201) to a 6-term
+//                         16x8-bit dot product (dp2a).
+//  K2 yb_fill_kernel_w    a wavefront of B = 32*G lanes per block pair (G = 1: one warp per pair; G = 4/8:
+//                         one CTA per pair, for wide bands), persistent, pairs pulled from a queue.  Lane
+//                         l owns rows l+1, l+1+B, ... and walks its row left to right; lane l is always
+//                         one column behind lane l-1, so at every step the wavefront advances one
+//                         anti-diagonal of the band.  (C,D,I) of the row above arrive through a 2-slot
+//                         shared-memory mailbox per lane; last lane -> lane 0 goes through a ring that
+//                         holds one band row.  One traceback byte per cell (mz_yama.c:253) is packed 4 at
+//                         a time into 32-bit stores.
+//  K3 yb_traceback_*      follow the packed pointers (mz_yama.c:257-291) and emit the edit script as 2-bit
+//                         codes: one thread per pair, or one warp per path for long paths.
 //
-// Exactness: every in-band cell gets exactly the reference's int32 value and traceback byte, including
+// Exactness: every in-band cell gets exactly the reference's int32 values and traceback decisions, including
 // the "predecessor does not exist -> no gap-open charge" guards (mz_yama.c:131-135,180-186,218-223) and
 // the MININT-minus-penalty values on the right fringe (mz_yama.c:93-94).  The guards are carried as data:
 // every mailbox record holds, next to (C,D,I), the multipliers (-gap_open or 0) that a consumer applies
@@ -255,7 +256,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
 }
 
 // =================================================================================================
-// K2: banded three-state fill, one warp per pair.
+// K2: banded three-state fill, one wavefront (warp or CTA) per pair.
 // =================================================================================================
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
