@@ -664,6 +664,8 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     CUDA_TRY(d, cudaEventRecord(s.ev[1], st));
     CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)s.count * sizeof(PairOut), st));
     CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, st));
+    // a script region holds ceil((M+N)/16) words but a path has m_new <= M+N ops: the unwritten tail is copied back too
+    if (s.scriptWords) CUDA_TRY(d, cudaMemsetAsync(s.dScript.p, 0, s.scriptWords * 4, st));
     if (s.nValid > 0) {
         yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0);
         d.launches++;

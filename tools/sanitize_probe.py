@@ -1,0 +1,19 @@
+"""Small batch through every kernel bin, for compute-sanitizer (memcheck / racecheck / initcheck) runs."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from multiz_b200 import YamaB200
+from tools.synth import SynthBatch, random_problem
+
+ctx = YamaB200(devices=[0])
+rng = np.random.default_rng(1)
+probs = [random_problem(rng, int(rng.integers(1, 6)), int(rng.integers(1, 4)), int(rng.integers(1, 80)), int(rng.integers(1, 80)),
+                        band=("smooth", "full", "ragged")[i % 3]) for i in range(60)]
+for (K, L, M, R) in ((2, 1, 300, 30), (3, 1, 150, 150), (2, 1, 400, 150), (2, 1, 700, 400), (1, 1, 1200, 1100), (90, 10, 70, 30)):
+    sb = SynthBatch(K * 7 + M, [K, K], [L, L], [M, max(1, M - 13)], R=R)
+    probs += [tuple(np.array(x) for x in sb.problem(i)) for i in range(sb.n)]
+jobs, keep = ctx.make_jobs(probs)
+res, st = ctx.run_batch(jobs)
+assert int((res["status"] != 0).sum()) == 0
+print("pairs", len(jobs), "cells", st.cells, "launches", st.kernel_launches, "checksum", int(res["m_new"].sum()), int(res["C"].astype(np.int64).sum()))
+ctx.close()
