@@ -80,7 +80,8 @@ struct __align__(16) RowRec {
     int LB16;                          //     16*LB[r]
     int RB16, LBp16;                   // q3: 16*RB[r], 16*LB[r-1]
     int off;                           //     wavefront schedule: this row computes column (step - off)
-    int RBn;                           //     RB[r+1] (RB[r] on the last row): how far the row below reads us
+    int RBn;                           //     warp-sized wavefronts: RB[r+1] (RB[r] on the last row), how far the row below
+                                       //     reads us; CTA-sized wavefronts: 16*RB[r-1] + 16, where the row above ends
 };
 
 // Traceback matrix layout: the wavefront (B = 32 << (lgLanes-5) lanes: one warp, or the warps of a CTA) advances one
@@ -216,6 +217,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
         rr.LB16 = lb * 16; rr.RB16 = band.rb(r) * 16; rr.LBp16 = lbp * 16;
         rr.off = r >= 1 ? sched[(r - 1) >> pm.lgLanes] + ((r - 1) & ((1 << pm.lgLanes) - 1)) : 0;
         rr.RBn = r < M ? band.rb(r + 1) : band.rb(r);
+        if (pm.lgLanes > 5 && r >= 1) rr.RBn = band.rb(r - 1) * 16 + 16;      // (row 0 keeps RB[1]: the ring initialisation)
         if (r >= 1) {
             const unsigned char *now = A + (size_t)(r - 1) * K;
             const Census q = census(now, r > 1 ? now - K : nullptr, K);    // mz_yama.c:175,213 (s==0 when row==1)
@@ -391,6 +393,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         int gIrow = 0, gIz = 0;
         unsigned w01 = 0, w23 = 0, w45 = 0, Efirst = 0;
         int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBp16 = 0, c16 = 0;
+        int rdMax16 = 0x7fffffff;                              // CTA-sized wavefronts: 16*(RB[r-1]+1), see the row-end code
         auto load_row = [&](int t) {
             const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);       // (recomputed: no pointer carried by the loop)
             uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
@@ -399,6 +402,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
             w01 = q2.x; w23 = q2.y; w45 = q2.z; LB16 = (int)q2.w;
             RB16 = (int)q3.x; LBp16 = (int)q3.y;
             c16 = (t - (int)q3.z) * 16;
+            if (G > 1) rdMax16 = (int)q3.w;
             gIrow = r < M ? (Y16 ? (KnGO & 0xffff) : KnGO) : 0;     // mz_yama.c:123: no I-node gap-open on the last row
             gIz = Y16 ? gIrow << 16 : gIrow;                        // the z candidate's weight sits on byte 1 (b10)
             // first cell of the row: its I node never exists, its C node only if the band moved right
@@ -415,14 +419,17 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 // ---- grid point (r-1, c): read before anybody may overwrite it ------------------------
-                const uint4 up = lds128(and_xor((unsigned)c16, rdMask, rdBase));
+                const uint4 up = lds128(and_xor((unsigned)(G > 1 ? min(c16, rdMax16) : c16), rdMask, rdBase));
                 if (c16 > RB16) {
                     // ---- this lane finished its row -----------------------------------------------------
                     // (a) the row below keeps reading us up to its own right bound: stale dp[] entries (mz_yama.c:93-94).
-                    //     A mailbox lane of a warp-sized wavefront fills both of its slots (the reader took our last
-                    //     column at the top of this step); the ring lane, and CTA-sized wavefronts whose reader may sit
-                    //     in another warp, write them column by column.
-                    if (G == 1 && lane != B - 1) {
+                    //     A mailbox lane of a warp-sized wavefront fills both of its slots (the reader, in the same warp,
+                    //     took our last column at the top of this step); its ring lane writes them column by column.
+                    if (G > 1) {
+                        // the reader may sit in another warp and may not have taken our last column yet: touch only
+                        // the slot of column RB+1 (never the one of column RB); readers clamp their column to it
+                        sts128(and_xor((unsigned)(RB16 + 16), wrMask, wrBase), MININT, MININT, MININT, E_both);
+                    } else if (lane != B - 1) {
                         sts128(wrBase, MININT, MININT, MININT, E_both);
                         sts128(wrBase ^ 16u, MININT, MININT, MININT, E_both);
                     } else {
@@ -436,7 +443,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     // (c) move one wavefront width down
                     r += B;
                     if (r <= M) load_row(t4 + u);
-                    else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; }
+                    else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; rdMax16 = 0x7fffffff; }
                 }
                 const int Cu = (int)up.x, Du = (int)up.y, Iu = (int)up.z;
                 const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
