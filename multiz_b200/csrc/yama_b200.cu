@@ -213,7 +213,7 @@ struct yb_ctx {
     int maxDepth = 255;
     int nThreads = 1;
     size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave (steady state)
-    size_t waveMinBytes = (size_t)64 << 20; // first / last waves of a batch (measured: ramping does not pay on cfg2)
+    size_t waveMinBytes = (size_t)16 << 20; // first / last waves of a batch (the device idles while the first wave is packed)
     size_t batchBlobBytes = 0;              // input bytes of the current batch (dimension-only estimate)
     size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
     int64_t wavePairs = 1 << 20;
