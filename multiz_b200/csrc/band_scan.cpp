@@ -7,6 +7,7 @@
 // of the fill kernel (see make_schedule in yama_b200.cu).  A violation only sets a flag: the caller re-runs the
 // scalar check, which words the message exactly as the reference does.
 #include <cstdint>
+#include <cstdlib>
 
 #ifndef YB_BAND_SCAN_NAME
 #error "compile with -DYB_BAND_SCAN_NAME=..."
@@ -75,7 +76,8 @@ extern "C" int64_t yb_band_scan_avx2(int, int, const int32_t *, const int32_t *,
                                      int (*)(int, int), int32_t *);
 extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
                                 int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes) {
-    static const bool avx2 = __builtin_cpu_supports("avx2");
+    // YB_NO_AVX2=1 forces the baseline build (the CPU suite runs both)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("YB_NO_AVX2");
     return avx2 ? yb_band_scan_avx2(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes)
                 : YB_BAND_SCAN_NAME(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes);
 }

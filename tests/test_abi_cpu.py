@@ -158,3 +158,13 @@ def test_pair_facts_simd_scan_equals_scalar(oracle):
     for i in range(sb.n):
         A, B, LB, RB = sb.problem(i)
         assert facts(A.shape[0], B.shape[0], LB, RB) == 0 and cells.value == int((RB.astype(np.int64) - LB + 1).sum())
+
+
+def test_pair_facts_baseline_build_too():
+    """The same cross-check with the non-AVX2 build of the band scan (YB_NO_AVX2=1), in a fresh process."""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_abi_cpu as t\nfrom oracle.oracle_py import Oracle\nt.test_pair_facts_simd_scan_equals_scalar(Oracle(70))\nprint('ok')"
+            % (ROOT, os.path.join(ROOT, "tests")))
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, YB_NO_AVX2="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0 and p.stdout.strip().endswith(b"ok"), p.stderr.decode()[-800:]
