@@ -78,7 +78,8 @@ int yb_device_count(const yb_ctx *ctx);
 /* ---- score tables (replaces reading the globals of mz_scores.h:8-11) ----------------------- */
 /* ss: 128*128 ints row-major (ss[c][d] of the reference), gop: 16 ints, gap_extend.
  * Verifies the 6-class structure (ACGT/acgt, other, '-') of mz_scores.c:39-54 and the six-pattern
- * gop of :57-79, then uploads S6/gap_open/gap_extend to __constant__ memory on every device. */
+ * gop of :57-79, then keeps S6/gap_open/gap_extend with the context (they reach the kernels as
+ * arguments, so contexts with different tables can coexist in one process). */
 int yb_set_scores(yb_ctx *ctx, const int32_t *ss, const int32_t *gop, int32_t gap_extend);
 
 /* ---- batched path (the product) ------------------------------------------------------------ */
@@ -101,6 +102,21 @@ void yb_clear(yb_ctx *ctx);
 
 /* Expands res->script into one byte per op (the reference's `script[]`, mz_yama.c:257-291): ops[i], i < m_new. */
 int yb_script_unpack(const yb_result *res, uint8_t *ops);
+
+/* ---- block scoring: mafScoreRange (mz_scores.c:124-152), SURVEY 8(f) rank 1 ------------------- */
+/* One alignment block as mafScoreRange sees it: struct mafAli (maf.h:28-36) with its components' text
+ * (struct mafComp::text, maf.h:43-58), and the column range to score. */
+typedef struct {
+    int32_t nrows;               /* number of components                                           */
+    int32_t text_size;           /* mafAli::textSize                                               */
+    int32_t start, size;         /* mafScoreRange's arguments: columns start .. start+size-1       */
+    const uint8_t *const *rows;  /* nrows pointers to mafComp::text (text_size bytes, each < 128)  */
+} yb_block;
+/* scores[i] = mafScoreRange(block i, start, size) for n independent blocks, bit-identical doubles (the sums are
+ * integers).  A bad range fails the whole call with YB_ERR_ARG and the reference's message (mz_scores.c:130-132);
+ * no score tables -> YB_ERR_SCORES ("mafScoreRange: scores not initialized").  stats->cells counts row pairs x
+ * columns, the reference's unit of work.  Runs on the context's first device. */
+int yb_score_blocks(yb_ctx *ctx, int64_t n, const yb_block *blocks, double *scores, yb_stats *stats);
 
 /* ---- column assembly (mz_yama.c:293-313), host side ----------------------------------------- */
 /* Writes m_new*(K+L) bytes to out (caller-allocated). */

@@ -13,6 +13,7 @@
 // There is no CPU implementation of the DP in this library.
 #include "../../include/yama_b200.h"
 #include "yama_kernels.cuh"
+#include "score_kernels.cuh"
 
 #include <emmintrin.h>
 
@@ -186,10 +187,23 @@ struct Slot {
     int binStart[NBINS + 1] = {};
 };
 
+// Block scoring (yb_score_blocks): one wave of blocks in flight per stage, two stages so that packing the next
+// wave overlaps the copy and the kernel of the previous one.
+struct ScoreStage {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {};
+    DevBuf dIn, dSums;
+    PinBuf hIn, hSums;
+    int64_t first = 0, count = 0;
+    bool busy = false;
+};
+
 struct Device {
     int id = -1;
     int sms = 0;
     Slot slots[NSLOTS];
+    ScoreStage score[2];
+    ScoreConst sc{};                       // the owning context's score tables (kernel arguments)
     int fillBlocks[NBINS] = {};
     int helpers = 1;
     std::unique_ptr<Pool> pool;
@@ -348,15 +362,15 @@ __global__ void __launch_bounds__(G * P * 32)
 yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                  const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
-                 const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs) {
-    fill_body<RING, G, P, Y16>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs);
+                 const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int gapOpen, int gapExt) {
+    fill_body<RING, G, P, Y16>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
 }
 }  // namespace yb
 
 namespace {
 
 typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *, const ColRec *,
-                       unsigned char *, const unsigned long long *, PairOut *);
+                       unsigned char *, const unsigned long long *, PairOut *, int, int);
 FillFn fill_fn(int bin, bool y16) {
     switch (bin) {
         case 0: return y16 ? yb_fill_kernel_w<128, 1, 8, true> : yb_fill_kernel_w<128, 1, 8, false>;
@@ -667,7 +681,7 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     // a script region holds ceil((M+N)/16) words but a path has m_new <= M+N ops: the unwritten tail is copied back too
     if (s.scriptWords) CUDA_TRY(d, cudaMemsetAsync(s.dScript.p, 0, s.scriptWords * 4, st));
     if (s.nValid > 0) {
-        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0);
+        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0, d.sc);
         d.launches++;
     }
     CUDA_TRY(d, cudaEventRecord(s.ev[2], st));
@@ -681,7 +695,7 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
         cudaStream_t bs = b == 0 ? st : s.binStream[b];
         if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
         fill_fn(b, s.y16)<<<blocks, bc.G * bc.P * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
-                                                                  reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs);
+                                                                  reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs, d.sc.gap_open, d.sc.gap_ext);
         if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
         d.launches++;
     }
@@ -1028,6 +1042,11 @@ void yb_destroy(yb_ctx *ctx) {
             for (auto &b : s.binStream) if (b) cudaStreamDestroy(b);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
+        for (auto &g : d.score) {
+            g.dIn.release(); g.dSums.release(); g.hIn.release(); g.hSums.release();
+            for (auto &e : g.ev) if (e) cudaEventDestroy(e);
+            if (g.stream) cudaStreamDestroy(g.stream);
+        }
     }
     if (ctx->scriptStore) cudaFreeHost(ctx->scriptStore);
     delete ctx;
@@ -1076,12 +1095,7 @@ int yb_set_scores(yb_ctx *ctx, const int32_t *ss, const int32_t *gop, int32_t ga
     ctx->sc = sc;
     // 16-bit weights in the kernels: sum-of-pairs weights K*max|S6| and the extension weight K*gap_extend
     ctx->maxDepth = std::min(255, 32767 / std::max(maxabs, std::max(1, (int)gap_extend)));
-    for (auto &d : ctx->devs) {
-        if (cudaSetDevice(d.id) != cudaSuccess || cudaMemcpyToSymbol(c_sc, &sc, sizeof sc) != cudaSuccess) {
-            set_err(ctx, "cudaMemcpyToSymbol failed on device %d", d.id);
-            return YB_ERR_CUDA;
-        }
-    }
+    for (auto &d : ctx->devs) d.sc = sc;
     ctx->scoresSet = true;
     return YB_OK;
 }
@@ -1298,6 +1312,163 @@ int yb_assemble(const yb_job *job, const yb_result *res, uint8_t *out) {
         ++m;
     }
     if (i != job->M || j != job->N) return YB_ERR_TRACEBACK;   // mz_yama.c:310-312
+    return YB_OK;
+}
+
+// ---- block scoring: mafScoreRange (mz_scores.c:124-152), SURVEY 8(f) rank 1 ------------------------------------
+// Blocks are cut into waves of about 64 MB of text; a wave's metas, warp units and text go up in ONE copy from a
+// pinned buffer, one kernel scores it, one copy brings the per-block int64 sums back.  Two stages alternate, so the
+// helpers pack wave w+1 while wave w is on the device.  Device 0 of the context only: a multi-GPU host shards the
+// block list itself (blocks are independent), like the yama jobs.
+namespace {
+struct ScoreLayout { size_t off; int pitch; int units; };
+int score_finish(Device &d, ScoreStage &g, double *scores) {
+    if (!g.busy) return YB_OK;
+    CUDA_TRY(d, cudaStreamSynchronize(g.stream));
+    g.busy = false;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]) == cudaSuccess) d.h2d_ms += ms;
+    if (cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]) == cudaSuccess) d.kernel_ms += ms;
+    if (cudaEventElapsedTime(&ms, g.ev[2], g.ev[3]) == cudaSuccess) d.d2h_ms += ms;
+    const long long *sums = static_cast<const long long *>(g.hSums.p);
+    for (int64_t i = 0; i < g.count; ++i) scores[g.first + i] = (double)sums[i];   // integer-valued, exact below 2^53
+    return YB_OK;
+}
+}  // namespace
+
+int yb_score_blocks(yb_ctx *ctx, int64_t n, const yb_block *blocks, double *scores, yb_stats *stats) {
+    if (!ctx || n < 0 || (n > 0 && (!blocks || !scores))) return YB_ERR_ARG;
+    if (!ctx->scoresSet) { set_err(ctx, "mafScoreRange: scores not initialized"); return YB_ERR_SCORES; }   // mz_scores.c:133-134
+    for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < a; ++b)
+            if (ctx->sc.S6[a][b] != ctx->sc.S6[b][a]) {
+                set_err(ctx, "yb_score_blocks needs a symmetric substitution matrix (class %d/%d: %d vs %d)", a, b, ctx->sc.S6[a][b], ctx->sc.S6[b][a]);
+                return YB_ERR_SCORES;
+            }
+    const double t0 = now_ms();
+    Device &d = ctx->devs[0];
+    reset_stats(d);
+    if (cudaSetDevice(d.id) != cudaSuccess) { set_err(ctx, "cudaSetDevice failed"); return YB_ERR_CUDA; }
+    int maxabs = 1;
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) maxabs = std::max(maxabs, std::abs(ctx->sc.S6[a][b]));
+    // rows up to which a column's quadratic form fits 32 bits: |column| <= (maxabs + gap_open) * rows^2 / 2
+    int rows32 = 1;
+    while ((double)(rows32 + 1) * (rows32 + 1) * (maxabs + ctx->sc.gap_open) / 2.0 < 2147483647.0 && rows32 < 46340) ++rows32;
+
+    // validation, in the reference's order and wording (mz_scores.c:130-132)
+    int64_t pairCols = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const yb_block &b = blocks[i];
+        if (b.start < 0 || b.size <= 0 || (int64_t)b.start + b.size > b.text_size) {
+            set_err(ctx, "mafScoreRange: start = %d, size = %d, textSize = %d\n", b.start, b.size, b.text_size);
+            return YB_ERR_ARG;
+        }
+        if (b.nrows < 0 || (b.nrows > 0 && !b.rows)) { set_err(ctx, "yb_score_blocks: block %lld has no rows", (long long)i); return YB_ERR_ARG; }
+        pairCols += (int64_t)b.nrows * (b.nrows - 1) / 2 * b.size;
+    }
+    const size_t waveBytes = (size_t)64 << 20;
+    int rc = YB_OK, which = 0;
+    std::vector<ScoreLayout> lay;
+    std::vector<uint32_t> rowBlock;              // per text row of the wave: its block (wave-relative)
+    std::vector<uint32_t> rowFirst;              // per block of the wave: index of its first row
+    int64_t lo = 0;
+    while (lo < n && rc == YB_OK) {
+        // ---- cut a wave ------------------------------------------------------------------------------------
+        lay.clear(); rowBlock.clear(); rowFirst.clear();
+        size_t text = 0;
+        int64_t units = 0, hi = lo;
+        while (hi < n && (hi == lo || text < waveBytes)) {
+            const yb_block &b = blocks[hi];
+            ScoreLayout L;
+            L.pitch = 4 + (int)align_up((size_t)b.size, 4);
+            L.off = text;
+            L.units = (b.size + SCORE_UNIT_COLS - 1) / SCORE_UNIT_COLS;
+            text += align_up((size_t)L.pitch * (size_t)b.nrows, 16);
+            units += L.units;
+            rowFirst.push_back((uint32_t)rowBlock.size());
+            rowBlock.insert(rowBlock.end(), (size_t)b.nrows, (uint32_t)(hi - lo));
+            lay.push_back(L);
+            ++hi;
+        }
+        const int64_t cnt = hi - lo;
+        if (units > 0x7fffffff / 2) { set_err(ctx, "yb_score_blocks: wave too large"); rc = YB_ERR_LIMIT; break; }
+        const size_t metaOff = 0, unitOff = align_up((size_t)cnt * sizeof(ScoreMeta), 64);
+        const size_t textOff = align_up(unitOff + (size_t)units * sizeof(ScoreUnit), 256);
+        const size_t total = textOff + text + 256;
+        ScoreStage &g = d.score[which];
+        which ^= 1;
+        if ((rc = score_finish(d, g, scores)) != YB_OK) break;
+        if (!g.stream) {
+            CUDA_TRY(d, cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+            for (auto &e : g.ev) CUDA_TRY(d, cudaEventCreate(&e));
+        }
+        CUDA_TRY(d, g.hIn.reserve(total));
+        CUDA_TRY(d, g.dIn.reserve(total));
+        CUDA_TRY(d, g.hSums.reserve((size_t)cnt * 8));
+        CUDA_TRY(d, g.dSums.reserve((size_t)cnt * 8));
+        // ---- pack: metas + units per block, text per row, on the helpers ---------------------------------------
+        const double tp = now_ms();
+        unsigned char *h = static_cast<unsigned char *>(g.hIn.p);
+        ScoreMeta *metas = reinterpret_cast<ScoreMeta *>(h + metaOff);
+        ScoreUnit *un = reinterpret_cast<ScoreUnit *>(h + unitOff);
+        {
+            int64_t u = 0;
+            for (int64_t i = 0; i < cnt; ++i) {
+                const yb_block &b = blocks[lo + i];
+                metas[i].off = textOff + lay[(size_t)i].off;
+                metas[i].nrows = b.nrows; metas[i].size = b.size; metas[i].pitch = lay[(size_t)i].pitch;
+                metas[i].firstGap = b.start > 0;
+                for (int k = 0; k < lay[(size_t)i].units; ++k) { un[u].block = (int)i; un[u].col0 = k * SCORE_UNIT_COLS; ++u; }
+            }
+        }
+        d.pool->run((int64_t)rowBlock.size(), 16, [&](int64_t a, int64_t z) {
+            for (int64_t r = a; r < z; ++r) {
+                const uint32_t bi = rowBlock[(size_t)r];
+                const yb_block &b = blocks[lo + bi];
+                const ScoreLayout &L = lay[bi];
+                const uint8_t *src = b.rows[r - rowFirst[bi]];
+                unsigned char *dst = h + textOff + L.off + (size_t)(r - rowFirst[bi]) * (size_t)L.pitch;
+                dst[0] = dst[1] = dst[2] = 0;
+                dst[3] = b.start > 0 ? src[b.start - 1] : 0;            // the column before the range (mz_scores.c:143-147)
+                memcpy(dst + 4, src + b.start, (size_t)b.size);
+                memset(dst + 4 + b.size, 0, (size_t)L.pitch - 4 - (size_t)b.size);
+            }
+        });
+        d.pack_ms += now_ms() - tp;
+        // ---- device ---------------------------------------------------------------------------------------------
+        unsigned char *dIn = static_cast<unsigned char *>(g.dIn.p);
+        CUDA_TRY(d, cudaEventRecord(g.ev[0], g.stream));
+        CUDA_TRY(d, cudaMemcpyAsync(dIn, h, total - 256, cudaMemcpyHostToDevice, g.stream));
+        CUDA_TRY(d, cudaMemsetAsync(g.dSums.p, 0, (size_t)cnt * 8, g.stream));
+        CUDA_TRY(d, cudaEventRecord(g.ev[1], g.stream));
+        if (units > 0) {
+            const int warps = SCORE_THREADS / 32;
+            yb_score_kernel<<<(unsigned)((units + warps - 1) / warps), SCORE_THREADS, 0, g.stream>>>(
+                reinterpret_cast<const ScoreMeta *>(dIn + metaOff), reinterpret_cast<const ScoreUnit *>(dIn + unitOff), (int)units,
+                dIn, static_cast<unsigned long long *>(g.dSums.p), rows32, d.sc);
+            CUDA_TRY(d, cudaGetLastError());
+            ++d.launches;
+        }
+        CUDA_TRY(d, cudaEventRecord(g.ev[2], g.stream));
+        CUDA_TRY(d, cudaMemcpyAsync(g.hSums.p, g.dSums.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, g.stream));
+        CUDA_TRY(d, cudaEventRecord(g.ev[3], g.stream));
+        g.first = lo; g.count = cnt; g.busy = true;
+        d.h2d_bytes += (int64_t)(total - 256);
+        d.d2h_bytes += cnt * 8;
+        ++d.waves;
+        lo = hi;
+    }
+    for (int k = 0; k < 2; ++k) {                      // drain, oldest first
+        ScoreStage &g = d.score[which ^ k];
+        int r2 = score_finish(d, g, scores);
+        if (rc == YB_OK) rc = r2;
+    }
+    if (rc != YB_OK) {
+        for (auto &g : d.score) if (g.busy) { cudaStreamSynchronize(g.stream); g.busy = false; }
+        if (!d.err.empty()) ctx->err = d.err;
+        return rc;
+    }
+    collect_stats(ctx, stats, now_ms() - t0, pairCols, n);
     return YB_OK;
 }
 

@@ -40,7 +40,7 @@ struct ScoreConst {
     int gap_open;   // GO
     int gap_ext;    // GE
 };
-__constant__ ScoreConst c_sc;
+// (passed to the kernels by value: score tables belong to a context, not to the process)
 
 // ---- per-pair descriptor (device copy) --------------------------------------------------------
 struct PairMeta {
@@ -178,7 +178,8 @@ constexpr int K1_THREADS = 128;
 
 __global__ void __launch_bounds__(K1_THREADS)
 yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__restrict__ blob,
-                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int y16) {
+                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int y16,
+                  const __grid_constant__ ScoreConst c_sc) {
     const PairMeta pm = metas[blockIdx.x];
     const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
     if (M < 1) return;                                  // invalid pair (rejected on the host)
@@ -310,7 +311,7 @@ __device__ __forceinline__ void
 fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
           const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
-          const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs) {
+          const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, const int gapOpen, const int gapExt) {
     static_assert(G == 1 || P == 1, "several groups per CTA only for warp-sized groups");
     constexpr int B = 32 * G;                                     // lanes of the wavefront
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -323,7 +324,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
     const unsigned boxAddr = smem0 + P * RING * 16 + grp * B * 32;
     const unsigned slotAddr = smem0 + P * RING * 16 + P * B * 32;
     auto group_sync = [&]() { if (G == 1) __syncwarp(); else __syncthreads(); };
-    const int GO = c_sc.gap_open;
+    const int GO = gapOpen;
     const int nGO = -GO;
     const unsigned E_both = pack16(nGO, nGO);
 
@@ -353,8 +354,8 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
         const RowRec *rows = rowPool + pm.rowBase;
         const ColRec *cols = colPool + pm.colBase;
         unsigned char *tb = tbPool + __ldg(tbBase + p);
-        const unsigned nKGE_lo = launder((unsigned)(-(pm.K * c_sc.gap_ext)) & 0xffffu);   // dp2a.hi weight of byte 2 (ndB)
-        const int KGE = pm.K * c_sc.gap_ext;
+        const unsigned nKGE_lo = launder((unsigned)(-(pm.K * gapExt)) & 0xffffu);   // dp2a.hi weight of byte 2 (ndB)
+        const int KGE = pm.K * gapExt;
         const int nSteps = pm.nSteps;
         const int N16 = pm.N * 16;
         const int KnGO = pm.K * nGO;                        // I-node y / z charge per residue / per closing gap of B

@@ -17,6 +17,7 @@ ABI_SYMBOLS = (
     "yb_create", "yb_destroy", "yb_last_error", "yb_device_count", "yb_set_scores",
     "yb_run_batch", "yb_resident_load", "yb_resident_step", "yb_resident_fetch",
     "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band", "yb_plan_split", "yb_pair_facts", "yb_script_unpack",
+    "yb_score_blocks",
 )
 
 
@@ -55,6 +56,15 @@ JOB_DTYPE = np.dtype([("K", "<i4"), ("M", "<i4"), ("L", "<i4"), ("N", "<i4"),
 RESULT_DTYPE = np.dtype([("status", "<i4"), ("m_new", "<i4"), ("C", "<i4"), ("D", "<i4"), ("I", "<i4"),
                          ("reserved", "<i4"), ("cells", "<i8"), ("script", "<u8")])
 assert JOB_DTYPE.itemsize == C.sizeof(yb_job) and RESULT_DTYPE.itemsize == C.sizeof(yb_result)
+
+
+class yb_block(C.Structure):
+    _fields_ = [("nrows", C.c_int32), ("text_size", C.c_int32), ("start", C.c_int32), ("size", C.c_int32),
+                ("rows", C.c_void_p)]
+
+
+BLOCK_DTYPE = np.dtype([("nrows", "<i4"), ("text_size", "<i4"), ("start", "<i4"), ("size", "<i4"), ("rows", "<u8")])
+assert BLOCK_DTYPE.itemsize == C.sizeof(yb_block)
 
 
 def lib_path() -> str:
@@ -109,6 +119,8 @@ def load_library():
     lib.yb_script_unpack.restype = C.c_int
     lib.yb_pair_facts.argtypes = [P(yb_job), P(C.c_int64), P(C.c_int32), P(C.c_int32), C.c_char_p, C.c_int]
     lib.yb_pair_facts.restype = C.c_int
+    lib.yb_score_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(yb_stats)]
+    lib.yb_score_blocks.restype = C.c_int
     lib.yb_plan_split.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.yb_plan_split.restype = C.c_int
     _LIB = lib
@@ -268,6 +280,38 @@ class YamaB200:
         if rc != 0:
             raise YamaError(rc, "new_align: edit script does not consume both alignments")
         return out
+
+    # ---- block scoring (mafScoreRange, mz_scores.c:124-152) -------------------------------------
+    @staticmethod
+    def make_blocks(blocks) -> tuple[np.ndarray, list]:
+        """blocks: iterable of (text[rows, textSize] u8, start, size) -> (block array, keep-alive)."""
+        keep = []
+        arr = np.zeros(len(blocks), dtype=BLOCK_DTYPE)
+        for i, (text, start, size) in enumerate(blocks):
+            text = _u8(text)
+            if text.ndim != 2:
+                raise ValueError("a block is a [rows, columns] byte matrix")
+            ptrs = np.array([text.ctypes.data + j * text.strides[0] for j in range(text.shape[0])], dtype=np.uint64)
+            keep.append((text, ptrs))
+            arr[i] = (text.shape[0], text.shape[1], start, size, ptrs.ctypes.data if len(ptrs) else 0)
+        return arr, keep
+
+    def score_blocks(self, blocks: np.ndarray, check: bool = True):
+        """blocks: array of BLOCK_DTYPE -> (scores float64[n], stats)."""
+        assert blocks.dtype == BLOCK_DTYPE and blocks.flags.c_contiguous
+        scores = np.zeros(len(blocks), dtype=np.float64)
+        st = yb_stats()
+        rc = self.lib.yb_score_blocks(self.h, len(blocks), blocks.ctypes.data, scores.ctypes.data, C.byref(st))
+        if rc != 0 and check:
+            raise self._err(rc)
+        return scores, st
+
+    def mafScoreRange(self, text, start: int, size: int) -> float:
+        """mafScoreRange(maf, start, size) of one block given as its [rows, textSize] text (mz_scores.c:124)."""
+        arr, keep = self.make_blocks([(text, start, size)])
+        sc, _ = self.score_blocks(arr)
+        del keep
+        return float(sc[0])
 
     # ---- the reference's own call shape -------------------------------------------------------
     def yama(self, A, K, M, B, L, N, LB, RB):

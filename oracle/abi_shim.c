@@ -85,3 +85,18 @@ int yb_assemble(const yb_job *job, const yb_result *res, uint8_t *out) {
     }
     return (i == job->M && j == job->N) ? YB_OK : YB_ERR_TRACEBACK;
 }
+int oracle_score_range(int nrows, const uchar *const *rows, int text_size, int start, int size,
+                       const int *ss, const int *gop, double *out);
+int yb_score_blocks(yb_ctx *c, int64_t n, const yb_block *blocks, double *scores, yb_stats *st) {
+    if (!c->have_scores) { snprintf(c->err, sizeof c->err, "mafScoreRange: scores not initialized"); return YB_ERR_SCORES; }
+    for (int64_t i = 0; i < n; i++) {
+        const yb_block *b = &blocks[i];
+        int rc = oracle_score_range(b->nrows, b->rows, b->text_size, b->start, b->size, c->ss, c->gop, &scores[i]);
+        if (rc) {
+            snprintf(c->err, sizeof c->err, "mafScoreRange: start = %d, size = %d, textSize = %d\n", b->start, b->size, b->text_size);
+            return YB_ERR_ARG;
+        }
+    }
+    if (st) { memset(st, 0, sizeof *st); st->pairs = n; }
+    return YB_OK;
+}

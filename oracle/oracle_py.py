@@ -1,7 +1,8 @@
 """ctypes loaders for the CHECKERS in oracle/ (test infrastructure -- never imported by multiz_b200).
 
-  Oracle     liboracle.so         our plain-C restatement (yama_oracle.c)
-  Reference  _ref/libyama_ref.so  the unmodified reference yama() (mz_yama.c) behind ref_hook.c
+  Oracle     liboracle.so         our plain-C restatements (yama_oracle.c, score_oracle.c)
+  Reference  _ref/libyama_ref.so  the unmodified reference yama() (mz_yama.c) and mafScoreRange (mz_scores.c)
+                                  behind ref_hook.c / ref_score_hook.c
 """
 from __future__ import annotations
 
@@ -26,6 +27,15 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def _row_table(block):
+    """block: uint8 [nrows, text_size] -> (contiguous copy, ctypes array of row pointers)."""
+    blk = _u8(block)
+    if blk.ndim != 2:
+        raise ValueError("a block is a [rows, columns] byte matrix")
+    ptrs = (C.c_void_p * max(1, blk.shape[0]))(*[blk.ctypes.data + j * blk.strides[0] for j in range(blk.shape[0])])
+    return blk, ptrs
+
+
 def cells_of(LB, RB) -> int:
     return int((np.asarray(RB, dtype=np.int64) - np.asarray(LB, dtype=np.int64) + 1).sum())
 
@@ -46,7 +56,20 @@ class Oracle:
         self.lib.oracle_scores.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         self.lib.oracle_check_band.restype = C.c_long
         self.lib.oracle_check_band.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        self.lib.oracle_score_range.restype = C.c_int
+        self.lib.oracle_score_range.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.POINTER(C.c_double)]
         self.set_scores(which)
+
+    def score_range(self, block, start, size):
+        """mafScoreRange of a [rows, textSize] block; ValueError(message) for a bad range."""
+        blk, ptrs = _row_table(block)
+        out = C.c_double()
+        rc = self.lib.oracle_score_range(blk.shape[0], ptrs, blk.shape[1], start, size, self.ss.ctypes.data,
+                                         self.gop.ctypes.data, C.byref(out))
+        if rc:
+            raise ValueError("mafScoreRange: start = %d, size = %d, textSize = %d\n" % (start, size, blk.shape[1]))
+        return out.value
 
     def set_scores(self, which):
         self.ss = np.zeros((128, 128), dtype=np.int32)
@@ -97,7 +120,15 @@ class Reference:
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.lib.ref_init_scores.argtypes = [C.c_int]
         self.lib.ref_get_tables.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        self.lib.ref_score_range.restype = C.c_double
+        self.lib.ref_score_range.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         self.lib.ref_init_scores(which)
+
+    def score_range(self, block, start, size):
+        """The reference's mafScoreRange; the range must be valid (the reference exit(1)s otherwise)."""
+        blk, ptrs = _row_table(block)
+        assert 0 <= start and size > 0 and start + size <= blk.shape[1]
+        return float(self.lib.ref_score_range(blk.shape[0], ptrs, blk.shape[1], start, size))
 
     @staticmethod
     def available() -> bool:

@@ -60,3 +60,23 @@ class GoldenYama:
                 assert np.array_equal(digest(got["tback"]), e["tback"]), ("tback", i)
         if "cells" in got:
             assert int(got["cells"]) == e["cells"]
+
+
+class GoldenScores:
+    """tests/golden/score_small.npz: blocks[i] = (text[rows, cols], start, size); score70/score85 = the reference's
+    mafScoreRange (mz_scores.c:124-152) under init_scores70 / init_scores85."""
+
+    def __init__(self, name="score_small.npz"):
+        self.z = np.load(os.path.join(GOLD, name))
+        self.n = len(self.z["rows"])
+
+    def block(self, i):
+        z = self.z
+        off = z["text_off"]
+        return (z["text"][off[i]:off[i + 1]].reshape(int(z["rows"][i]), int(z["cols"][i])), int(z["start"][i]), int(z["size"][i]))
+
+    def blocks(self):
+        return [self.block(i) for i in range(self.n)]
+
+    def expected(self, which=70):
+        return self.z[f"score{which}"]

@@ -140,12 +140,34 @@ def make_maf_golden():
             subprocess.run([tool] + argv, cwd=d, stdout=f, check=True)
 
 
+def make_score_golden(ref):
+    # block scoring: the reference's mafScoreRange under both score sets
+    from tools.score_cases import score_cases
+    cases = score_cases()
+    refs = {70: ref, 85: Reference(85)}      # (init_scores70/85 switch the globals of the one library: score per set in turn)
+    out = {}
+    for which in (70, 85):
+        refs[which].lib.ref_init_scores(which)
+        out[which] = np.asarray([refs[which].score_range(t, s, n) for (t, s, n) in cases], dtype=np.float64)
+    ref.lib.ref_init_scores(70)
+    np.savez_compressed(
+        os.path.join(GOLD, "score_small.npz"),
+        rows=np.asarray([t.shape[0] for t, _, _ in cases], np.int32), cols=np.asarray([t.shape[1] for t, _, _ in cases], np.int32),
+        start=np.asarray([s for _, s, _ in cases], np.int32), size=np.asarray([n for _, _, n in cases], np.int32),
+        text=np.concatenate([t.ravel() for t, _, _ in cases]),
+        text_off=np.concatenate([[0], np.cumsum([t.size for t, _, _ in cases])]).astype(np.int64),
+        score70=out[70], score85=out[85])
+
+
 def main():
     build(quiet=True)
     if not Reference.available():
         raise SystemExit("oracle/_ref/libyama_ref.so missing: needs /root/reference")
     os.makedirs(GOLD, exist_ok=True)
     ref = Reference(70)
+    if sys.argv[1:] == ["score"]:            # only the block-scoring fixture
+        make_score_golden(ref)
+        return
     np.savez_compressed(os.path.join(GOLD, "yama_small.npz"), **pack_problems(ref, small_problems(), full=True))
     np.savez_compressed(os.path.join(GOLD, "yama_deep.npz"), **pack_problems(ref, deep_problems(), full=False))
 
@@ -156,6 +178,8 @@ def main():
         sc[f"ss{which}"], sc[f"gop{which}"], sc[f"ge{which}"] = ss, gop, np.asarray([ge], np.int32)
     Reference(70)   # leave the shared library's globals on HOXD70
     np.savez_compressed(os.path.join(GOLD, "scores.npz"), **sc)
+
+    make_score_golden(ref)
 
     host = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libhost_ref.so"))
     host.smooth.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
