@@ -1,0 +1,50 @@
+/* score_dropin.c -- the reference-side binding of block scoring: multiz's own `mafScoreRange` symbol
+ * (mz_scores.h:19, defined in mz_scores.c:124-152), re-routed.  The reference's definition is kept, renamed at
+ * compile time (mz_scores.c is compiled with -DmafScoreRange=ref_mafScoreRange, integration/Makefile); this file
+ * supplies the symbol every caller links to (mz_preyama.c:79, multi_util.c:509,:581,:611,:794,:802) and decides:
+ *
+ *   speculative pass of the record/replay driver (yama_dropin.cpp): return 0.  The pass's output is discarded and
+ *       scores never steer the host (they are only stored in mafAli::score and printed by mafWrite, maf.c:257-258),
+ *       so the O(rows^2 * columns) loop is simply skipped there;
+ *   real pass, default: the reference's own function (kept host code);
+ *   real pass, YB_SCORE=gpu: yb_score_blocks() of libyama_b200.so, one synchronous call per block -- pays off for
+ *       deep alignments (tens of rows), costs a launch latency per block for shallow ones.
+ *
+ * This file is C because it walks the reference's own structs (maf.h:28-58), included from the reference tree.
+ */
+#include <stdlib.h>
+#include "maf.h"
+
+void fatalf(const char *fmt, ...);                                   /* util.c:21 */
+void fatal(const char *msg);                                          /* util.c:17 */
+extern int **ss;                                                      /* mz_scores.h:8 */
+double ref_mafScoreRange(struct mafAli *maf, int start, int size);    /* the reference's, renamed */
+/* yama_dropin.cpp */
+int yb_dropin_score_mode(void);                                       /* 0: host function, 1: skip (speculative pass), 2: GPU */
+double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size);
+
+double mafScoreRange(struct mafAli *maf, int start, int size) {
+    const int mode = yb_dropin_score_mode();
+    if (mode == 0) return ref_mafScoreRange(maf, start, size);
+    /* the reference's checks, in its order and wording (mz_scores.c:130-134) */
+    if (start < 0 || size <= 0 || start + size > maf->textSize)
+        fatalf("mafScoreRange: start = %d, size = %d, textSize = %d\n", start, size, maf->textSize);
+    if (ss == NULL)
+        fatal("mafScoreRange: scores not initialized");
+    if (mode == 1) return 0.0;
+    {
+        static const unsigned char **rows = NULL;
+        static int cap = 0;
+        int n = 0;
+        struct mafComp *c;
+        for (c = maf->components; c != NULL; c = c->next) {
+            if (n == cap) {
+                cap = cap ? 2 * cap : 64;
+                rows = realloc(rows, (size_t)cap * sizeof *rows);
+                if (rows == NULL) fatal("mafScoreRange: out of memory");
+            }
+            rows[n++] = (const unsigned char *)c->text;
+        }
+        return yb_dropin_score(n, rows, maf->textSize, start, size);
+    }
+}

@@ -50,6 +50,9 @@ void fatalf(const char *fmt, ...);
 int ref_tool_main(int argc, char **argv) __attribute__((weak));
 void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uchar ***OAL, int *OM);
 void yb_host_exit(int code) __attribute__((noreturn));
+// block scoring, called by score_dropin.c (the `mafScoreRange` symbol)
+int yb_dropin_score_mode(void);
+double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size);
 }
 
 namespace {
@@ -97,6 +100,9 @@ struct Globals {
     int64_t cells = 0, batches = 0, jobs = 0, failed = 0;
     int passes = 0;
     double child_ms = 0, final_ms = 0;      // wall time of the speculative passes / of the real pass
+    int scoreGpu = -1;                      // YB_SCORE=gpu: mafScoreRange on the device in the real pass
+    uint64_t scoreCalls = 0;
+    double score_ms = 0;
     bool debug = false;
     std::unordered_map<Key, int, KeyHash> failedKeys;   // debug: batch status of jobs that did not align
 } G;
@@ -411,10 +417,10 @@ void print_stats() {
     if (!G.stats) return;
     fprintf(stderr,
             "yama_b200: passes=%d batches=%lld jobs=%lld failed=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
-            "gpu_ms=%.2f kernel_ms=%.2f speculative_ms=%.0f final_ms=%.0f devices=%d\n",
+            "gpu_ms=%.2f kernel_ms=%.2f speculative_ms=%.0f final_ms=%.0f score_calls=%llu score_ms=%.1f devices=%d\n",
             G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.failed, (long long)G.cells, (unsigned long long)G.calls,
             (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.child_ms, G.final_ms,
-            G.ctx ? yb_device_count(G.ctx) : 0);
+            (unsigned long long)G.scoreCalls, G.score_ms, G.ctx ? yb_device_count(G.ctx) : 0);
 }
 
 }  // namespace
@@ -432,6 +438,30 @@ void yb_host_exit(int code) {
     fflush(nullptr);
     print_stats();
     exit(code);
+}
+
+// mafScoreRange (score_dropin.c): skipped in a speculative pass, the host's own function by default, the device
+// with YB_SCORE=gpu
+int yb_dropin_score_mode(void) {
+    if (G.mode == RECORD) return 1;
+    if (G.scoreGpu < 0) {
+        const char *e = getenv("YB_SCORE");
+        G.scoreGpu = (e && strcmp(e, "gpu") == 0) ? 1 : 0;
+    }
+    return G.scoreGpu ? 2 : 0;
+}
+
+double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size) {
+    ensure_ctx();
+    yb_block blk;
+    blk.nrows = nrows; blk.text_size = text_size; blk.start = start; blk.size = size; blk.rows = rows;
+    double score = 0.0;
+    const double t0 = now_ms();
+    const int rc = yb_score_blocks(G.ctx, 1, &blk, &score, nullptr);
+    G.score_ms += now_ms() - t0;
+    ++G.scoreCalls;
+    if (rc != YB_OK) fatalf("%s", yb_last_error(G.ctx));     // (a bad range carries the reference's own message)
+    return score;
 }
 
 void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uchar ***OAL, int *OM) {

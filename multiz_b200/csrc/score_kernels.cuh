@@ -30,6 +30,7 @@ struct ScoreUnit { int block, col0; };      // one warp: columns col0 .. col0+12
 
 constexpr int SCORE_THREADS = 128;
 constexpr int SCORE_UNIT_COLS = 128;
+constexpr int SCORE_ROWS = 8;              // rows in flight per lane
 
 template <typename T>
 __device__ __forceinline__ T column_score(const ScoreConst &c_sc, const int n[6], int t01, int t10, int t11, int nrows, bool gap) {
@@ -70,18 +71,30 @@ yb_score_kernel(const ScoreMeta *__restrict__ metas, const ScoreUnit *__restrict
     for (int j0 = 0; j0 < bm.nrows; j0 += 255) {
         const int j1 = min(bm.nrows, j0 + 255);
         unsigned cA = 0, cC = 0, cG = 0, cT = 0, c01 = 0, c11 = 0, c10 = 0;      // byte lane b counts column c0+b
-#pragma unroll 4
-        for (int j = j0; j < j1; ++j) {
-            const unsigned w = live ? __ldg(reinterpret_cast<const unsigned *>(p)) : 0u;
-            unsigned pw = __shfl_up_sync(0xffffffffu, w, 1);
-            if (lane == 0) pw = __ldg(reinterpret_cast<const unsigned *>(p - 4));   // the lead word, or the unit before
-            p += pitch;
-            const unsigned lw = w | 0x20202020u;
-            const unsigned mD = eq_bytes80(w, 0x2d2d2d2du);
-            const unsigned pD = __funnelshift_l(eq_bytes80(pw, 0x2d2d2d2du), mD, 8);   // dash mask of the column before
-            cA += eq_bytes80(lw, 0x61616161u) >> 7; cC += eq_bytes80(lw, 0x63636363u) >> 7;
-            cG += eq_bytes80(lw, 0x67676767u) >> 7; cT += eq_bytes80(lw, 0x74747474u) >> 7;
-            c01 += (mD & ~pD) >> 7; c11 += (mD & pD) >> 7; c10 += (pD & ~mD) >> 7;
+        // SCORE_ROWS rows per trip: all their loads are issued before the first one is consumed (the kernel is
+        // bound by bytes in flight, and loads do not move across the warp shuffle below on their own)
+        for (int j = j0; j < j1; j += SCORE_ROWS) {
+            unsigned wv[SCORE_ROWS], lead[SCORE_ROWS];
+#pragma unroll
+            for (int k = 0; k < SCORE_ROWS; ++k) {
+                const bool in = j + k < j1;
+                wv[k] = (live && in) ? __ldg(reinterpret_cast<const unsigned *>(p + (size_t)k * pitch)) : 0u;
+                lead[k] = (lane == 0 && in) ? __ldg(reinterpret_cast<const unsigned *>(p + (size_t)k * pitch - 4)) : 0u;
+            }
+            p += (size_t)min(SCORE_ROWS, j1 - j) * pitch;
+#pragma unroll
+            for (int k = 0; k < SCORE_ROWS; ++k) {
+                if (j + k >= j1) break;
+                const unsigned w = wv[k];
+                unsigned pw = __shfl_up_sync(0xffffffffu, w, 1);
+                if (lane == 0) pw = lead[k];                                        // the lead word, or the unit before
+                const unsigned lw = w | 0x20202020u;
+                const unsigned mD = eq_bytes80(w, 0x2d2d2d2du);
+                const unsigned pD = __funnelshift_l(eq_bytes80(pw, 0x2d2d2d2du), mD, 8);   // dash mask of the column before
+                cA += eq_bytes80(lw, 0x61616161u) >> 7; cC += eq_bytes80(lw, 0x63636363u) >> 7;
+                cG += eq_bytes80(lw, 0x67676767u) >> 7; cT += eq_bytes80(lw, 0x74747474u) >> 7;
+                c01 += (mD & ~pD) >> 7; c11 += (mD & pD) >> 7; c10 += (pD & ~mD) >> 7;
+            }
         }
         const unsigned acc[7] = {cA, cC, cG, cT, c01, c11, c10};
 #pragma unroll

@@ -19,6 +19,12 @@ def test_golden_maf_cases(tmp_path, mode):
     check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_DROPIN": mode})
 
 
+def test_golden_maf_cases_with_block_scores_through_the_abi(tmp_path):
+    """YB_SCORE=gpu routes the host's mafScoreRange (mz_scores.c:124) through yb_score_blocks in the real pass and
+    skips it in the speculative passes; every `a score=` line must still match the reference's."""
+    check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_SCORE": "gpu"})
+
+
 @pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin/multiz not built")
 def test_fresh_data_against_reference_binary(tmp_path):
     rep = check_against_live_reference(SHIM_MULTIZ, tmp_path, ref_len=60_000, n_species=4, seed=5,

@@ -21,6 +21,17 @@ def test_golden_maf_cases_gpu(tmp_path, mode):
     check_golden_cases(GPU_MULTIZ, tmp_path, env={"YB_DROPIN": mode})
 
 
+def test_block_scores_on_the_device(tmp_path):
+    """YB_SCORE=gpu: the host's mafScoreRange calls (mz_preyama.c:79, multi_util.c:509..802) answered by
+    yb_score_kernel -- the `a score=` lines of every golden case and of a fresh progressive merge stay identical."""
+    _need(GPU_MULTIZ); _need(REF_MULTIZ)
+    check_golden_cases(GPU_MULTIZ, tmp_path / "golden", env={"YB_SCORE": "gpu"})
+    rep = check_against_live_reference(GPU_MULTIZ, tmp_path / "fresh", ref_len=100_000, n_species=4, seed=12,
+                                       env={"YB_SCORE": "gpu", "YB_DROPIN_STATS": "1"})
+    stats = [last[0] for _, _, last in rep if last]
+    assert stats and all("score_calls=" in s and "score_calls=0 " not in s for s in stats), stats
+
+
 def test_cfg1_one_megabase_merge(tmp_path):
     """configs[0]: multiz merge of two synthetic pairwise MAFs on a 1 Mb reference, R=30 M=1, v=1 and v=0."""
     _need(GPU_MULTIZ); _need(REF_MULTIZ)
