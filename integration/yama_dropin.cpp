@@ -21,6 +21,7 @@
 // order.  There is no CPU alignment code here: without a usable GPU yama() dies through fatalf(), the
 // reference's own error convention (util.c:17-32).
 #include "../include/yama_b200.h"
+#include "yb_wire.h"
 
 #include <cerrno>
 #include <cstdint>
@@ -28,10 +29,16 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include <fcntl.h>
+#include <malloc.h>
+#include <stdio_ext.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/un.h>
 #include <sys/time.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -50,6 +57,7 @@ void fatalf(const char *fmt, ...);
 int ref_tool_main(int argc, char **argv) __attribute__((weak));
 void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uchar ***OAL, int *OM);
 void yb_host_exit(int code) __attribute__((noreturn));
+FILE *yb_host_fopen(const char *path, const char *mode);
 // block scoring, called by score_dropin.c (the `mafScoreRange` symbol)
 int yb_dropin_score_mode(void);
 double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size);
@@ -100,6 +108,7 @@ struct Globals {
     int64_t cells = 0, batches = 0, jobs = 0, failed = 0;
     int passes = 0;
     double child_ms = 0, final_ms = 0;      // wall time of the speculative passes / of the real pass
+    double create_ms = 0, t_start = 0;      // yb_create (CUDA start-up), process start
     int scoreGpu = -1;                      // YB_SCORE=gpu: mafScoreRange on the device in the real pass
     uint64_t scoreCalls = 0;
     double score_ms = 0;
@@ -160,8 +169,13 @@ Key key_of(int K, int M, int L, int N, const uint8_t *A, const uint8_t *B, const
 // main() -- hence init_scores70/85 -- when it aligns the first batch)
 std::vector<int32_t> g_wireScores;     // 128*128 ss + 16 gop + gap_extend
 
-void ensure_ctx() {
-    if (G.ctx) return;
+// CUDA start-up (driver + context + module load, around a second) runs on its own thread while the first speculative
+// pass reads and walks the inputs: the parent forks first (a child never touches CUDA), then starts this.
+std::thread g_warm;
+int g_createRc = YB_OK;
+
+void create_ctx() {
+    const double t0 = now_ms();
     std::vector<int> devs;
     if (const char *e = getenv("YB_DEVICES")) {
         for (const char *p = e; *p;) {
@@ -169,8 +183,24 @@ void ensure_ctx() {
             while (*p == ',' || *p == ' ') ++p;
         }
     }
-    int rc = yb_create(devs.empty() ? nullptr : devs.data(), (int)devs.size(), &G.ctx);
-    if (rc != YB_OK) fatalf("yama_b200: no usable CUDA device (this yama has no CPU implementation)");
+    g_createRc = yb_create(devs.empty() ? nullptr : devs.data(), (int)devs.size(), &G.ctx);
+    G.create_ms = now_ms() - t0;
+}
+
+void warm_ctx() {
+    if (G.ctx || g_warm.joinable()) return;
+    g_warm = std::thread(create_ctx);
+}
+
+bool g_scoresStale = false;
+void ensure_ctx() {
+    static bool ready = false;
+    if (ready && !g_scoresStale) return;
+    g_scoresStale = false;
+    if (g_warm.joinable()) g_warm.join();
+    else if (!G.ctx) create_ctx();
+    int rc = g_createRc;
+    if (rc != YB_OK || !G.ctx) fatalf("yama_b200: no usable CUDA device (this yama has no CPU implementation)");
     if (!g_wireScores.empty()) {
         rc = yb_set_scores(G.ctx, g_wireScores.data(), g_wireScores.data() + 128 * 128, g_wireScores[128 * 128 + 16]);
     } else {
@@ -180,6 +210,183 @@ void ensure_ctx() {
         rc = yb_set_scores(G.ctx, flat.data(), gop, gap_extend);
     }
     if (rc != YB_OK) fatalf("yama_b200: %s", yb_last_error(G.ctx));
+    ready = true;
+}
+
+// ---- the resident server (yama_b200d, yama_served.cpp) as the backend -----------------------------------------
+// YB_SERVER=auto | 1 | <socket path>: batches and block scores go to a yama_b200d process over a unix socket instead
+// of a CUDA context of our own -- no driver start-up, no buffer allocation in this process.  If nobody answers on
+// the socket the drop-in starts the server itself (YB_SERVER_SPAWN=0 forbids that) and waits for it.
+struct Remote {
+    bool enabled = false;
+    std::string path, err;
+    int fd = -1;
+    int devices = 0;
+    std::vector<uint8_t> scripts;        // packed scripts of the last batch
+    std::vector<ybwire::Job> wjobs;
+    std::vector<ybwire::Res> wres;
+    std::vector<uint8_t> tmp;
+} R;
+
+bool write_full(int fd, const void *src, size_t n) {
+    const uint8_t *p = static_cast<const uint8_t *>(src);
+    while (n) {
+        ssize_t k = write(fd, p, n);
+        if (k < 0) { if (errno == EINTR) continue; return false; }
+        p += k; n -= (size_t)k;
+    }
+    return true;
+}
+bool read_full(int fd, void *dst, size_t n);
+
+void remote_configure() {
+    const char *e = getenv("YB_SERVER");
+    if (!e || !*e || !strcmp(e, "0") || !strcmp(e, "off")) return;
+    R.enabled = true;
+    if (!strcmp(e, "auto") || !strcmp(e, "1")) {
+        char b[128];
+        snprintf(b, sizeof b, "/tmp/yama_b200-%u.sock", (unsigned)getuid());
+        R.path = b;
+    } else R.path = e;
+}
+
+int remote_try_connect() {
+    sockaddr_un addr{};
+    addr.sun_family = AF_UNIX;
+    if (R.path.size() >= sizeof addr.sun_path) fatalf("yama_b200: YB_SERVER socket path too long");
+    strcpy(addr.sun_path, R.path.c_str());
+    int fd = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (fd < 0) return -1;
+    if (connect(fd, reinterpret_cast<sockaddr *>(&addr), sizeof addr) != 0) { close(fd); return -1; }
+    return fd;
+}
+
+void remote_spawn() {
+    if (const char *e = getenv("YB_SERVER_SPAWN")) if (!strcmp(e, "0")) return;
+    std::string bin;
+    if (const char *e = getenv("YB_SERVER_BIN")) bin = e;
+    else {
+        char self[4096];
+        ssize_t n = readlink("/proc/self/exe", self, sizeof self - 1);
+        if (n <= 0) return;
+        self[n] = 0;
+        bin = self;
+        bin = bin.substr(0, bin.rfind('/') + 1) + "yama_b200d";
+    }
+    fflush(nullptr);
+    pid_t pid = fork();
+    if (pid != 0) { if (pid > 0) { int st; while (waitpid(pid, &st, 0) < 0 && errno == EINTR) {} } return; }
+    if (fork() != 0) _exit(0);                    // grandchild: not ours to wait for
+    setsid();
+    char log[128];
+    snprintf(log, sizeof log, "/tmp/yama_b200d-%u.log", (unsigned)getuid());
+    int nul = open("/dev/null", O_RDWR), lg = open(log, O_WRONLY | O_CREAT | O_APPEND, 0600);
+    if (nul >= 0) { dup2(nul, 0); dup2(nul, 1); }
+    if (lg >= 0) dup2(lg, 2); else if (nul >= 0) dup2(nul, 2);
+    for (int fd = 3; fd < 256; ++fd) close(fd);
+    const char *idle = getenv("YB_SERVER_IDLE_S");
+    if (idle) execl(bin.c_str(), "yama_b200d", "--socket", R.path.c_str(), "--idle", idle, (char *)nullptr);
+    else execl(bin.c_str(), "yama_b200d", "--socket", R.path.c_str(), (char *)nullptr);
+    _exit(127);
+}
+
+// first contact, as early as possible (while the speculative pass runs): start the server if nobody is there
+void remote_begin() {
+    if (!R.enabled || R.fd >= 0) return;
+    R.fd = remote_try_connect();
+    if (R.fd < 0) remote_spawn();
+}
+
+void remote_hello() {
+    ybwire::Hello h{ybwire::MAGIC_HELLO, ybwire::VERSION};
+    std::vector<int32_t> sc;
+    if (!g_wireScores.empty()) sc = g_wireScores;
+    else {
+        if (!ss || !gop) fatalf("yama_b200: score tables not initialised (init_scores70/85 must run before yama)");
+        sc.resize(ybwire::SCORE_INTS);
+        for (int c = 0; c < 128; ++c) memcpy(&sc[(size_t)c * 128], ss[c], 128 * sizeof(int));
+        memcpy(&sc[128 * 128], gop, 16 * sizeof(int));
+        sc[128 * 128 + 16] = gap_extend;
+    }
+    if (!write_full(R.fd, &h, sizeof h) || !write_full(R.fd, sc.data(), sc.size() * 4))
+        fatalf("yama_b200: lost the server at %s", R.path.c_str());
+}
+
+void remote_ensure() {
+    static bool greeted = false;
+    if (R.fd < 0) {
+        double wait_s = 60;
+        if (const char *e = getenv("YB_SERVER_WAIT_S")) wait_s = atof(e);
+        const double t0 = now_ms();
+        for (;;) {
+            R.fd = remote_try_connect();
+            if (R.fd >= 0 || now_ms() - t0 > wait_s * 1e3) break;
+            usleep(20000);
+        }
+        if (R.fd < 0) fatalf("yama_b200: no server answers on %s (YB_SERVER)", R.path.c_str());
+        greeted = false;
+    }
+    if (!greeted) { remote_hello(); greeted = true; }
+}
+
+// jobs whose inputs all lie inside [base, base+baseBytes) go up without a copy; a lone job is packed first
+int remote_batch(int64_t n, const yb_job *jobs, yb_result *res, yb_stats *st, const uint8_t *base, size_t baseBytes) {
+    remote_ensure();
+    if (!base) {
+        R.tmp.clear();
+        std::vector<size_t> offs;
+        auto add = [&](const void *p, size_t bytes) {
+            size_t off = (R.tmp.size() + 15) & ~(size_t)15;
+            R.tmp.resize(off + bytes);
+            memcpy(R.tmp.data() + off, p, bytes);
+            offs.push_back(off);
+        };
+        for (int64_t i = 0; i < n; ++i) {
+            add(jobs[i].A, (size_t)jobs[i].K * jobs[i].M); add(jobs[i].B, (size_t)jobs[i].L * jobs[i].N);
+            add(jobs[i].LB, (size_t)(jobs[i].M + 1) * 4); add(jobs[i].RB, (size_t)(jobs[i].M + 1) * 4);
+        }
+        R.wjobs.resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i)
+            R.wjobs[(size_t)i] = ybwire::Job{jobs[i].K, jobs[i].M, jobs[i].L, jobs[i].N, offs[4 * i], offs[4 * i + 1], offs[4 * i + 2], offs[4 * i + 3]};
+        base = R.tmp.data();
+        baseBytes = R.tmp.size();
+    } else {
+        R.wjobs.resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i)
+            R.wjobs[(size_t)i] = ybwire::Job{jobs[i].K, jobs[i].M, jobs[i].L, jobs[i].N, (uint64_t)(jobs[i].A - base), (uint64_t)(jobs[i].B - base),
+                                             (uint64_t)(reinterpret_cast<const uint8_t *>(jobs[i].LB) - base),
+                                             (uint64_t)(reinterpret_cast<const uint8_t *>(jobs[i].RB) - base)};
+    }
+    ybwire::BatchReq rq{ybwire::MAGIC_BATCH, 0, (uint64_t)n, (uint64_t)baseBytes};
+    ybwire::BatchResp rp;
+    R.wres.resize((size_t)n);
+    if (!write_full(R.fd, &rq, sizeof rq) || !write_full(R.fd, R.wjobs.data(), R.wjobs.size() * sizeof(ybwire::Job)) ||
+        !write_full(R.fd, base, baseBytes) || !read_full(R.fd, &rp, sizeof rp) || rp.magic != ybwire::MAGIC_RESP || rp.n != (uint64_t)n ||
+        !read_full(R.fd, R.wres.data(), R.wres.size() * sizeof(ybwire::Res)))
+        fatalf("yama_b200: lost the server at %s", R.path.c_str());
+    R.scripts.resize((size_t)rp.scriptBytes + 1);
+    R.err.resize(rp.errLen);
+    if (!read_full(R.fd, R.scripts.data(), (size_t)rp.scriptBytes) || !read_full(R.fd, &R.err[0], rp.errLen))
+        fatalf("yama_b200: lost the server at %s", R.path.c_str());
+    for (int64_t i = 0; i < n; ++i) {
+        memset(&res[i], 0, sizeof res[i]);
+        res[i].status = R.wres[(size_t)i].status;
+        res[i].m_new = R.wres[(size_t)i].m_new;
+        res[i].script = R.scripts.data() + R.wres[(size_t)i].scriptOff;
+    }
+    memset(st, 0, sizeof *st);
+    st->kernel_ms = rp.kernel_ms; st->total_ms = rp.total_ms; st->cells = rp.cells; st->pairs = n;
+    R.devices = rp.devices;
+    return rp.rc;
+}
+
+const char *backend_error() { return R.enabled ? R.err.c_str() : (G.ctx ? yb_last_error(G.ctx) : "device failure"); }
+
+// one batch through whichever backend this process uses
+int backend_batch(int64_t n, const yb_job *jobs, yb_result *res, yb_stats *st, const uint8_t *base = nullptr, size_t baseBytes = 0) {
+    if (R.enabled) return remote_batch(n, jobs, res, st, base, baseBytes);
+    ensure_ctx();
+    return yb_run_batch(G.ctx, n, jobs, res, st);
 }
 
 // allocate the reference's output shape: caller frees AL[1] and AL+1 (mz_yama.h:17-18)
@@ -207,15 +414,14 @@ void emit(const yb_job &job, int m_new, const uint8_t *script, uchar ***OAL, int
 
 void fail_from_status(int status) {
     if (status == YB_ERR_TRACEBACK) fatalf("Error generating edit script.");
-    fatalf("yama_b200: %s", G.ctx ? yb_last_error(G.ctx) : "device failure");
+    fatalf("yama_b200: %s", backend_error());
 }
 
 void run_direct(const yb_job &job, uchar ***OAL, int *OM) {
-    ensure_ctx();
     yb_result r;
     yb_stats st;
     double t0 = now_ms();
-    int rc = yb_run_batch(G.ctx, 1, &job, &r, &st);
+    int rc = backend_batch(1, &job, &r, &st);
     G.gpu_ms += now_ms() - t0;
     G.kernel_ms += st.kernel_ms;
     G.cells += st.cells;
@@ -306,7 +512,7 @@ bool drain_child(int fd, WireEnd &end) {
             std::vector<int32_t> sc(128 * 128 + 17);
             if (!read_full(fd, sc.data(), sc.size() * 4)) return false;
             if (!g_wireScores.empty() && sc != g_wireScores) {       // tables changed between passes: start over
-                if (G.ctx) { yb_destroy(G.ctx); G.ctx = nullptr; }
+                g_scoresStale = true;                       // ensure_ctx() uploads the new tables before the next batch
                 G.table.clear();
                 G.scripts.clear();
             }
@@ -333,7 +539,6 @@ bool drain_child(int fd, WireEnd &end) {
 
 void align_pending() {
     if (G.pending.empty()) return;
-    ensure_ctx();
     const size_t n = G.pending.size();
     std::vector<yb_job> jobs(n);
     for (size_t i = 0; i < n; ++i) {
@@ -347,13 +552,13 @@ void align_pending() {
     std::vector<yb_result> res(n);
     yb_stats st;
     double t0 = now_ms();
-    int rc = yb_run_batch(G.ctx, (int64_t)n, jobs.data(), res.data(), &st);
+    int rc = backend_batch((int64_t)n, jobs.data(), res.data(), &st, G.arena.data(), G.arena.size());
     G.gpu_ms += now_ms() - t0;
     G.kernel_ms += st.kernel_ms;
     G.cells += st.cells;
     G.jobs += (int64_t)n;
     ++G.batches;
-    if (rc == YB_ERR_CUDA || rc == YB_ERR_SCORES || rc == YB_ERR_ARG) fatalf("yama_b200: %s", yb_last_error(G.ctx));
+    if (rc == YB_ERR_CUDA || rc == YB_ERR_SCORES || rc == YB_ERR_ARG) fatalf("yama_b200: %s", backend_error());
     // per-pair failures (band / limit / traceback) are not fatal here: the final pass meets the same job
     // as a miss and reports it at the point where the reference would
     for (size_t i = 0; i < n; ++i) {
@@ -395,6 +600,7 @@ int run_batched(int argc, char **argv) {
             yb_host_exit(0);
         }
         close(fds[1]);
+        if (R.enabled) remote_begin(); else warm_ctx();
         WireEnd end{};
         const bool clean = drain_child(fds[0], end);
         close(fds[0]);
@@ -413,19 +619,42 @@ int run_batched(int argc, char **argv) {
     return rc;
 }
 
+void print_stats();
+// End of the process: everything the tool wrote is flushed, then _exit -- tearing the CUDA context down buffer by
+// buffer (yb_destroy + the runtime's atexit handlers) costs a few hundred milliseconds that no caller needs; the
+// driver reclaims the context with the process.  The reference registers no atexit handlers of its own.
+[[noreturn]] void finish_process(int code) {
+    if (g_warm.joinable()) g_warm.join();
+    fflush(nullptr);
+    print_stats();
+    fflush(nullptr);
+    _exit(code);
+}
+
 void print_stats() {
     if (!G.stats) return;
     fprintf(stderr,
             "yama_b200: passes=%d batches=%lld jobs=%lld failed=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
-            "gpu_ms=%.2f kernel_ms=%.2f speculative_ms=%.0f final_ms=%.0f score_calls=%llu score_ms=%.1f devices=%d\n",
+            "gpu_ms=%.2f kernel_ms=%.2f create_ms=%.0f speculative_ms=%.0f final_ms=%.0f wall_ms=%.0f score_calls=%llu score_ms=%.1f devices=%d\n",
             G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.failed, (long long)G.cells, (unsigned long long)G.calls,
-            (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.child_ms, G.final_ms,
-            (unsigned long long)G.scoreCalls, G.score_ms, G.ctx ? yb_device_count(G.ctx) : 0);
+            (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.create_ms, G.child_ms, G.final_ms,
+            now_ms() - G.t_start, (unsigned long long)G.scoreCalls, G.score_ms, R.enabled ? R.devices : (G.ctx ? yb_device_count(G.ctx) : 0));
 }
 
 }  // namespace
 
 extern "C" {
+
+// fopen() of the reference objects (compiled with -Dfopen=yb_host_fopen; util.c:36 ckopen, multi_util.c:107, multiz.c:242-243).  The host
+// reads and writes MAF a character at a time (fgetc/fputc, maf.c); once a process has ever started a thread -- ours
+// does: the packing helpers, the CUDA runtime -- glibc takes the stream lock on every one of those calls, which
+// made the real pass 1.7x slower than the same pass in a thread-free process.  Only one thread ever runs host
+// code, so its streams need no locking.
+FILE *yb_host_fopen(const char *path, const char *mode) {
+    FILE *f = fopen(path, mode);
+    if (f) __fsetlocking(f, FSETLOCKING_BYCALLER);
+    return f;
+}
 
 // exit() of the reference objects (compiled with -Dexit=yb_host_exit): a forked speculative pass must not
 // run the parent's atexit handlers (the CUDA runtime's among them) and must flush its job pipe.
@@ -435,9 +664,7 @@ void yb_host_exit(int code) {
         fflush(nullptr);
         _exit(code);
     }
-    fflush(nullptr);
-    print_stats();
-    exit(code);
+    finish_process(code);
 }
 
 // mafScoreRange (score_dropin.c): skipped in a speculative pass, the host's own function by default, the device
@@ -452,15 +679,29 @@ int yb_dropin_score_mode(void) {
 }
 
 double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size) {
-    ensure_ctx();
-    yb_block blk;
-    blk.nrows = nrows; blk.text_size = text_size; blk.start = start; blk.size = size; blk.rows = rows;
     double score = 0.0;
     const double t0 = now_ms();
-    const int rc = yb_score_blocks(G.ctx, 1, &blk, &score, nullptr);
+    int rc;
+    if (R.enabled) {
+        remote_ensure();
+        ybwire::ScoreReq rq{ybwire::MAGIC_SCORE, nrows, text_size, start, size, 0};
+        ybwire::ScoreResp rp;
+        bool ok = write_full(R.fd, &rq, sizeof rq);
+        for (int j = 0; ok && j < nrows; ++j) ok = write_full(R.fd, rows[j], (size_t)text_size);
+        ok = ok && read_full(R.fd, &rp, sizeof rp) && rp.magic == ybwire::MAGIC_RESP;
+        if (ok) { R.err.resize(rp.errLen); ok = read_full(R.fd, &R.err[0], rp.errLen); }
+        if (!ok) fatalf("yama_b200: lost the server at %s", R.path.c_str());
+        rc = rp.rc;
+        score = rp.score;
+    } else {
+        ensure_ctx();
+        yb_block blk;
+        blk.nrows = nrows; blk.text_size = text_size; blk.start = start; blk.size = size; blk.rows = rows;
+        rc = yb_score_blocks(G.ctx, 1, &blk, &score, nullptr);
+    }
     G.score_ms += now_ms() - t0;
     ++G.scoreCalls;
-    if (rc != YB_OK) fatalf("%s", yb_last_error(G.ctx));     // (a bad range carries the reference's own message)
+    if (rc != YB_OK) fatalf("%s", backend_error());          // (a bad range carries the reference's own message)
     return score;
 }
 
@@ -519,6 +760,17 @@ int main(int argc, char **argv) {
         fprintf(stderr, "yama_dropin: linked without a reference tool (ref_tool_main)\n");
         return 2;
     }
+    G.t_start = now_ms();
+    // The host allocates and frees an alignment block per yama() call; above glibc's 128 KB mmap threshold each of
+    // them is an mmap/munmap pair, and every munmap of a process that holds a CUDA context runs the driver's
+    // mmu-notifier.  Keep those blocks on the heap.  (YB_MALLOPT=0 leaves malloc alone.)
+    if (const char *e = getenv("YB_MALLOPT"); !e || strcmp(e, "0") != 0) {
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+        mallopt(M_TOP_PAD, 64 << 20);
+    }
+    for (FILE *f : {stdin, stdout, stderr}) __fsetlocking(f, FSETLOCKING_BYCALLER);     // see yb_host_fopen
+    remote_configure();
     G.stats = getenv("YB_DROPIN_STATS") != nullptr;
     G.debug = getenv("YB_DROPIN_DEBUG") != nullptr;
     const char *m = getenv("YB_DROPIN");
@@ -529,8 +781,5 @@ int main(int argc, char **argv) {
     } else {
         rc = run_batched(argc, argv);
     }
-    fflush(nullptr);
-    print_stats();
-    if (G.ctx) { yb_destroy(G.ctx); G.ctx = nullptr; }
-    return rc;
+    finish_process(rc);
 }

@@ -992,7 +992,9 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (!out) return YB_ERR_ARG;
     *out = nullptr;
     int avail = 0;
+    const double tc0 = now_ms();
     if (cudaGetDeviceCount(&avail) != cudaSuccess || avail < 1) return YB_ERR_CUDA;
+    const double tc1 = now_ms();
     yb_ctx *ctx = new yb_ctx();
     std::vector<int> ids;
     if (devices && ndev > 0) ids.assign(devices, devices + ndev);
@@ -1004,6 +1006,8 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     }
     for (auto &d : ctx->devs)
         if (device_init(d) != YB_OK) { fprintf(stderr, "yama_b200: %s\n", d.err.c_str()); yb_destroy(ctx); return YB_ERR_CUDA; }
+    if (getenv("YB_PROFILE"))
+        fprintf(stderr, "yama_b200[profile] start-up: driver %.0f ms, contexts + streams + kernel attributes %.0f ms\n", tc1 - tc0, now_ms() - tc1);
     int hw = (int)std::thread::hardware_concurrency();
     if (hw < 1) hw = 1;
     ctx->nThreads = std::min(hw, 32);

@@ -15,6 +15,33 @@ REF_MULTIZ = os.path.join(ROOT, "oracle", "_ref", "bin", "multiz")
 GPU_MULTIZ = os.path.join(ROOT, "integration", "_ref", "bin", "multiz")
 GPU_MULTIC = os.path.join(ROOT, "integration", "_ref", "bin", "multic")
 SHIM_MULTIZ = os.path.join(ROOT, "integration", "_ref", "bin", "multiz_shim")
+GPU_SERVER = os.path.join(ROOT, "integration", "_ref", "bin", "yama_b200d")
+SHIM_SERVER = os.path.join(ROOT, "integration", "_ref", "bin", "yama_b200d_shim")
+
+
+def server_env(tmp_path, server_bin, idle_s=20):
+    """Environment that sends the drop-in's batches to a resident server on a private socket (started on demand)."""
+    return {"YB_SERVER": str(tmp_path / "yb.sock"), "YB_SERVER_BIN": server_bin, "YB_SERVER_IDLE_S": str(idle_s),
+            "YB_DROPIN_STATS": "1"}
+
+
+def stop_server(env):
+    """Send SIGTERM to the server this test started (found by its unique --socket argument in /proc) instead of
+    letting it idle out."""
+    import signal
+    sock = env["YB_SERVER"].encode()
+    for pid in os.listdir("/proc"):
+        if not pid.isdigit():
+            continue
+        try:
+            argv = open(f"/proc/{pid}/cmdline", "rb").read().split(b"\0")
+        except OSError:
+            continue
+        if len(argv) >= 3 and argv[0].endswith(b"yama_b200d") and sock in argv:
+            try:
+                os.kill(int(pid), signal.SIGTERM)
+            except OSError:
+                pass
 
 
 def run_tool(tool, argv, cwd, env=None, timeout=600):

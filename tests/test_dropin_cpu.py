@@ -7,8 +7,8 @@ import os
 
 import pytest
 
-from dropin_util import (REF_MULTIZ, SHIM_MULTIZ, check_against_live_reference, check_golden_cases, check_speculation,
-                         make_roast_dataset, run_roast)
+from dropin_util import (REF_MULTIZ, SHIM_MULTIZ, SHIM_SERVER, check_against_live_reference, check_golden_cases,
+                         check_speculation, make_roast_dataset, run_roast, server_env, stop_server)
 
 pytestmark = pytest.mark.skipif(not os.path.exists(SHIM_MULTIZ),
                                 reason="integration/_ref/bin/multiz_shim not built (needs /root/reference at build time)")
@@ -23,6 +23,32 @@ def test_golden_maf_cases_with_block_scores_through_the_abi(tmp_path):
     """YB_SCORE=gpu routes the host's mafScoreRange (mz_scores.c:124) through yb_score_blocks in the real pass and
     skips it in the speculative passes; every `a score=` line must still match the reference's."""
     check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_SCORE": "gpu"})
+
+
+def test_golden_maf_cases_through_the_resident_server(tmp_path):
+    """YB_SERVER: the drop-in ships its batches (and, with YB_SCORE=gpu, its block scores) to yama_b200d over a unix
+    socket (integration/yb_wire.h) instead of owning a context; the server is started on demand, serves every
+    invocation of the test, and the output bytes stay the reference's.  Host logic only: the server here is the same
+    program linked against the oracle shim."""
+    assert os.path.exists(SHIM_SERVER)
+    env = server_env(tmp_path, SHIM_SERVER)
+    try:
+        check_golden_cases(SHIM_MULTIZ, tmp_path / "a", env=env)
+        assert os.path.exists(env["YB_SERVER"])                     # one server, still there for the next invocation
+        check_golden_cases(SHIM_MULTIZ, tmp_path / "b", env=dict(env, YB_SCORE="gpu"))
+        check_golden_cases(SHIM_MULTIZ, tmp_path / "c", env=dict(env, YB_DROPIN="direct"))
+    finally:
+        stop_server(env)
+
+
+def test_no_server_and_no_spawn_fails_loudly(tmp_path):
+    import shutil
+    from dropin_util import GOLD_MAF, run_tool
+    for f in ("ref.sp1.maf", "ref.sp2.maf"):
+        shutil.copy(os.path.join(GOLD_MAF, f), tmp_path)
+    env = {"YB_SERVER": str(tmp_path / "nobody.sock"), "YB_SERVER_SPAWN": "0", "YB_SERVER_WAIT_S": "0.2"}
+    rc, out, err = run_tool(SHIM_MULTIZ, ["ref.sp1.maf", "ref.sp2.maf", "1", "o1", "o2"], str(tmp_path), env)
+    assert rc != 0 and b"no server answers on" in err
 
 
 @pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin/multiz not built")

@@ -5,8 +5,8 @@ import os
 
 import pytest
 
-from dropin_util import (GPU_MULTIC, GPU_MULTIZ, REF_MULTIZ, check_against_live_reference, check_golden_cases,
-                         check_speculation, make_roast_dataset, run_roast, run_tool)
+from dropin_util import (GPU_MULTIC, GPU_MULTIZ, GPU_SERVER, REF_MULTIZ, check_against_live_reference, check_golden_cases,
+                         check_speculation, make_roast_dataset, run_roast, run_tool, server_env, stop_server)
 
 pytestmark = [pytest.mark.gpu]
 
@@ -30,6 +30,21 @@ def test_block_scores_on_the_device(tmp_path):
                                        env={"YB_SCORE": "gpu", "YB_DROPIN_STATS": "1"})
     stats = [last[0] for _, _, last in rep if last]
     assert stats and all("score_calls=" in s and "score_calls=0 " not in s for s in stats), stats
+
+
+def test_resident_server_backend(tmp_path):
+    """YB_SERVER: yama_b200d owns the CUDA context; every multiz invocation of the test (golden cases, a progressive
+    4-way merge with v=1 and v=0, block scores on the device) goes through it and stays byte-identical."""
+    _need(GPU_MULTIZ); _need(GPU_SERVER); _need(REF_MULTIZ)
+    env = server_env(tmp_path, GPU_SERVER, idle_s=60)
+    try:
+        check_golden_cases(GPU_MULTIZ, tmp_path / "golden", env=env)
+        rep = check_against_live_reference(GPU_MULTIZ, tmp_path / "fresh", ref_len=150_000, n_species=4, seed=21,
+                                           env=dict(env, YB_SCORE="gpu"))
+        check_speculation(rep)
+        assert all("create_ms=0 " in last[0] for _, _, last in rep if last)      # no CUDA start-up in the tool itself
+    finally:
+        stop_server(env)
 
 
 def test_cfg1_one_megabase_merge(tmp_path):
