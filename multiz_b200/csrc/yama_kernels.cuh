@@ -439,12 +439,14 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                         for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
                             sts128(and_xor((unsigned)cc << 4, wrMask, wrBase), MININT, MININT, MININT, E_both);
                     }
-                    // (b) final scores
-                    if (r == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
-                    // (c) move one wavefront width down
+                    // (b) move one wavefront width down; a lane that runs out of rows idles, and the one that just
+                    //     finished row M leaves the final scores (checked only on that rare path)
                     r += B;
                     if (r <= M) load_row(t4 + u);
-                    else { LB16 = 0x7fffffff; RB16 = 0x7fffffff; rdMax16 = 0x7fffffff; }
+                    else {
+                        if (r - B == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
+                        LB16 = 0x7fffffff; RB16 = 0x7fffffff; rdMax16 = 0x7fffffff;
+                    }
                 }
                 const int Cu = (int)up.x, Du = (int)up.y, Iu = (int)up.z;
                 const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
