@@ -1,4 +1,4 @@
-/* score_dropin.c -- the reference-side binding of block scoring: multiz's own `mafScoreRange` symbol
+/* score_dropin.c -- the reference-side binding of block scoring (and of block output): multiz's own `mafScoreRange` symbol
  * (mz_scores.h:19, defined in mz_scores.c:124-152), re-routed.  The reference's definition is kept, renamed at
  * compile time (mz_scores.c is compiled with -DmafScoreRange=ref_mafScoreRange, integration/Makefile); this file
  * supplies the symbol every caller links to (mz_preyama.c:79, multi_util.c:509,:581,:611,:794,:802) and decides:
@@ -22,6 +22,16 @@ double ref_mafScoreRange(struct mafAli *maf, int start, int size);    /* the ref
 /* yama_dropin.cpp */
 int yb_dropin_score_mode(void);                                       /* 0: host function, 1: skip (speculative pass), 2: GPU */
 double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size);
+
+/* mafWrite (maf.h, maf.c:251-284; maf.c is compiled with -DmafWrite=ref_mafWrite): formatting a block costs an
+ * fprintf per row; a speculative pass's output goes nowhere, so it is not produced.  The real pass writes as ever. */
+void ref_mafWrite(FILE *f, struct mafAli *maf);
+void mafWrite(FILE *f, struct mafAli *maf) {
+    static int keep = -1;
+    if (keep < 0) keep = getenv("YB_SPEC_WRITE") != NULL;        /* measurement knob: format in speculative passes too */
+    if (!keep && yb_dropin_score_mode() == 1) return;
+    ref_mafWrite(f, maf);
+}
 
 double mafScoreRange(struct mafAli *maf, int start, int size) {
     const int mode = yb_dropin_score_mode();
