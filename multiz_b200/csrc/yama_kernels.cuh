@@ -454,7 +454,7 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 
                 // column record of column c; lanes outside their row read a clamped (valid) column and discard the result
                 const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) +
-                                                                       __vimin_s32_relu(c16, N16)));
+                                                                       (unsigned)__vimin_s32_relu(c16, N16)));
 
                 // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
                 int vI, vC, vD;
