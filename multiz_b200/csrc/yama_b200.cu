@@ -862,6 +862,7 @@ void plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cut) {
 // Hands out waves: contiguous job ranges whose input fits one staging slot (sizes known from dimensions).
 // Waves start small (the device idles while the first one is packed), grow to maxBytes, and shrink again
 // towards the end of the batch (the host idles while the last one is on the device).
+constexpr int64_t kWavePairsWanted = 256;
 struct Dispatcher {
     const yb_job *jobs = nullptr;
     int64_t n = 0, cursor = 0;
@@ -881,11 +882,15 @@ struct Dispatcher {
         const int round = handed / ndev;
         size_t target = std::min(maxBytes, minBytes << std::min(round, 16));           // ramp up
         target = std::min(target, std::max(minBytes, remaining / (size_t)(2 * ndev))); // ramp down
+        // Large pairs (wide bands, deep profiles: a megabyte each) run one CTA per pair, and the device wants a few
+        // hundred of them in flight: such a wave is sized by pairs, up to 8x the byte target (cfg5: +50 % end to end).
+        const int64_t wantPairs = std::min<int64_t>(kWavePairsWanted, (int64_t)32 << std::min(round, 3));
+        const size_t hardBytes = 8 * maxBytes;
         size_t bytes = 0;
         int64_t i = lo;
         while (i < n && i - lo < maxPairs) {
             size_t b = bytes_of(jobs[i]);
-            if (i > lo && bytes + b > target) break;
+            if (i > lo && bytes + b > target && (i - lo >= wantPairs || bytes + b > hardBytes)) break;
             bytes += b;
             ++i;
         }
