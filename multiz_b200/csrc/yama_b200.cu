@@ -1145,7 +1145,17 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     if (!ctx->scoresSet) { set_err(ctx, "yb_set_scores has not been called"); return YB_ERR_SCORES; }
     const double t0 = now_ms();
     if (prepare_script_store(ctx, n, jobs) != YB_OK) { set_err(ctx, "cudaHostAlloc failed for the script store"); return YB_ERR_CUDA; }
-    for (auto &d : ctx->devs) { reset_stats(d); d.hasResident = false; }
+    for (auto &d : ctx->devs) {
+        reset_stats(d);
+        if (d.hasResident) {        // a resident batch sized slot 0 for the WHOLE batch: give that memory back before waves
+            Slot &s = d.slots[0];
+            if (cudaSetDevice(d.id) == cudaSuccess) {
+                for (DevBuf *b : {&s.dIn, &s.dRow, &s.dCol, &s.dTb, &s.dScript, &s.dOut}) b->release();
+                s.hIn.release();
+            }
+            d.hasResident = false;
+        }
+    }
     Dispatcher disp;
     disp.jobs = jobs; disp.n = n;
     disp.maxBytes = ctx->waveInBytes; disp.maxPairs = ctx->wavePairs;
