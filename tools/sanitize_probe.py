@@ -17,3 +17,12 @@ res, st = ctx.run_batch(jobs)
 assert int((res["status"] != 0).sum()) == 0
 print("pairs", len(jobs), "cells", st.cells, "launches", st.kernel_launches, "checksum", int(res["m_new"].sum()), int(res["C"].astype(np.int64).sum()))
 ctx.close()
+
+# block scoring (yb_score_kernel): unit seams, ranges starting inside the text, > 255 rows, many small blocks
+from tools.score_cases import score_cases  # noqa: E402
+ctx = YamaB200(devices=[0])
+cases = score_cases()
+blocks, keep2 = ctx.make_blocks(cases)
+scores, st2 = ctx.score_blocks(blocks)
+print("blocks", len(cases), "launches", st2.kernel_launches, "checksum", float(scores.sum()))
+ctx.close()
