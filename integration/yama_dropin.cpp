@@ -23,13 +23,19 @@
 #include "../include/yama_b200.h"
 #include "yb_wire.h"
 
+#include <algorithm>
 #include <cerrno>
+#include <csignal>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <unordered_map>
 #include <vector>
 
@@ -77,7 +83,7 @@ struct KeyHash {
 
 struct Entry {            // one aligned job: its edit script (packed 2 bits per op, see yama_b200.h)
     int32_t m_new = 0;
-    size_t off = 0;       // into G.scripts
+    const uint8_t *script = nullptr;   // into one of G.scriptChunks (a chunk per batch, never reallocated)
 };
 
 struct Pending {          // a job shipped by a child, waiting for the GPU
@@ -90,7 +96,7 @@ struct Globals {
     Mode mode = DIRECT;
     yb_ctx *ctx = nullptr;
     std::unordered_map<Key, Entry, KeyHash> table;
-    std::vector<uint8_t> scripts;
+    std::deque<std::vector<uint8_t>> scriptChunks;
     // child side
     int pipe_w = -1;
     std::vector<uint8_t> wbuf;
@@ -115,6 +121,32 @@ struct Globals {
     bool debug = false;
     std::unordered_map<Key, int, KeyHash> failedKeys;   // debug: batch status of jobs that did not align
 } G;
+
+// ---- streamed replay (YB_DROPIN=stream) ------------------------------------------------------------------------
+// The real pass starts at once in the parent and runs BESIDE the speculative child instead of after it: a reader
+// thread takes the child's jobs off the pipe, aligns them in chunks as they arrive and publishes the scripts; the
+// parent's yama() waits only if its job has not been answered yet.  The child is ahead by construction (its yama()
+// returns placeholders immediately), so the tool takes about one host pass instead of two.  A call the child never
+// shipped is a miss once the LAST speculative pass has passed it (the child's call counter travels with its jobs) and is
+// aligned synchronously -- exact as ever.  v=0 needs two speculative passes (stage 2 consumes stage 1's output): a
+// spare child is forked at the start, before any thread or CUDA state exists; if the first child reports placeholder
+// inputs, the spare receives the stage-1 results over a pipe and runs the second pass, again streamed.
+struct Stream {
+    bool active = false;
+    std::mutex mu;                       // table, pendingKeys, childCalls, readerDone, starved
+    std::condition_variable cv;
+    std::mutex backendMu;                // one backend call at a time (reader's chunks, the real pass's direct calls)
+    std::unordered_set<Key, KeyHash> pendingKeys;   // received from the child, not aligned yet
+    uint64_t childCalls = 0;             // the child's yama() call index as of its last shipped job
+    bool readerDone = false, starved = false;
+    bool lastPass = false;               // the speculative pass now feeding us is the last one: what it skips is a miss
+    std::thread reader;
+    size_t chunkBytes = (size_t)16 << 20;   // a chunk is aligned when it holds this much input ...
+    size_t minStarved = 128;                // ... or this many jobs while the real pass is waiting (a launch costs the
+                                            // same for 1 job and for 100: never feed it job by job)
+    uint64_t waits = 0;
+} S;
+
 
 double now_ms() {
     timeval tv;
@@ -420,6 +452,7 @@ void fail_from_status(int status) {
 void run_direct(const yb_job &job, uchar ***OAL, int *OM) {
     yb_result r;
     yb_stats st;
+    std::lock_guard<std::mutex> backend(S.backendMu);       // (the script stays valid while we hold the backend)
     double t0 = now_ms();
     int rc = backend_batch(1, &job, &r, &st);
     G.gpu_ms += now_ms() - t0;
@@ -445,7 +478,7 @@ void put(const void *p, size_t n) {
     G.wbuf.insert(G.wbuf.end(), s, s + n);
     if (G.wbuf.size() > (1u << 20)) flush_pipe();
 }
-struct WireHdr { uint32_t magic; int32_t K, M, L, N; Key key; };
+struct WireHdr { uint32_t magic; int32_t K, M, L, N; Key key; uint64_t call; };   // call: the child's yama() call index
 struct WireEnd { uint32_t magic; uint32_t pad; uint64_t tainted, shipped, hits; };
 constexpr uint32_t MAGIC_JOB = 0x4a4f4231u, MAGIC_END = 0x454e4431u, MAGIC_SCORES = 0x53434f31u;
 
@@ -456,7 +489,7 @@ void ship(const Key &k, const yb_job &j) {
         put(gop, 16 * sizeof(int));
         put(&gap_extend, sizeof(int));
     }
-    WireHdr h{MAGIC_JOB, j.K, j.M, j.L, j.N, k};
+    WireHdr h{MAGIC_JOB, j.K, j.M, j.L, j.N, k, G.calls};
     put(&h, sizeof h);
     put(j.A, (size_t)j.K * j.M);
     put(j.B, (size_t)j.L * j.N);
@@ -500,6 +533,7 @@ bool read_full(int fd, void *dst, size_t n) {
 }
 
 // returns false if the stream ended without a trailer (child died: fatal() in the host, bad input, ...)
+void align_pending();
 bool drain_child(int fd, WireEnd &end) {
     for (;;) {
         uint32_t magic;
@@ -514,7 +548,7 @@ bool drain_child(int fd, WireEnd &end) {
             if (!g_wireScores.empty() && sc != g_wireScores) {       // tables changed between passes: start over
                 g_scoresStale = true;                       // ensure_ctx() uploads the new tables before the next batch
                 G.table.clear();
-                G.scripts.clear();
+                G.scriptChunks.clear();
             }
             g_wireScores.swap(sc);
             continue;
@@ -534,6 +568,17 @@ bool drain_child(int fd, WireEnd &end) {
             !grab((size_t)(h.M + 1) * 4, p.offLB) || !grab((size_t)(h.M + 1) * 4, p.offRB))
             return false;
         G.pending.push_back(p);
+        if (S.active) {
+            bool go;
+            {
+                std::lock_guard<std::mutex> g(S.mu);
+                S.pendingKeys.insert(p.key);
+                S.childCalls = h.call;
+                go = G.arena.size() >= S.chunkBytes || (S.starved && G.pending.size() >= S.minStarved);
+            }
+            S.cv.notify_all();
+            if (go) align_pending();
+        }
     }
 }
 
@@ -551,6 +596,7 @@ void align_pending() {
     }
     std::vector<yb_result> res(n);
     yb_stats st;
+    std::unique_lock<std::mutex> backend(S.backendMu);
     double t0 = now_ms();
     int rc = backend_batch((int64_t)n, jobs.data(), res.data(), &st, G.arena.data(), G.arena.size());
     G.gpu_ms += now_ms() - t0;
@@ -561,22 +607,39 @@ void align_pending() {
     if (rc == YB_ERR_CUDA || rc == YB_ERR_SCORES || rc == YB_ERR_ARG) fatalf("yama_b200: %s", backend_error());
     // per-pair failures (band / limit / traceback) are not fatal here: the final pass meets the same job
     // as a miss and reports it at the point where the reference would
+    size_t bytes = 0;
+    for (size_t i = 0; i < n; ++i) if (res[i].status == YB_OK) bytes += (size_t)(res[i].m_new + 3) / 4;
+    std::vector<uint8_t> chunk(bytes + 1);
+    std::vector<Entry> entries(n);
+    size_t off = 0;
     for (size_t i = 0; i < n; ++i) {
-        if (res[i].status != YB_OK) {
-            ++G.failed;
-            if (G.debug) {
-                G.failedKeys.emplace(G.pending[i].key, res[i].status);
-                fprintf(stderr, "yama_b200[debug]: batch job %zu failed status=%d K=%d M=%d L=%d N=%d\n", i, res[i].status,
-                        G.pending[i].K, G.pending[i].M, G.pending[i].L, G.pending[i].N);
-            }
-            continue;
-        }
-        Entry e;
-        e.m_new = res[i].m_new;
-        e.off = G.scripts.size();
-        G.scripts.insert(G.scripts.end(), res[i].script, res[i].script + (res[i].m_new + 3) / 4);   // packed, 2 bits per op
-        G.table.emplace(G.pending[i].key, e);
+        if (res[i].status != YB_OK) continue;
+        const size_t len = (size_t)(res[i].m_new + 3) / 4;                 // packed, 2 bits per op
+        memcpy(chunk.data() + off, res[i].script, len);
+        entries[i].m_new = res[i].m_new;
+        entries[i].script = chunk.data() + off;
+        off += len;
     }
+    backend.unlock();
+    {
+        std::lock_guard<std::mutex> g(S.mu);
+        G.scriptChunks.push_back(std::move(chunk));                        // (moving a vector keeps its buffer: pointers stay valid)
+        for (size_t i = 0; i < n; ++i) {
+            if (S.active) S.pendingKeys.erase(G.pending[i].key);
+            if (res[i].status != YB_OK) {
+                ++G.failed;
+                if (G.debug) {
+                    G.failedKeys.emplace(G.pending[i].key, res[i].status);
+                    fprintf(stderr, "yama_b200[debug]: batch job %zu failed status=%d K=%d M=%d L=%d N=%d\n", i, res[i].status,
+                            G.pending[i].K, G.pending[i].M, G.pending[i].L, G.pending[i].N);
+                }
+                continue;
+            }
+            G.table.emplace(G.pending[i].key, entries[i]);
+        }
+        S.starved = false;
+    }
+    S.cv.notify_all();
     G.pending.clear();
     G.arena.clear();
 }
@@ -619,11 +682,136 @@ int run_batched(int argc, char **argv) {
     return rc;
 }
 
+// YB_DROPIN=stream: speculative children, the real pass beside them (see Stream above)
+constexpr uint32_t MAGIC_TABLE = 0x54424c31u;
+
+[[noreturn]] void run_record_child(int argc, char **argv, int pipe_w) {
+    G.mode = RECORD;
+    G.pipe_w = pipe_w;
+    int nul = open("/dev/null", O_WRONLY);
+    if (nul >= 0) { dup2(nul, 1); dup2(nul, 2); close(nul); }
+    ref_tool_main(argc, argv);
+    yb_host_exit(0);
+}
+
+// the spare: sleeps until the parent sends the stage-1 results (then it is the second speculative pass) or hangs up
+[[noreturn]] void run_spare_child(int argc, char **argv, int ctl_r, int pipe_w) {
+    uint32_t magic = 0;
+    uint64_t n = 0;
+    if (!read_full(ctl_r, &magic, 4) || magic != MAGIC_TABLE || !read_full(ctl_r, &n, 8)) _exit(0);
+    std::vector<int32_t> sc(128 * 128 + 17);
+    if (!read_full(ctl_r, sc.data(), sc.size() * 4)) _exit(0);
+    g_wireScores.swap(sc);
+    uint64_t bytes = 0;
+    if (!read_full(ctl_r, &bytes, 8)) _exit(0);
+    G.scriptChunks.emplace_back((size_t)bytes + 1);
+    uint8_t *base = G.scriptChunks.back().data();
+    size_t off = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        Key k;
+        int32_t m_new;
+        if (!read_full(ctl_r, &k, sizeof k) || !read_full(ctl_r, &m_new, 4)) _exit(0);
+        const size_t len = (size_t)(m_new + 3) / 4;
+        if (off + len > bytes || !read_full(ctl_r, base + off, len)) _exit(0);
+        Entry e;
+        e.m_new = m_new;
+        e.script = base + off;
+        off += len;
+        G.table.emplace(k, e);
+    }
+    close(ctl_r);
+    run_record_child(argc, argv, pipe_w);
+}
+
+bool send_table(int fd) {
+    std::lock_guard<std::mutex> g(S.mu);
+    uint64_t n = G.table.size(), bytes = 0;
+    for (auto &kv : G.table) bytes += (uint64_t)(kv.second.m_new + 3) / 4;
+    if (g_wireScores.size() != 128 * 128 + 17) return false;
+    bool ok = write_full(fd, &MAGIC_TABLE, 4) && write_full(fd, &n, 8) && write_full(fd, g_wireScores.data(), g_wireScores.size() * 4) &&
+              write_full(fd, &bytes, 8);
+    for (auto it = G.table.begin(); ok && it != G.table.end(); ++it)
+        ok = write_full(fd, &it->first, sizeof(Key)) && write_full(fd, &it->second.m_new, 4) &&
+             write_full(fd, it->second.script, (size_t)(it->second.m_new + 3) / 4);
+    return ok;
+}
+
+int run_streamed(int argc, char **argv) {
+    int p1[2], p2[2], ctl[2];
+    if (pipe(p1) != 0) return run_batched(argc, argv);
+    if (pipe(p2) != 0 || pipe(ctl) != 0) { close(p1[0]); close(p1[1]); return run_batched(argc, argv); }
+    const double tc = now_ms();
+    fflush(nullptr);
+    pid_t spare = fork();                          // before any thread or CUDA state exists in this process
+    if (spare == 0) {
+        close(p1[0]); close(p1[1]); close(p2[0]); close(ctl[1]);
+        run_spare_child(argc, argv, ctl[0], p2[1]);
+    }
+    pid_t first = spare < 0 ? -1 : fork();
+    if (first == 0) {
+        close(p1[0]); close(p2[0]); close(p2[1]); close(ctl[0]); close(ctl[1]);
+        run_record_child(argc, argv, p1[1]);
+    }
+    close(p1[1]); close(p2[1]); close(ctl[0]);
+    if (spare < 0 || first < 0) {                  // could not fork: the classic way
+        close(p1[0]); close(p2[0]); close(ctl[1]);
+        int st;
+        if (spare > 0) while (waitpid(spare, &st, 0) < 0 && errno == EINTR) {}
+        return run_batched(argc, argv);
+    }
+    signal(SIGPIPE, SIG_IGN);
+    if (R.enabled) remote_begin(); else warm_ctx();
+    S.active = true;
+    if (const char *e = getenv("YB_STREAM_CHUNK_MB")) S.chunkBytes = (size_t)std::max(1, atoi(e)) << 20;
+    if (const char *e = getenv("YB_STREAM_MIN_JOBS")) S.minStarved = (size_t)std::max(1, atoi(e));
+    S.reader = std::thread([=] {
+        int status = 0;
+        WireEnd end{};
+        const bool clean = drain_child(p1[0], end);
+        close(p1[0]);
+        align_pending();                                   // what is left of pass 1
+        while (waitpid(first, &status, 0) < 0 && errno == EINTR) {}
+        ++G.passes;
+        bool second = clean && end.tainted > 0;
+        if (second) {
+            { std::lock_guard<std::mutex> g(S.mu); S.childCalls = 0; }
+            second = send_table(ctl[1]);
+        }
+        close(ctl[1]);                                     // (without a table the spare just leaves)
+        {
+            std::lock_guard<std::mutex> g(S.mu);
+            S.lastPass = true;
+        }
+        S.cv.notify_all();
+        if (second) {
+            WireEnd end2{};
+            drain_child(p2[0], end2);
+            align_pending();
+            ++G.passes;
+        }
+        close(p2[0]);
+        while (waitpid(spare, &status, 0) < 0 && errno == EINTR) {}
+        G.child_ms = now_ms() - tc;
+        {
+            std::lock_guard<std::mutex> g(S.mu);
+            S.readerDone = true;
+        }
+        S.cv.notify_all();
+    });
+    G.mode = REPLAY;
+    const double tf = now_ms();
+    const int rc = ref_tool_main(argc, argv);
+    G.final_ms = now_ms() - tf;
+    if (S.reader.joinable()) S.reader.join();
+    return rc;
+}
+
 void print_stats();
 // End of the process: everything the tool wrote is flushed, then _exit -- tearing the CUDA context down buffer by
 // buffer (yb_destroy + the runtime's atexit handlers) costs a few hundred milliseconds that no caller needs; the
 // driver reclaims the context with the process.  The reference registers no atexit handlers of its own.
 [[noreturn]] void finish_process(int code) {
+    if (S.reader.joinable()) S.reader.join();      // (the host called exit() inside the streamed real pass)
     if (g_warm.joinable()) g_warm.join();
     fflush(nullptr);
     print_stats();
@@ -635,10 +823,10 @@ void print_stats() {
     if (!G.stats) return;
     fprintf(stderr,
             "yama_b200: passes=%d batches=%lld jobs=%lld failed=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
-            "gpu_ms=%.2f kernel_ms=%.2f create_ms=%.0f speculative_ms=%.0f final_ms=%.0f wall_ms=%.0f score_calls=%llu score_ms=%.1f devices=%d\n",
+            "gpu_ms=%.2f kernel_ms=%.2f create_ms=%.0f speculative_ms=%.0f final_ms=%.0f wall_ms=%.0f score_calls=%llu score_ms=%.1f stream_waits=%llu devices=%d\n",
             G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.failed, (long long)G.cells, (unsigned long long)G.calls,
             (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.create_ms, G.child_ms, G.final_ms,
-            now_ms() - G.t_start, (unsigned long long)G.scoreCalls, G.score_ms, R.enabled ? R.devices : (G.ctx ? yb_device_count(G.ctx) : 0));
+            now_ms() - G.t_start, (unsigned long long)G.scoreCalls, G.score_ms, (unsigned long long)S.waits, R.enabled ? R.devices : (G.ctx ? yb_device_count(G.ctx) : 0));
 }
 
 }  // namespace
@@ -680,6 +868,7 @@ int yb_dropin_score_mode(void) {
 
 double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size) {
     double score = 0.0;
+    std::lock_guard<std::mutex> backend(S.backendMu);
     const double t0 = now_ms();
     int rc;
     if (R.enabled) {
@@ -731,11 +920,27 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
     if (G.mode == DIRECT) { run_direct(job, OAL, OM); return; }
 
     const Key key = key_of(K, M, L, N, job.A, job.B, LB, RB);
-    auto it = G.table.find(key);
-    if (it != G.table.end()) {
-        ++G.nHits;
-        emit(job, it->second.m_new, G.scripts.data() + it->second.off, OAL, OM);
-        return;
+    {
+        std::unique_lock<std::mutex> lk(S.mu, std::defer_lock);
+        if (S.active) lk.lock();                // (only the streamed real pass shares the table with another thread)
+        for (;;) {
+            auto it = G.table.find(key);
+            if (it != G.table.end()) {
+                const Entry e = it->second;
+                if (lk.owns_lock()) lk.unlock();
+                ++G.nHits;
+                emit(job, e.m_new, e.script, OAL, OM);
+                return;
+            }
+            // streamed: not answered yet?  Wait while the child may still ship it: it has not reached this call, or
+            // the job sits in the reader's queue.  Once the child's call counter has passed ours without shipping it
+            // (v=0 stage 2), or the child is gone, it is a miss.
+            if (!S.active || G.mode != REPLAY || S.readerDone) break;
+            if (S.lastPass && S.childCalls > G.calls && !S.pendingKeys.count(key)) break;
+            S.starved = true;
+            ++S.waits;
+            S.cv.wait(lk);
+        }
     }
     if (G.mode == RECORD) {
         if (G.shipped.emplace(key, 1).second) { ship(key, job); ++G.nShipped; }
@@ -778,6 +983,8 @@ int main(int argc, char **argv) {
     if (m && strcmp(m, "direct") == 0) {
         G.mode = DIRECT;
         rc = ref_tool_main(argc, argv);
+    } else if (m && strcmp(m, "stream") == 0) {
+        rc = run_streamed(argc, argv);
     } else {
         rc = run_batched(argc, argv);
     }

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(SHIM_MULTIZ),
                                 reason="integration/_ref/bin/multiz_shim not built (needs /root/reference at build time)")
 
 
-@pytest.mark.parametrize("mode", ["batch", "direct"])
+@pytest.mark.parametrize("mode", ["batch", "direct", "stream"])
 def test_golden_maf_cases(tmp_path, mode):
     check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_DROPIN": mode})
 
