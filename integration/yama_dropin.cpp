@@ -142,7 +142,7 @@ struct Stream {
     bool lastPass = false;               // the speculative pass now feeding us is the last one: what it skips is a miss
     std::thread reader;
     size_t chunkBytes = (size_t)16 << 20;   // a chunk is aligned when it holds this much input ...
-    size_t minStarved = 128;                // ... or this many jobs while the real pass is waiting (a launch costs the
+    size_t minStarved = 256;                // ... or this many jobs while the real pass is waiting (a launch costs the
                                             // same for 1 job and for 100: never feed it job by job)
     uint64_t waits = 0;
 } S;

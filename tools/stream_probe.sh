@@ -5,7 +5,7 @@ cd /root/repo
 python - <<'PY'
 import sys; sys.path.insert(0,'/root/repo')
 from tools.mafsynth import make_dataset
-make_dataset('/tmp/ds', ref_len=10000000, n_species=2, seed=3, lower=0.01)
+make_dataset('/tmp/ds', ref_len=int(__import__("os").environ.get("REF_LEN", "10000000")), n_species=2, seed=3, lower=0.01)
 PY
 cd /tmp/ds
 export YB_DROPIN_STATS=1
