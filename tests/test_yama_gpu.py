@@ -207,3 +207,48 @@ def test_full_size_batch_sampled_and_wave_invariant(oracle):
         for i in sample:
             assert ctx2.script_of(res2[int(i)]).tobytes() == scripts[int(i)]
     ctx2.close()
+
+
+def test_two_devices_in_one_context_match_one_device(oracle):
+    """inside one process the waves of a batch go to whichever device is free; results must not depend on
+    it.  Needs two visible GPUs (skipped on a one-GPU box): batch, resident path and block scores with devices [0, 1]
+    against devices [0]."""
+    from multiz_b200 import YamaB200
+    try:
+        import torch
+        ndev = torch.cuda.device_count()
+    except Exception:
+        ndev = 1
+    if ndev < 2:
+        pytest.skip("one visible GPU")
+    Ms = list(np.random.default_rng(9).integers(5, 900, 600))
+    sb = SynthBatch(77, [2, 3, 4, 5, 2, 8] * 100, [1, 1, 1, 1, 2, 8] * 100, Ms, R=30)
+    one = YamaB200(devices=[0])
+    two = YamaB200(devices=[0, 1])
+    try:
+        assert two.n_devices == 2
+        import os
+        os.environ["YB_WAVE_MB"] = "1"                      # many waves, so both devices get some
+        try:
+            two_small = YamaB200(devices=[0, 1])
+        finally:
+            del os.environ["YB_WAVE_MB"]
+        ra, _ = one.run_batch(sb.jobs)
+        for ctx in (two, two_small):
+            rb, st = ctx.run_batch(sb.jobs)
+            assert st.n_devices == 2 and st.cells == sb.cells
+            for i in range(sb.n):
+                assert tuple(ra[i][f] for f in ("status", "m_new", "C", "D", "I", "cells")) == \
+                       tuple(rb[i][f] for f in ("status", "m_new", "C", "D", "I", "cells")), i
+                assert np.array_equal(one.script_of(ra[i]), ctx.script_of(rb[i])), i
+        two.resident_load(sb.jobs)
+        two.resident_step()
+        rr = two.resident_fetch()
+        for i in range(0, sb.n, 7):
+            assert np.array_equal(one.script_of(ra[i]), two.script_of(rr[i])), i
+        A, B, LB, RB = sb.problem(11)
+        assert np.array_equal(one.script_of(ra[11]), oracle.yama(A, B, LB, RB, want_tback=False)["script"])
+        two_small.close()
+    finally:
+        one.close()
+        two.close()
