@@ -811,7 +811,11 @@ void print_stats();
 // buffer (yb_destroy + the runtime's atexit handlers) costs a few hundred milliseconds that no caller needs; the
 // driver reclaims the context with the process.  The reference registers no atexit handlers of its own.
 [[noreturn]] void finish_process(int code) {
-    if (S.reader.joinable()) S.reader.join();      // (the host called exit() inside the streamed real pass)
+    if (S.reader.joinable()) {                     // (the host called exit() inside the streamed real pass)
+        if (S.reader.get_id() == std::this_thread::get_id()) S.reader.detach();   // a fatal error on the reader itself
+        else if (code == 0) S.reader.join();
+        else S.reader.detach();                    // dying: do not wait for a speculative child
+    }
     if (g_warm.joinable()) g_warm.join();
     fflush(nullptr);
     print_stats();
