@@ -172,6 +172,8 @@ struct Slot {
     uint8_t *scriptDst = nullptr;          // where this wave's packed scripts go in the context's pinned store
     bool filled = false;                   // H2D + K1 + K2 queued, K3 not yet
     bool busy = false;                     // K3 + D2H queued, results not yet unpacked
+    size_t sentLo = 0, sentHi = 0;         // bytes [sentLo, sentHi) of the blob were queued for H2D while the rest was packed
+    double tPack0 = 0, tPack1 = 0, tTbLaunch = 0;   // host times (ms) of the wave: pack start/end, traceback launch
     // the wave it holds
     int64_t first = 0, count = 0;
     std::vector<JobInfo> info;
@@ -203,6 +205,9 @@ struct Device {
     int sms = 0;
     Slot slots[NSLOTS];
     ScoreStage score[2];
+    cudaEvent_t evBase = nullptr;          // YB_PROFILE=2: start of the batch on this device (timeline origin)
+    double tBase = 0;
+    int timeline = 0;
     ScoreConst sc{};                       // the owning context's score tables (kernel arguments)
     int fillBlocks[NBINS] = {};
     int helpers = 1;
@@ -227,12 +232,14 @@ struct yb_ctx {
     int maxDepth = 255;
     int nThreads = 1;
     size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave (steady state)
-    size_t waveMinBytes = (size_t)16 << 20; // first / last waves of a batch (the device idles while the first wave is packed)
+    size_t waveMinBytes = (size_t)16 << 20; // first waves of a batch (the device idles while the first wave is packed)
+    size_t waveTailBytes = (size_t)16 << 20; // last waves of a batch (a short last wave shortens the traceback + unpack tail)
     size_t batchBlobBytes = 0;              // input bytes of the current batch (dimension-only estimate)
     size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
     int64_t wavePairs = 1 << 20;
     int tbLong = TB_LONG;                   // paths of at least this many moves: warp-per-path traceback (YB_TB_LONG)
     bool ntStores = true;                   // full-line non-temporal staging stores (YB_NT=0 turns them off)
+    bool earlyH2D = true;                   // a wave's parts are copied while the rest is packed (YB_EARLY_H2D=0 turns it off)
     // results of the last batch
     uint8_t *scriptStore = nullptr;         // pinned (portable): the D2H copies of the waves land here directly
     size_t scriptStoreCap = 0;
@@ -500,8 +507,10 @@ inline size_t blob_bytes(const yb_job &j) {
 // are prefix sums taken up front and each helper validates the band (mz_yama.c:58-71), writes the schedule
 // and copies A, B and the band while they are hot in its cache.  Traceback offsets are assigned afterwards.
 // `maxTb` caps the wave's traceback bytes: the wave is cut short (count shrinks, at least one job stays).
-int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t &count, size_t maxTb) {
+int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t &count, size_t maxTb,
+              bool earlyH2D = false) {
     const double t0 = now_ms();
+    s.tPack0 = t0;
     // ---- dimension-only layout (serial, a few ns per job) ------------------------------------------------------
     struct Off { size_t blob, row, col; uint32_t script; };
     s.off.resize((size_t)count);
@@ -532,71 +541,102 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     d.t_layout += t1 - t0;
     // ---- analyse + pack (parallel) -----------------------------------------------------------------------------
     std::mutex errMu;
-    d.pool->run(count, 32, [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            const yb_job &j = jobs[first + i];
-            JobInfo &ji = s.info[(size_t)i];
-            const Slot::Off &of = s.off[(size_t)i];
-            PairMeta pm;
-            memset(&pm, 0, sizeof pm);
-            s.scriptOff[(size_t)i] = of.script;
-            char msg[256];
-            msg[0] = 0;
-            // the schedule goes straight to its place in the blob (after A, B and the band)
-            size_t o = dataOff + of.blob;
-            const bool dimsOk = dims_ok(j);
-            size_t oA = o, oB = 0, oBand = 0, oSched = 0;
-            if (dimsOk) {
-                oB = oA + align_up((size_t)j.K * j.M, 64);
-                oBand = oB + align_up((size_t)j.L * j.N, 64);
-                oSched = oBand + align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 64);
-            }
-            analyse_one(ctx, j, ji, dimsOk ? reinterpret_cast<int *>(h + oSched) : nullptr, msg, sizeof msg);
-            if (ji.status != YB_OK) {
-                metas[i] = pm;
-                std::lock_guard<std::mutex> g(errMu);
-                if (d.err.empty() || first + i < d.errJob) {
-                    char b[400];
-                    if (ji.status == YB_ERR_BAND) snprintf(b, sizeof b, "%s", msg);   // reference wording
-                    else snprintf(b, sizeof b, "job %lld: %s", (long long)(first + i), msg);
-                    d.err = b;
-                    d.errJob = first + i;
-                }
-                continue;
-            }
-            pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
-            pm.offA = oA; pm.offB = oB;
-            if (ctx->ntStores) {
-                copy_nt64(h + oA, j.A, (size_t)j.K * j.M);
-                copy_nt64(h + oB, j.B, (size_t)j.L * j.N);
-            } else {
-                memcpy(h + oA, j.A, (size_t)j.K * j.M);
-                memcpy(h + oB, j.B, (size_t)j.L * j.N);
-            }
-            pm.offBand = oBand;
-            pm.bandFmt = band_fmt(j);
-            if (pm.bandFmt == 0) {
-                if (ctx->ntStores) pack_band_nt64(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
-                else pack_band(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
-            } else {
-                memcpy(h + oBand, j.LB, (size_t)(j.M + 1) * 4);
-                memcpy(h + oBand + (size_t)(j.M + 1) * 4, j.RB, (size_t)(j.M + 1) * 4);
-            }
-            pm.offSched = oSched;
-            pm.nSteps = ji.nSteps;
-            pm.lgLanes = lg_of(32 * kBin[ji.bin].G);
-            pm.rowBase = of.row;
-            pm.colBase = of.col;
-            pm.scriptBase = of.script;
-            metas[i] = pm;
-            if (ctx->ntStores) _mm_sfence();
-            {
-                const int lg = 63 - __builtin_clzll((unsigned long long)std::max<int64_t>(ji.cells, 1));
-                const int frac = lg >= 2 ? (int)((ji.cells >> (lg - 2)) & 3) : 0;
-                ji.bucket = ji.bin * NB + (NB - 1 - std::min(NB - 1, lg * 4 + frac));
-            }
+    // The wave is packed in a few contiguous parts; a part's bytes start their way to the device while the next part
+    // is packed (the header -- metas, launch order, traceback offsets -- and the last part follow in slot_launch_fill).
+    // Without this a wave's copy starts only when all of it is packed: 1.3 ms per 64 MB that the device idles at the
+    // start of a batch.
+    s.sentLo = s.sentHi = 0;
+    const int nParts = (earlyH2D && blob >= ((size_t)4 << 20) && count >= 64) ? 4 : 1;
+    if (nParts > 1) {
+        CUDA_TRY(d, s.dIn.reserve(dataOff + blob));
+        CUDA_TRY(d, cudaEventRecord(s.ev[0], s.stream));
+    }
+    int64_t partLo = 0;
+    for (int part = 0; part < nParts; ++part) {
+        int64_t partHi = count;
+        if (part + 1 < nParts) {                                    // cut by bytes
+            const size_t want = blob / (size_t)nParts * (size_t)(part + 1);
+            partHi = std::lower_bound(s.off.begin() + partLo, s.off.end(), want,
+                                      [](const Slot::Off &o, size_t v) { return o.blob < v; }) - s.off.begin();
+            partHi = std::max(partLo, std::min<int64_t>(partHi, count));
         }
-    });
+        const int64_t base = partLo;
+        // dynamic chunks: 32 pairs when pairs are small, fewer when a part holds only a few (large) pairs
+        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(32, (partHi - partLo) / (4 * (int64_t)d.helpers)));
+        d.pool->run(partHi - partLo, chunk, [&](int64_t lo0, int64_t hi0) {
+            for (int64_t i = base + lo0; i < base + hi0; ++i) {
+                const yb_job &j = jobs[first + i];
+                JobInfo &ji = s.info[(size_t)i];
+                const Slot::Off &of = s.off[(size_t)i];
+                PairMeta pm;
+                memset(&pm, 0, sizeof pm);
+                s.scriptOff[(size_t)i] = of.script;
+                char msg[256];
+                msg[0] = 0;
+                // the schedule goes straight to its place in the blob (after A, B and the band)
+                size_t o = dataOff + of.blob;
+                const bool dimsOk = dims_ok(j);
+                size_t oA = o, oB = 0, oBand = 0, oSched = 0;
+                if (dimsOk) {
+                    oB = oA + align_up((size_t)j.K * j.M, 64);
+                    oBand = oB + align_up((size_t)j.L * j.N, 64);
+                    oSched = oBand + align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 64);
+                }
+                analyse_one(ctx, j, ji, dimsOk ? reinterpret_cast<int *>(h + oSched) : nullptr, msg, sizeof msg);
+                if (ji.status != YB_OK) {
+                    metas[i] = pm;
+                    std::lock_guard<std::mutex> g(errMu);
+                    if (d.err.empty() || first + i < d.errJob) {
+                        char b[400];
+                        if (ji.status == YB_ERR_BAND) snprintf(b, sizeof b, "%s", msg);   // reference wording
+                        else snprintf(b, sizeof b, "job %lld: %s", (long long)(first + i), msg);
+                        d.err = b;
+                        d.errJob = first + i;
+                    }
+                    continue;
+                }
+                pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
+                pm.offA = oA; pm.offB = oB;
+                if (ctx->ntStores) {
+                    copy_nt64(h + oA, j.A, (size_t)j.K * j.M);
+                    copy_nt64(h + oB, j.B, (size_t)j.L * j.N);
+                } else {
+                    memcpy(h + oA, j.A, (size_t)j.K * j.M);
+                    memcpy(h + oB, j.B, (size_t)j.L * j.N);
+                }
+                pm.offBand = oBand;
+                pm.bandFmt = band_fmt(j);
+                if (pm.bandFmt == 0) {
+                    if (ctx->ntStores) pack_band_nt64(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
+                    else pack_band(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
+                } else {
+                    memcpy(h + oBand, j.LB, (size_t)(j.M + 1) * 4);
+                    memcpy(h + oBand + (size_t)(j.M + 1) * 4, j.RB, (size_t)(j.M + 1) * 4);
+                }
+                pm.offSched = oSched;
+                pm.nSteps = ji.nSteps;
+                pm.lgLanes = lg_of(32 * kBin[ji.bin].G);
+                pm.rowBase = of.row;
+                pm.colBase = of.col;
+                pm.scriptBase = of.script;
+                metas[i] = pm;
+                if (ctx->ntStores) _mm_sfence();
+                {
+                    const int lg = 63 - __builtin_clzll((unsigned long long)std::max<int64_t>(ji.cells, 1));
+                    const int frac = lg >= 2 ? (int)((ji.cells >> (lg - 2)) & 3) : 0;
+                    ji.bucket = ji.bin * NB + (NB - 1 - std::min(NB - 1, lg * 4 + frac));
+                }
+            }
+        });
+        if (part + 1 < nParts && partHi > partLo) {
+            const size_t a = dataOff + s.off[(size_t)partLo].blob;
+            const size_t z = partHi < count ? dataOff + s.off[(size_t)partHi].blob : dataOff + blob;
+            CUDA_TRY(d, cudaMemcpyAsync(static_cast<unsigned char *>(s.dIn.p) + a, h + a, z - a, cudaMemcpyHostToDevice, s.stream));
+            if (s.sentHi == 0) s.sentLo = a;
+            s.sentHi = z;
+        }
+        partLo = partHi;
+    }
 
     // ---- traceback offsets, wave cut, launch order (serial, O(count)) -----------------------------------------------
     // launch order: per ring bin, big pairs first (longest-processing-time-first on the warp queue); quarter-octave
@@ -656,6 +696,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     CUDA_TRY(d, s.hOut.reserve((size_t)count * sizeof(PairOut) + 64));
     d.t_reserve += now_ms() - t3;
     d.pack_ms += now_ms() - t0;
+    s.tPack1 = now_ms();
     return YB_OK;
 }
 
@@ -673,8 +714,16 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     cudaStream_t st = s.stream;
     const double tl = now_ms();
 
-    CUDA_TRY(d, cudaEventRecord(s.ev[0], st));
-    if (h2d) CUDA_TRY(d, cudaMemcpyAsync(s.dIn.p, s.hIn.p, s.blobBytes, cudaMemcpyHostToDevice, st));
+    if (h2d && s.sentHi > s.sentLo) {            // part of the blob is already on its way (slot_pack): header + the rest
+        unsigned char *dst = static_cast<unsigned char *>(s.dIn.p);
+        const unsigned char *src = static_cast<const unsigned char *>(s.hIn.p);
+        CUDA_TRY(d, cudaMemcpyAsync(dst, src, std::min(s.sentLo, s.blobBytes), cudaMemcpyHostToDevice, st));
+        if (s.blobBytes > s.sentHi)
+            CUDA_TRY(d, cudaMemcpyAsync(dst + s.sentHi, src + s.sentHi, s.blobBytes - s.sentHi, cudaMemcpyHostToDevice, st));
+    } else {
+        CUDA_TRY(d, cudaEventRecord(s.ev[0], st));
+        if (h2d) CUDA_TRY(d, cudaMemcpyAsync(s.dIn.p, s.hIn.p, s.blobBytes, cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(d, cudaEventRecord(s.ev[1], st));
     CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)s.count * sizeof(PairOut), st));
     CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, st));
@@ -723,6 +772,7 @@ int slot_launch_traceback(Device &d, Slot &s, bool d2h) {
     const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
     cudaStream_t st = s.stream;
     const double tl = now_ms();
+    s.tTbLaunch = tl;
     CUDA_TRY(d, cudaEventRecord(s.ev[6], st));
     // the warp-per-path kernel (issue-bound) runs beside the thread-per-pair kernel (latency-bound), on a side stream
     if (s.nLong > 0) {
@@ -778,6 +828,14 @@ int slot_wait(Device &d, Slot &s) {
     cudaEventElapsedTime(&e, s.ev[4], s.ev[5]);
     d.h2d_ms += h; d.profile_ms += a; d.fill_ms += b; d.tb_ms += c; d.d2h_ms += e;
     d.kernel_ms += a + b + c;
+    if (d.timeline && d.evBase) {           // YB_PROFILE=2: where this wave sat on the device's and the host's clocks
+        float t[7] = {0};
+        const int idx[7] = {0, 1, 2, 3, 6, 4, 5};
+        for (int k = 0; k < 7; ++k) cudaEventElapsedTime(&t[k], d.evBase, s.ev[idx[k]]);
+        fprintf(stderr, "yama_b200[timeline] dev %d wave %3d pairs %6lld | host: pack %.2f-%.2f tb-launch %.2f wait-done %.2f | device: h2d %.2f-%.2f "
+                "K1 -%.2f K2 -%.2f | K3 %.2f-%.2f d2h -%.2f\n", d.id, d.waves, (long long)s.count, s.tPack0 - d.tBase, s.tPack1 - d.tBase,
+                s.tTbLaunch - d.tBase, now_ms() - d.tBase, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+    }
     s.busy = false;
     return YB_OK;
 }
@@ -866,7 +924,7 @@ constexpr int64_t kWavePairsWanted = 256;
 struct Dispatcher {
     const yb_job *jobs = nullptr;
     int64_t n = 0, cursor = 0;
-    size_t maxBytes = 0, minBytes = 0, remaining = 0;
+    size_t maxBytes = 0, minBytes = 0, tailBytes = 0, remaining = 0;
     int64_t maxPairs = 0;
     int ndev = 1, handed = 0;
     std::mutex mu;
@@ -881,7 +939,7 @@ struct Dispatcher {
         lo = cursor;
         const int round = handed / ndev;
         size_t target = std::min(maxBytes, minBytes << std::min(round, 16));           // ramp up
-        target = std::min(target, std::max(minBytes, remaining / (size_t)(2 * ndev))); // ramp down
+        target = std::min(target, std::max(tailBytes, remaining / (size_t)(2 * ndev))); // ramp down
         // Large pairs (wide bands, deep profiles: a megabyte each) run one CTA per pair, and the device wants a few
         // hundred of them in flight: such a wave is sized by pairs, up to 8x the byte target (cfg5: +50 % end to end).
         const int64_t wantPairs = std::min<int64_t>(kWavePairsWanted, (int64_t)32 << std::min(round, 3));
@@ -908,6 +966,12 @@ int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
     if (cudaSetDevice(d.id) != cudaSuccess) { d.err = "cudaSetDevice failed"; return YB_ERR_CUDA; }
     int rc = YB_OK, next = 0, nFilled = 0;
     int filledSlots[NSLOTS];
+    if (const char *e = getenv("YB_PROFILE")) d.timeline = atoi(e) >= 2;
+    if (d.timeline) {
+        if (!d.evBase) cudaEventCreate(&d.evBase);
+        d.tBase = now_ms();
+        cudaEventRecord(d.evBase, d.slots[0].stream);
+    }
     int64_t lo = 0, hi = 0;                      // jobs grabbed but not yet packed
     auto flush_group = [&]() -> int {
         for (int k = 0; k < nFilled; ++k) {
@@ -926,7 +990,7 @@ int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
             slot_unpack(ctx, d, s, results);
         }
         int64_t count = hi - lo;
-        if ((rc = slot_pack(ctx, d, s, disp.jobs, lo, count, ctx->waveTbBytes)) != YB_OK) break;
+        if ((rc = slot_pack(ctx, d, s, disp.jobs, lo, count, ctx->waveTbBytes, ctx->earlyH2D)) != YB_OK) break;
         lo += count;
         if ((rc = slot_launch_fill(d, s, true)) != YB_OK) break;
         filledSlots[nFilled++] = next;
@@ -1019,6 +1083,7 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_THREADS")) ctx->nThreads = std::max(1, atoi(e));
     if (const char *e = getenv("YB_WAVE_MB")) ctx->waveInBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_MIN_MB")) ctx->waveMinBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
+    if (const char *e = getenv("YB_WAVE_TAIL_MB")) ctx->waveTailBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     {   // traceback bytes per wave: an eighth of the smallest device's free memory (NSLOTS waves can be in flight)
         size_t cap = (size_t)24 << 30;
         for (auto &d : ctx->devs) {
@@ -1029,6 +1094,7 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     }
     if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_NT")) ctx->ntStores = atoi(e) != 0;
+    if (const char *e = getenv("YB_EARLY_H2D")) ctx->earlyH2D = atoi(e) != 0;
     if (const char *e = getenv("YB_TB_LONG")) ctx->tbLong = std::max(1, atoi(e));
     if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
     for (auto &d : ctx->devs) {
@@ -1160,6 +1226,7 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     disp.jobs = jobs; disp.n = n;
     disp.maxBytes = ctx->waveInBytes; disp.maxPairs = ctx->wavePairs;
     disp.minBytes = std::min(ctx->waveInBytes, ctx->waveMinBytes);
+    disp.tailBytes = std::min(ctx->waveInBytes, ctx->waveTailBytes);
     disp.ndev = (int)ctx->devs.size();
     disp.remaining = ctx->batchBlobBytes;
     int rc = for_each_device(ctx, [&](int d) { return device_run(ctx, ctx->devs[(size_t)d], disp, results); });
