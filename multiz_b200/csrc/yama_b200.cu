@@ -214,7 +214,7 @@ struct Device {
     std::unique_ptr<Pool> pool;
     // accumulated stats of the current call
     double kernel_ms = 0, fill_ms = 0, profile_ms = 0, tb_ms = 0, h2d_ms = 0, d2h_ms = 0, pack_ms = 0, unpack_ms = 0;
-    int64_t h2d_bytes = 0, d2h_bytes = 0, cells = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0, cells = 0, failed = 0;
     int launches = 0, waves = 0;
     std::string err;
     int64_t errJob = 0;
@@ -244,6 +244,7 @@ struct yb_ctx {
     uint8_t *scriptStore = nullptr;         // pinned (portable): the D2H copies of the waves land here directly
     size_t scriptStoreCap = 0;
     std::vector<uint64_t> scriptOff;
+    std::vector<uint64_t> blobPrefix;       // input bytes of jobs [0, i): waves are cut by binary search
     // record/replay queue
     std::vector<uint8_t> arena;
     struct QJob { int K, M, L, N; size_t offA, offB, offLB, offRB; };
@@ -844,7 +845,9 @@ int slot_wait(Device &d, Slot &s) {
 void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
     const double t0 = now_ms();
     const PairOut *outs = static_cast<const PairOut *>(s.hOut.p);
+    std::atomic<int64_t> cells{0}, failed{0};
     d.pool->run(s.count, 256, [&](int64_t lo, int64_t hi) {
+        int64_t c = 0, f = 0;
         for (int64_t i = lo; i < hi; ++i) {
             const int64_t g = s.first + i;
             yb_result &r = results[g];
@@ -852,22 +855,25 @@ void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
             memset(&r, 0, sizeof r);
             r.status = ji.status;
             r.cells = ji.cells;
-            if (ji.status != YB_OK) continue;
+            if (ji.status != YB_OK) { ++f; continue; }
+            c += ji.cells;
             const PairOut &o = outs[i];
             r.status = o.status;
+            if (o.status != YB_OK) ++f;
             r.m_new = o.m_new; r.C = o.C; r.D = o.D; r.I = o.I;
             // the device's 2-bit codes are the ABI's script format and the D2H copy put them in place
             r.script = ctx->scriptStore + ctx->scriptOff[(size_t)g];
         }
+        cells += c; failed += f;
     });
-    for (int64_t i = 0; i < s.count; ++i)
-        if (s.info[(size_t)i].status == YB_OK) d.cells += s.info[(size_t)i].cells;
+    d.cells += cells.load();
+    d.failed += failed.load();
     d.unpack_ms += now_ms() - t0;
 }
 
 void reset_stats(Device &d) {
     d.kernel_ms = d.fill_ms = d.profile_ms = d.tb_ms = d.h2d_ms = d.d2h_ms = d.pack_ms = d.unpack_ms = 0;
-    d.h2d_bytes = d.d2h_bytes = d.cells = 0;
+    d.h2d_bytes = d.d2h_bytes = d.cells = d.failed = 0;
     d.launches = d.waves = 0;
     d.err.clear();
     d.errJob = 0;
@@ -923,6 +929,7 @@ void plan_split(int64_t n, const int64_t *cells, int nparts, int64_t *cut) {
 constexpr int64_t kWavePairsWanted = 256;
 struct Dispatcher {
     const yb_job *jobs = nullptr;
+    const uint64_t *prefix = nullptr;      // input bytes of jobs [0, i), n + 1 entries (prepare_script_store)
     int64_t n = 0, cursor = 0;
     size_t maxBytes = 0, minBytes = 0, tailBytes = 0, remaining = 0;
     int64_t maxPairs = 0;
@@ -946,6 +953,16 @@ struct Dispatcher {
         const size_t hardBytes = 8 * maxBytes;
         size_t bytes = 0;
         int64_t i = lo;
+        if (prefix) {
+            // first job whose inclusion would pass the byte target, then the pairs rule, then the hard cap
+            auto upto = [&](size_t lim) {        // largest i with prefix[i] - prefix[lo] <= lim
+                return (int64_t)(std::upper_bound(prefix + lo, prefix + n + 1, prefix[lo] + lim) - prefix) - 1;
+            };
+            i = std::max(lo + 1, upto(target));
+            if (i - lo < wantPairs) i = std::max(i, std::min(lo + wantPairs, std::max(lo + 1, upto(hardBytes))));
+            i = std::min(std::min(i, n), lo + maxPairs);
+            bytes = (size_t)(prefix[i] - prefix[lo]);
+        } else
         while (i < n && i - lo < maxPairs) {
             size_t b = bytes_of(jobs[i]);
             if (i > lo && bytes + b > target && (i - lo >= wantPairs || bytes + b > hardBytes)) break;
@@ -1010,14 +1027,39 @@ int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
 }
 
 int prepare_script_store(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
-    ctx->scriptOff.assign((size_t)n, 0);
-    size_t tot = 0, blob = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        ctx->scriptOff[(size_t)i] = tot;
-        if (dims_ok(jobs[i])) tot += (((size_t)jobs[i].M + jobs[i].N + 15) / 16) * 4;   // packed, whole words: the layout
-                                                                                       // of the waves' device script pools
-        blob += Dispatcher::bytes_of(jobs[i]);
-    }
+    // per-job offsets into the script store (packed scripts, whole words: the layout of the waves' device script pools)
+    // and the batch's input bytes: a prefix sum over all jobs, done in chunks on the helper threads -- it runs before
+    // the first wave can be packed, i.e. while the device idles
+    ctx->scriptOff.resize((size_t)n);
+    ctx->blobPrefix.resize((size_t)n + 1);
+    constexpr int64_t CH = 4096;
+    const int64_t nch = (n + CH - 1) / CH;
+    std::vector<size_t> chTot((size_t)nch + 1, 0), chBlob((size_t)nch + 1, 0);
+    Pool &pool = *ctx->devs[0].pool;
+    pool.run(nch, 1, [&](int64_t a, int64_t z) {
+        for (int64_t c = a; c < z; ++c) {
+            size_t t = 0, b = 0;
+            for (int64_t i = c * CH, e = std::min(n, (c + 1) * CH); i < e; ++i) {
+                if (dims_ok(jobs[i])) t += (((size_t)jobs[i].M + jobs[i].N + 15) / 16) * 4;
+                b += Dispatcher::bytes_of(jobs[i]);
+            }
+            chTot[(size_t)c + 1] = t; chBlob[(size_t)c + 1] = b;
+        }
+    });
+    for (int64_t c = 0; c < nch; ++c) { chTot[(size_t)c + 1] += chTot[(size_t)c]; chBlob[(size_t)c + 1] += chBlob[(size_t)c]; }
+    pool.run(nch, 1, [&](int64_t a, int64_t z) {
+        for (int64_t c = a; c < z; ++c) {
+            size_t t = chTot[(size_t)c], b = chBlob[(size_t)c];
+            for (int64_t i = c * CH, e = std::min(n, (c + 1) * CH); i < e; ++i) {
+                ctx->scriptOff[(size_t)i] = t;
+                ctx->blobPrefix[(size_t)i] = b;
+                if (dims_ok(jobs[i])) t += (((size_t)jobs[i].M + jobs[i].N + 15) / 16) * 4;
+                b += Dispatcher::bytes_of(jobs[i]);
+            }
+        }
+    });
+    const size_t tot = chTot[(size_t)nch], blob = chBlob[(size_t)nch];
+    ctx->blobPrefix[(size_t)n] = blob;
     ctx->batchBlobBytes = blob;
     if (tot + 64 > ctx->scriptStoreCap) {
         if (ctx->scriptStore) cudaFreeHost(ctx->scriptStore);
@@ -1211,6 +1253,7 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     if (!ctx->scoresSet) { set_err(ctx, "yb_set_scores has not been called"); return YB_ERR_SCORES; }
     const double t0 = now_ms();
     if (prepare_script_store(ctx, n, jobs) != YB_OK) { set_err(ctx, "cudaHostAlloc failed for the script store"); return YB_ERR_CUDA; }
+    const double tPrepared = now_ms();
     for (auto &d : ctx->devs) {
         reset_stats(d);
         if (d.hasResident) {        // a resident batch sized slot 0 for the WHOLE batch: give that memory back before waves
@@ -1224,22 +1267,28 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     }
     Dispatcher disp;
     disp.jobs = jobs; disp.n = n;
+    disp.prefix = ctx->blobPrefix.data();
     disp.maxBytes = ctx->waveInBytes; disp.maxPairs = ctx->wavePairs;
     disp.minBytes = std::min(ctx->waveInBytes, ctx->waveMinBytes);
     disp.tailBytes = std::min(ctx->waveInBytes, ctx->waveTailBytes);
     disp.ndev = (int)ctx->devs.size();
     disp.remaining = ctx->batchBlobBytes;
     int rc = for_each_device(ctx, [&](int d) { return device_run(ctx, ctx->devs[(size_t)d], disp, results); });
+    const double tRan = now_ms();
     int64_t cells = 0;
     for (auto &d : ctx->devs) cells += d.cells;
     collect_stats(ctx, stats, now_ms() - t0, cells, n);
     if (getenv("YB_PROFILE"))
         for (auto &d : ctx->devs)
+            fprintf(stderr, "yama_b200[profile] prepare %.2f ms, devices %.2f ms\n", tPrepared - t0, tRan - tPrepared),
             fprintf(stderr, "yama_b200[profile] dev %d: waves %d total %.2f ms | pack %.2f (layout %.2f, analyse+copy %.2f, order %.2f, reserve %.2f) "
                     "launch %.2f wait %.2f unpack %.2f | device: h2d %.2f kernels %.2f d2h %.2f\n", d.id, d.waves, now_ms() - t0, d.pack_ms,
                     d.t_layout, d.t_par, d.t_post, d.t_reserve, d.t_launch, d.t_wait, d.unpack_ms, d.h2d_ms, d.kernel_ms, d.d2h_ms);
     if (rc != YB_OK) return rc;
     // per-pair failures: report the first in job order, in the reference's wording where it has one
+    int64_t failed = 0;
+    for (auto &d : ctx->devs) failed += d.failed;
+    if (failed == 0) return YB_OK;                  // (the usual case: no scan of the results)
     for (int64_t i = 0; i < n; ++i)
         if (results[i].status != YB_OK) {
             bool have = false;
