@@ -210,6 +210,25 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything but the result line goes to stderr: libraries (NCCL's version banner, torch) write to fd 1 too, and
+    the caller is owed exactly one JSON line there."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +240,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,7 +257,7 @@ def main():
             budget = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.warmup + args.steps)))
             r = cpu_reference_rate(args.workload, seed + s, procs, budget, args.scale)
             if r is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libyama_ref.so missing (built from /root/reference by oracle/Makefile)"}))
+                emit({"impl": "reference", "unavailable": "oracle/_ref/libyama_ref.so missing (built from /root/reference by oracle/Makefile)"})
                 return
             if s >= args.warmup:
                 vals.append(r)
@@ -252,7 +272,7 @@ def main():
                 "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": procs, "kind": "reference", "sample": sample},
                 "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---------------- our arm -------------------------------------------------------------------------
@@ -264,6 +284,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the yama path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its banner on STDOUT, next to the one JSON line this script owes its caller
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -369,7 +392,7 @@ def main():
                 line["cpu_baseline"] = {"value": r["gcups"], "unit": "GCUPS", "cores": 1, "kind": "reference",
                                         "pairs_per_s": r["pairs_per_s"],
                                         "sample": f"first {r['pairs']} pairs ({r['cells']} cells) of the same workload, reference yama() -O2, one core"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
