@@ -37,6 +37,7 @@ def test_golden_maf_cases_through_the_resident_server(tmp_path):
         assert os.path.exists(env["YB_SERVER"])                     # one server, still there for the next invocation
         check_golden_cases(SHIM_MULTIZ, tmp_path / "b", env=dict(env, YB_SCORE="gpu"))
         check_golden_cases(SHIM_MULTIZ, tmp_path / "c", env=dict(env, YB_DROPIN="direct"))
+        check_golden_cases(SHIM_MULTIZ, tmp_path / "d", env=dict(env, YB_DROPIN="stream"))       # the fast configuration
     finally:
         stop_server(env)
 

@@ -43,6 +43,7 @@ def test_resident_server_backend(tmp_path):
                                            env=dict(env, YB_SCORE="gpu"))
         check_speculation(rep)
         assert all("create_ms=0 " in last[0] for _, _, last in rep if last)      # no CUDA start-up in the tool itself
+        check_golden_cases(GPU_MULTIZ, tmp_path / "stream", env=dict(env, YB_DROPIN="stream"))   # streamed replay behind the server
     finally:
         stop_server(env)
 
