@@ -4,8 +4,9 @@
 // allocating pinned staging and device buffers -- often more than all of its host work.  tba and roast run multiz
 // once per tree node.  This process pays that once: it creates the yb context, listens on a unix socket and answers
 // the drop-in's batches (protocol: yb_wire.h) with yb_run_batch / yb_score_blocks of libyama_b200.so.  It has no
-// alignment logic of its own; one client at a time (others wait in the listen queue); exits after --idle seconds
-// without a client.  Started by hand, or by the drop-in itself when YB_SERVER names a socket nobody answers on.
+// alignment logic of its own; any number of clients stay connected, their requests are answered one at a time in
+// arrival order (each client's score tables are installed before its request if they differ); exits after --idle
+// seconds without a client.  Started by hand, or by the drop-in itself when YB_SERVER names a socket nobody answers on.
 //
 //   yama_b200d [--socket PATH] [--idle SECONDS]
 #include "../include/yama_b200.h"
@@ -19,7 +20,9 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
 #include <poll.h>
+#include <sys/file.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/un.h>
@@ -66,20 +69,21 @@ struct Server {
     std::vector<const uint8_t *> rows;
     uint64_t batches = 0, pairs = 0;
 
-    bool hello(int fd) {
+    // a client's greeting: its score tables (kept with the client, installed before each of its requests)
+    bool hello(int fd, std::vector<int32_t> &sc) {
         Hello h;
         if (!read_full(fd, &h, sizeof h) || h.magic != MAGIC_HELLO || h.version != VERSION) return false;
-        std::vector<int32_t> sc(SCORE_INTS);
-        if (!read_full(fd, sc.data(), sc.size() * 4)) return false;
-        if (sc != scores) {
-            if (yb_set_scores(ctx, sc.data(), sc.data() + 128 * 128, sc[128 * 128 + 16]) != YB_OK) {
-                fprintf(stderr, "yama_b200d: %s\n", yb_last_error(ctx));
-                scores.clear();
-                return true;                 // the batch will fail with YB_ERR_SCORES and carry the message
-            }
-            scores.swap(sc);
+        sc.resize(SCORE_INTS);
+        return read_full(fd, sc.data(), sc.size() * 4);
+    }
+    void install(const std::vector<int32_t> &sc) {
+        if (sc == scores) return;
+        if (yb_set_scores(ctx, sc.data(), sc.data() + 128 * 128, sc[128 * 128 + 16]) != YB_OK) {
+            fprintf(stderr, "yama_b200d: %s\n", yb_last_error(ctx));
+            scores.clear();                  // the request will fail with YB_ERR_SCORES and carry the message
+            return;
         }
-        return true;
+        scores = sc;
     }
 
     bool batch(int fd, const BatchReq &rq) {
@@ -144,21 +148,22 @@ struct Server {
         return write_full(fd, &rp, sizeof rp) && write_full(fd, err.data(), err.size());
     }
 
-    void serve(int fd) {
-        if (!hello(fd)) return;
-        for (;;) {
-            uint32_t magic;
-            if (!read_full(fd, &magic, 4)) return;
-            if (magic == MAGIC_BATCH) {
-                BatchReq rq;
-                rq.magic = magic;
-                if (!read_full(fd, reinterpret_cast<uint8_t *>(&rq) + 4, sizeof rq - 4) || !batch(fd, rq)) return;
-            } else if (magic == MAGIC_SCORE) {
-                ScoreReq rq;
-                rq.magic = magic;
-                if (!read_full(fd, reinterpret_cast<uint8_t *>(&rq) + 4, sizeof rq - 4) || !score(fd, rq)) return;
-            } else return;
+    // one request of a greeted client; false: the client is gone (or sent garbage) and is dropped
+    bool request(int fd, const std::vector<int32_t> &sc) {
+        uint32_t magic;
+        if (!read_full(fd, &magic, 4)) return false;
+        install(sc);
+        if (magic == MAGIC_BATCH) {
+            BatchReq rq;
+            rq.magic = magic;
+            return read_full(fd, reinterpret_cast<uint8_t *>(&rq) + 4, sizeof rq - 4) && batch(fd, rq);
         }
+        if (magic == MAGIC_SCORE) {
+            ScoreReq rq;
+            rq.magic = magic;
+            return read_full(fd, reinterpret_cast<uint8_t *>(&rq) + 4, sizeof rq - 4) && score(fd, rq);
+        }
+        return false;
     }
 };
 
@@ -187,6 +192,13 @@ int main(int argc, char **argv) {
         if (probe >= 0 && connect(probe, reinterpret_cast<sockaddr *>(&addr), sizeof addr) == 0) { close(probe); return 0; }
         if (probe >= 0) close(probe);
     }
+    // one server per socket: whoever holds the lock file serves; a second one started at the same moment (several
+    // clients found nobody at once) leaves, and its client finds the first
+    {
+        const std::string lock = path + ".lock";
+        int lf = open(lock.c_str(), O_CREAT | O_RDWR, 0600);
+        if (lf < 0 || flock(lf, LOCK_EX | LOCK_NB) != 0) return 0;      // (kept open, hence locked, for our lifetime)
+    }
     signal(SIGPIPE, SIG_IGN);
     Server S;
     if (yb_create(nullptr, 0, &S.ctx) != YB_OK) {          // (YB_DEVICES-style selection: CUDA_VISIBLE_DEVICES)
@@ -205,15 +217,30 @@ int main(int argc, char **argv) {
     signal(SIGTERM, on_signal);
     signal(SIGINT, on_signal);
     fprintf(stderr, "yama_b200d: serving %d device(s) on %s (idle limit %d s)\n", yb_device_count(S.ctx), path.c_str(), idle_s);
+    struct Client { int fd; bool greeted; std::vector<int32_t> scores; };
+    std::vector<Client> clients;
+    std::vector<pollfd> fds;
     for (;;) {
-        pollfd p{ls, POLLIN, 0};
-        int r = poll(&p, 1, idle_s > 0 ? idle_s * 1000 : -1);
+        fds.assign(1, pollfd{ls, POLLIN, 0});
+        for (auto &c : clients) fds.push_back(pollfd{c.fd, POLLIN, 0});
+        int r = poll(fds.data(), fds.size(), (clients.empty() && idle_s > 0) ? idle_s * 1000 : -1);
         if (r < 0 && errno == EINTR) continue;
-        if (r <= 0) break;                                   // idle (or error): leave
-        int fd = accept(ls, nullptr, nullptr);
-        if (fd < 0) continue;
-        S.serve(fd);
-        close(fd);
+        if (r < 0) break;
+        if (r == 0) { if (clients.empty()) break; else continue; }      // idle with nobody connected: leave
+        if (fds[0].revents & POLLIN) {
+            int fd = accept(ls, nullptr, nullptr);
+            if (fd >= 0) clients.push_back(Client{fd, false, {}});
+        }
+        for (size_t k = 1; k < fds.size(); ++k) {
+            if (!(fds[k].revents & (POLLIN | POLLHUP | POLLERR))) continue;
+            Client &c = clients[k - 1];
+            bool ok;
+            if (!c.greeted) { ok = S.hello(c.fd, c.scores); c.greeted = ok; }
+            else ok = S.request(c.fd, c.scores);
+            if (!ok) { close(c.fd); c.fd = -1; }
+        }
+        for (size_t k = clients.size(); k-- > 0;)
+            if (clients[k].fd < 0) clients.erase(clients.begin() + (long)k);
     }
     fprintf(stderr, "yama_b200d: idle, leaving after %llu batches / %llu pairs\n", (unsigned long long)S.batches, (unsigned long long)S.pairs);
     unlink(path.c_str());

@@ -42,6 +42,34 @@ def test_golden_maf_cases_through_the_resident_server(tmp_path):
         stop_server(env)
 
 
+def test_resident_server_answers_concurrent_clients(tmp_path):
+    """Several multiz invocations at once (parallel pipelines) share one yama_b200d: every client stays connected and
+    the server answers their requests one at a time; each output must still be the reference's."""
+    import shutil
+    import subprocess
+    from dropin_util import GOLD_MAF
+    env = dict(os.environ, **server_env(tmp_path, SHIM_SERVER))
+    try:
+        procs = []
+        for k in range(6):
+            d = tmp_path / f"w{k}"
+            d.mkdir()
+            for f in ("ref.sp1.maf", "ref.sp2.maf"):
+                shutil.copy(os.path.join(GOLD_MAF, f), d)
+            v = str(k % 2)
+            e = dict(env, YB_DROPIN="stream") if k >= 4 else env
+            procs.append((v, subprocess.Popen([SHIM_MULTIZ, "ref.sp1.maf", "ref.sp2.maf", v, "o1", "o2"], cwd=d, env=e,
+                                              stdout=subprocess.PIPE, stderr=subprocess.PIPE)))
+        for v, p in procs:
+            out, err = p.communicate(timeout=300)
+            assert p.returncode == 0, err.decode()[-300:]
+            want = open(os.path.join(GOLD_MAF, f"v{v}.stdout"), "rb").read()
+            strip = lambda b: b"".join(l for l in b.splitlines(keepends=True) if not l.startswith(b"#"))
+            assert strip(out) == strip(want)
+    finally:
+        stop_server(env)
+
+
 def test_no_server_and_no_spawn_fails_loudly(tmp_path):
     import shutil
     from dropin_util import GOLD_MAF, run_tool
