@@ -963,7 +963,8 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
 }  // extern "C"
 
 // The tool's entry point.  YB_DROPIN=direct keeps the reference's one-pair-at-a-time behaviour (each
-// yama() call is a synchronous GPU launch); the default batches through record/replay.
+// yama() call is a synchronous GPU launch); the default batches through record/replay (YB_DROPIN=batch), streamed
+// (YB_DROPIN=stream) when the resident server is the backend.
 int main(int argc, char **argv) {
     if (!ref_tool_main) {
         fprintf(stderr, "yama_dropin: linked without a reference tool (ref_tool_main)\n");
@@ -987,8 +988,9 @@ int main(int argc, char **argv) {
     if (m && strcmp(m, "direct") == 0) {
         G.mode = DIRECT;
         rc = ref_tool_main(argc, argv);
-    } else if (m && strcmp(m, "stream") == 0) {
-        rc = run_streamed(argc, argv);
+    } else if ((m && strcmp(m, "stream") == 0) || (R.enabled && !(m && strcmp(m, "batch") == 0))) {
+        rc = run_streamed(argc, argv);          // (the default behind the resident server: nothing to start up, so the
+                                                //  real pass can run beside the speculative one from the first call)
     } else {
         rc = run_batched(argc, argv);
     }

@@ -33,11 +33,11 @@ def test_golden_maf_cases_through_the_resident_server(tmp_path):
     assert os.path.exists(SHIM_SERVER)
     env = server_env(tmp_path, SHIM_SERVER)
     try:
-        check_golden_cases(SHIM_MULTIZ, tmp_path / "a", env=env)
+        check_golden_cases(SHIM_MULTIZ, tmp_path / "a", env=dict(env, YB_DROPIN="batch"))
         assert os.path.exists(env["YB_SERVER"])                     # one server, still there for the next invocation
         check_golden_cases(SHIM_MULTIZ, tmp_path / "b", env=dict(env, YB_SCORE="gpu"))
         check_golden_cases(SHIM_MULTIZ, tmp_path / "c", env=dict(env, YB_DROPIN="direct"))
-        check_golden_cases(SHIM_MULTIZ, tmp_path / "d", env=dict(env, YB_DROPIN="stream"))       # the fast configuration
+        check_golden_cases(SHIM_MULTIZ, tmp_path / "d", env=env)        # the default behind a server: streamed replay
     finally:
         stop_server(env)
 
