@@ -1501,8 +1501,8 @@ int yb_score_blocks(yb_ctx *ctx, int64_t n, const yb_block *blocks, double *scor
         if (b.nrows < 0 || (b.nrows > 0 && !b.rows)) { set_err(ctx, "yb_score_blocks: block %lld has no rows", (long long)i); return YB_ERR_ARG; }
         pairCols += (int64_t)b.nrows * (b.nrows - 1) / 2 * b.size;
     }
-    const size_t waveBytes = (size_t)64 << 20;
-    int rc = YB_OK, which = 0;
+    const size_t waveMax = (size_t)64 << 20;
+    int rc = YB_OK, which = 0, waveNo = 0;
     std::vector<ScoreLayout> lay;
     std::vector<uint32_t> rowBlock;              // per text row of the wave: its block (wave-relative)
     std::vector<uint32_t> rowFirst;              // per block of the wave: index of its first row
@@ -1512,6 +1512,8 @@ int yb_score_blocks(yb_ctx *ctx, int64_t n, const yb_block *blocks, double *scor
         lay.clear(); rowBlock.clear(); rowFirst.clear();
         size_t text = 0;
         int64_t units = 0, hi = lo;
+        const size_t waveBytes = std::min(waveMax, ((size_t)16 << 20) << std::min(waveNo, 4));   // small first waves: the
+        ++waveNo;                                                                                // device starts early
         while (hi < n && (hi == lo || text < waveBytes)) {
             const yb_block &b = blocks[hi];
             ScoreLayout L;
