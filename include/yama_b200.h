@@ -69,6 +69,8 @@ typedef struct {
 } yb_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
+/* A context is used by one thread at a time (the reference is single-threaded); it runs its own
+ * helper threads and streams inside a call.  Different contexts are independent, also across threads. */
 /* devices==NULL or ndev<=0: use every visible CUDA device. */
 int yb_create(const int *devices, int ndev, yb_ctx **out);
 void yb_destroy(yb_ctx *ctx);
