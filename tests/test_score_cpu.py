@@ -91,3 +91,52 @@ def test_shim_answers_the_score_abi_like_the_oracle(oracle):
     assert shim.yb_score_blocks(h, len(cases), blocks.ctypes.data, scores.ctypes.data, None) == -6      # YB_ERR_ARG
     assert b"mafScoreRange: start = " in shim.yb_last_error(h)
     shim.yb_destroy(h)
+
+
+def _count_form_score(text, start, size, S6, gap_open):
+    """The kernel's derivation (score_kernels.cuh) in numpy: per column ten counts and a quadratic form."""
+    t = np.asarray(text, dtype=np.uint8)
+    low = t | 0x20
+    cls = np.full(t.shape, 4, dtype=np.int64)
+    for k, ch in enumerate(b"acgt"):
+        cls[low == ch] = k
+    cls[t == ord("-")] = 5
+    total = 0
+    for i in range(start, start + size):
+        n = np.bincount(cls[:, i], minlength=6).astype(np.int64)
+        s = 0
+        for k in range(6):
+            s += int(S6[k][k]) * int(n[k] * (n[k] - 1) // 2)
+            for l in range(k + 1, 6):
+                s += int(S6[k][l]) * int(n[k] * n[l])
+        if i > 0:
+            d, p = t[:, i] == ord("-"), t[:, i - 1] == ord("-")
+            t00, t01, t10, t11 = int((~p & ~d).sum()), int((~p & d).sum()), int((p & ~d).sum()), int((p & d).sum())
+            s -= gap_open * (t00 * t01 + t01 * t10 + t10 * t11)
+        total += s
+    return float(total)
+
+
+@pytest.mark.parametrize("which", [70, 85])
+def test_count_vector_form_equals_the_pair_loop(which):
+    """The O(rows) closed form the CUDA kernel uses (six class counts + three dash-transition counts per column) against
+    the oracle's O(rows^2) pair loop, on the golden blocks and on random ones, for both score sets."""
+    from oracle.oracle_py import Oracle
+    o = Oracle(which)
+    reps = b"ACGTN-"
+    S6 = [[int(o.ss[a, b]) for b in reps] for a in reps]
+    GO = int(o.gop[1])
+    assert all(S6[a][b] == S6[b][a] for a in range(6) for b in range(6))
+    g = GoldenScores()
+    want = g.expected(which)
+    for i in range(0, g.n, 3):
+        text, start, size = g.block(i)
+        if text.shape[0] * size > 40000:
+            continue
+        assert _count_form_score(text, start, size, S6, GO) == want[i], i
+    rng = np.random.default_rng(which)
+    for _ in range(40):
+        rows, cols = int(rng.integers(1, 25)), int(rng.integers(1, 120))
+        text = alignment_block(rng, rows, cols, sub=0.25, gap_open=0.1, lower=0.1, other=0.05)
+        start = int(rng.integers(0, cols)); size = int(rng.integers(1, cols - start + 1))
+        assert _count_form_score(text, start, size, S6, GO) == o.score_range(text, start, size)
