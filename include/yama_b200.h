@@ -49,7 +49,8 @@ typedef struct {
 typedef struct {
     int32_t status;      /* YB_OK or a YB_ERR_* for this pair                                   */
     int32_t m_new;       /* merged width == number of edit ops (*OM of the reference)           */
-    int32_t C, D, I;     /* the three node scores at grid point (M,N) (mz_yama.c:262-267)       */
+    int32_t C, D, I;     /* the three node scores at grid point (M,N) (mz_yama.c:262-267); a node that no
+                            alignment path reaches holds a value near INT_MIN/2 whose low bits are unspecified */
     int32_t reserved;
     int64_t cells;       /* DP cells of this pair == tback_size of mz_yama.c:60-66              */
     const uint8_t *script; /* m_new ops in the reference's own (reversed) order, mz_yama.c:278, PACKED 2 bits

@@ -16,7 +16,7 @@
 // lanesOf(wmax, M) -> wavefront width B (32, 128, 256 ...) the pair will run with; the schedule depends on it
 extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ LB, const int32_t *__restrict__ RB,
                                      int32_t *wmax, int32_t *__restrict__ sched, int32_t *nSteps,
-                                     int (*lanesOf)(int, int), int32_t *lanes) {
+                                     int (*lanesOf)(int, int), int32_t *lanes, int32_t *connected) {
     const int need = N < 10 ? N : 10;
     int bad = (LB[0] != 0) | (RB[M] != N);
     int64_t cells = 0;
@@ -39,9 +39,15 @@ extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ L
         bad |= badw;
     }
     {
-        int badm = 0;
-        for (int r = 1; r <= M; ++r) badm |= (LB[r] < LB[r - 1]) | (RB[r] < RB[r - 1]);
+        // (connected: every row can be reached from the row above -- LB[r] <= RB[r-1] + 1; the reference does not ask for
+        //  it and pre_yama's bands always are, but the fill variant without existence multipliers relies on it)
+        int badm = 0, gap = 0;
+        for (int r = 1; r <= M; ++r) {
+            badm |= (LB[r] < LB[r - 1]) | (RB[r] < RB[r - 1]);
+            gap |= (LB[r] > RB[r - 1] + 1);
+        }
         bad |= badm;
+        if (connected) *connected = !gap;
     }
     if (bad) return -1;
     *wmax = wm + 1;
@@ -73,12 +79,12 @@ extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ L
 
 #ifdef YB_BAND_SCAN_DISPATCH
 extern "C" int64_t yb_band_scan_avx2(int, int, const int32_t *, const int32_t *, int32_t *, int32_t *, int32_t *,
-                                     int (*)(int, int), int32_t *);
+                                     int (*)(int, int), int32_t *, int32_t *);
 extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
-                                int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes) {
+                                int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes, int32_t *connected) {
     // YB_NO_AVX2=1 forces the baseline build (the CPU suite runs both)
     static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("YB_NO_AVX2");
-    return avx2 ? yb_band_scan_avx2(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes)
-                : YB_BAND_SCAN_NAME(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes);
+    return avx2 ? yb_band_scan_avx2(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes, connected)
+                : YB_BAND_SCAN_NAME(M, N, LB, RB, wmax, sched, nSteps, lanesOf, lanes, connected);
 }
 #endif

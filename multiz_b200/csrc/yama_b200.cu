@@ -36,7 +36,7 @@
 using namespace yb;
 
 extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
-                                int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes);   // band_scan.cpp
+                                int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes, int32_t *connected);   // band_scan.cpp
 
 namespace {
 
@@ -159,6 +159,7 @@ struct JobInfo {           // host-side facts about one pair
     int status = YB_OK;
     int bin = 0;           // kernel bin (ring size, warps per pair)
     int bucket = 0;        // launch-order bucket: ring bin * NB + quarter-octave of the cell count, descending
+    int connected = 0;     // every band row is reachable from the row above (LB[r] <= RB[r-1] + 1)
 };
 
 // One staging slot = one wave in flight.
@@ -185,6 +186,7 @@ struct Slot {
     int nLong = 0;                         // pairs whose traceback path gets a warp of its own
     int tbLong = TB_LONG;                  // ... those with at least this many moves
     bool y16 = false;                      // every pair has K*gap_open <= 32767: the kernels' 16-bit weight forms
+    bool ungated = false;                  // every pair is small enough for the fill variant without existence multipliers
     int nValid = 0;
     int binStart[NBINS + 1] = {};
 };
@@ -230,6 +232,8 @@ struct yb_ctx {
     bool scoresSet = false;
     ScoreConst sc{};
     int maxDepth = 255;
+    int maxAbsS = 1;                        // max |S6|
+    bool ungatedOk = true;                  // YB_UNGATED=0 keeps the existence multipliers in every fill kernel
     int nThreads = 1;
     size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave (steady state)
     size_t waveMinBytes = (size_t)16 << 20; // first waves of a batch (the device idles while the first wave is packed)
@@ -365,13 +369,13 @@ size_t fill_smem(int bin) {
 
 // ---- kernels with a runtime warps-per-CTA: thin wrappers around the template ---------------------
 namespace yb {
-template <int RING, int G, int P, bool Y16>
+template <int RING, int G, int P, bool Y16, bool GATED = true>
 __global__ void __launch_bounds__(G * P * 32)
 yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                  const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
                  const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int gapOpen, int gapExt) {
-    fill_body<RING, G, P, Y16>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
+    fill_body<RING, G, P, Y16, GATED>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
 }
 }  // namespace yb
 
@@ -379,7 +383,10 @@ namespace {
 
 typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *, const ColRec *,
                        unsigned char *, const unsigned long long *, PairOut *, int, int);
-FillFn fill_fn(int bin, bool y16) {
+// ungated: the variant without existence multipliers (bulk bins only), for waves of small enough pairs (Slot::ungated)
+FillFn fill_fn(int bin, bool y16, bool ungated = false) {
+    if (ungated && y16 && bin == 0) return yb_fill_kernel_w<128, 1, 8, true, false>;
+    if (ungated && y16 && bin == 1) return yb_fill_kernel_w<512, 1, 8, true, false>;
     switch (bin) {
         case 0: return y16 ? yb_fill_kernel_w<128, 1, 8, true> : yb_fill_kernel_w<128, 1, 8, false>;
         case 1: return y16 ? yb_fill_kernel_w<512, 1, 8, true> : yb_fill_kernel_w<512, 1, 8, false>;
@@ -406,6 +413,8 @@ int device_init(Device &d) {
         FillFn fn = fill_fn(b, true);
         size_t sm = fill_smem(b);
         CUDA_TRY(d, cudaFuncSetAttribute(fill_fn(b, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        if (fill_fn(b, true, true) != fn)
+            CUDA_TRY(d, cudaFuncSetAttribute(fill_fn(b, true, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         int occ = 0;
         CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBin[b].G * kBin[b].P * 32, sm));
@@ -472,8 +481,9 @@ void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, ch
     // vectorised scan (band_scan.cpp): validation + cells + widest row + schedule in one pass; on a violation
     // the scalar loop below words the message as the reference does
     int nSteps = 0, lanes = 0;
-    int64_t cells = yb_band_scan(j.M, j.N, j.LB, j.RB, &ji.wmax, sched, &nSteps, lanes_of, &lanes);
+    int64_t cells = yb_band_scan(j.M, j.N, j.LB, j.RB, &ji.wmax, sched, &nSteps, lanes_of, &lanes, &ji.connected);
     if (cells < 0) {
+        ji.connected = 0;
         cells = check_band(j.M, j.N, j.LB, j.RB, msg, msglen, &ji.wmax);
         if (cells < 0) { ji.status = YB_ERR_BAND; return; }
         lanes = lanes_of(ji.wmax, j.M);                        // (unreachable unless the two scans disagree)
@@ -517,16 +527,22 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     s.off.resize((size_t)count);
     size_t blob = 0, rows = 0, cols = 0, words = 0;
     int maxK = 0;
+    int64_t maxWork = 0;                     // max over pairs of (M+N)*K*L: bounds every real score and every drift
     for (int64_t i = 0; i < count; ++i) {
         const yb_job &j = jobs[first + i];
         s.off[(size_t)i] = Slot::Off{blob, rows, cols, (uint32_t)words};
         if (!dims_ok(j)) continue;
         maxK = std::max(maxK, j.K);
+        maxWork = std::max(maxWork, ((int64_t)j.M + j.N) * j.K * j.L);
         blob += blob_bytes(j); rows += (size_t)j.M + 1; cols += (size_t)j.N + 1;
         words += ((size_t)j.M + j.N + 15) / 16;
     }
     s.first = first;
     s.y16 = (int64_t)std::min(maxK, ctx->maxDepth) * ctx->sc.gap_open <= 32767;
+    // Without existence multipliers a candidate from a node that does not exist (exactly MININT = -2^30) is charged a
+    // gap-open the reference skips.  That cannot change any real value, flag or script as long as real scores stay
+    // within +-2^28 and unreal ones within [-2^31, -2^29): both follow from (M+N)*K*L*(gap_open+gap_extend+max|S|) < 2^28.
+    s.ungated = ctx->ungatedOk && (long double)maxWork * (ctx->sc.gap_open + ctx->sc.gap_ext + ctx->maxAbsS) < (long double)(1 << 28);
     s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
     s.orderOff = s.metaBytes;
     s.longOff = s.orderOff + align_up((size_t)count * 4, 256);
@@ -656,6 +672,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
         tbBase[i] = tb;
         tb += need;
         s.bucketCount[(size_t)ji.bucket]++;
+        if (!ji.connected) s.ungated = false;
     }
     count = kept;
     s.count = count;
@@ -744,7 +761,7 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
         int blocks = std::min((n + bc.P - 1) / bc.P, d.fillBlocks[b]);
         cudaStream_t bs = b == 0 ? st : s.binStream[b];
         if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
-        fill_fn(b, s.y16)<<<blocks, bc.G * bc.P * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
+        fill_fn(b, s.y16, s.ungated)<<<blocks, bc.G * bc.P * 32, fill_smem(b), bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
                                                                   reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs, d.sc.gap_open, d.sc.gap_ext);
         if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
         d.launches++;
@@ -1137,6 +1154,7 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_NT")) ctx->ntStores = atoi(e) != 0;
     if (const char *e = getenv("YB_EARLY_H2D")) ctx->earlyH2D = atoi(e) != 0;
+    if (const char *e = getenv("YB_UNGATED")) ctx->ungatedOk = atoi(e) != 0;
     if (const char *e = getenv("YB_TB_LONG")) ctx->tbLong = std::max(1, atoi(e));
     if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
     for (auto &d : ctx->devs) {
@@ -1212,6 +1230,7 @@ int yb_set_scores(yb_ctx *ctx, const int32_t *ss, const int32_t *gop, int32_t ga
     ctx->sc = sc;
     // 16-bit weights in the kernels: sum-of-pairs weights K*max|S6| and the extension weight K*gap_extend
     ctx->maxDepth = std::min(255, 32767 / std::max(maxabs, std::max(1, (int)gap_extend)));
+    ctx->maxAbsS = maxabs;
     for (auto &d : ctx->devs) d.sc = sc;
     ctx->scoresSet = true;
     return YB_OK;
@@ -1223,7 +1242,7 @@ int yb_pair_facts(const yb_job *job, int64_t *cells, int32_t *wmax, int32_t *nst
     std::vector<int> s1((size_t)nblk + 1, -1), s2((size_t)nblk + 1, -1);
     int w1 = 0, w2 = 0, n1 = 0;
     int lanes1 = 0;
-    const int64_t c1 = yb_band_scan(job->M, job->N, job->LB, job->RB, &w1, s1.data(), &n1, lanes_of, &lanes1);
+    const int64_t c1 = yb_band_scan(job->M, job->N, job->LB, job->RB, &w1, s1.data(), &n1, lanes_of, &lanes1, nullptr);
     const int64_t c2 = check_band(job->M, job->N, job->LB, job->RB, msg, msglen, &w2);
     if (c2 < 0) return c1 < 0 ? YB_ERR_BAND : YB_ERR_LIMIT;
     const int lanes2 = lanes_of(w2, job->M);

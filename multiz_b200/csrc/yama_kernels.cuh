@@ -306,7 +306,7 @@ __device__ __forceinline__ int pick3(int x, int y, int z, bool exists, unsigned 
 // P:    groups (= pairs in flight) per CTA; P > 1 only with G = 1.
 // Y16:  every pair of the launch has K*gap_open <= 32767: the ungated y candidates and the I-node z candidate take
 //       one dp2a with 16-bit weights instead of dp4a/extract + imad.
-template <int RING, int G, int P, bool Y16>
+template <int RING, int G, int P, bool Y16, bool GATED = true>
 __device__ __forceinline__ void
 fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
@@ -449,7 +449,10 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     }
                 }
                 const int Cu = (int)up.x, Du = (int)up.y, Iu = (int)up.z;
-                const int gCu = (int)(short)(up.w & 0xffffu), gIu = ((int)up.w) >> 16;
+                // GATED = false: every pair of the launch is small enough (host-side bound) that a candidate from a node
+                // that does not exist -- exactly MININT -- can be charged like any other without ever winning a comparison
+                // against a real one, so the existence multipliers need not travel with the records
+                const int gCu = GATED ? (int)(short)(up.w & 0xffffu) : nGO, gIu = GATED ? ((int)up.w) >> 16 : nGO;
                 const bool active = (c16 >= LB16);
 
                 // column record of column c; lanes outside their row read a clamped (valid) column and discard the result
@@ -461,14 +464,14 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 acc >>= 8;                                   // make room for this cell's byte (bits 24..31)
                 const bool hasI = c16 > LB16, hasC = c16 > LBp16;
                 {
-                    int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
+                    int x = Cl + dp4a_uu(cw.x, avXI, 0) * (GATED ? gCl : nGO);
                     int y, z;
                     if (Y16) {
                         y = dp2a_hi_su((unsigned)gIrow, cw.x, Dl);                    // K*ndB opens (mz_yama.c:131-134)
-                        z = dp2a_lo_su((unsigned)gIl, cw.x, Il);                      // K*b10, if I(r,c-1) exists
+                        z = dp2a_lo_su((unsigned)(GATED ? gIl : gIz), cw.x, Il);       // K*b10, if I(r,c-1) exists
                     } else {
                         y = Dl + (int)__byte_perm(cw.x, 0, 0x4442) * gIrow;
-                        z = Il + (int)__byte_perm(cw.x, 0, 0x4441) * gIl;
+                        z = Il + (int)__byte_perm(cw.x, 0, 0x4441) * (GATED ? gIl : gIz);
                     }
                     vI = pick3<4>(x, y, z, hasI, acc);
                     vI = dp2a_hi_su(nKGE_lo, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
@@ -476,9 +479,9 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                 vI = hasI ? vI : MININT;
                 // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
                 {
-                    int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
+                    int x = Cd + dp4a_uu(cw.w, avXC, 0) * (GATED ? gCd : nGO);
                     int y = Y16 ? dp2a_hi_su(avYC, cw.w, Dd) : Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
-                    int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
+                    int z = Id + dp4a_uu(cw.w, avZC, 0) * (GATED ? gId : nGO);
                     vC = pick3<0>(x, y, z, hasC, acc);
                     vC = dp2a_lo_su(w01, cw.y, vC);
                     vC = dp2a_hi_su(w23, cw.y, vC);
@@ -493,13 +496,13 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
                     vD = pick3<2>(x, y, z, true, acc) - eD;
                 }
                 if (active) {
-                    sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, hasI ? E_both : Efirst);
+                    sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, GATED ? (hasI ? E_both : Efirst) : 0u);
                 }
                 // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
                 if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * (2 * B) + tbWord + ((t4 >> 2) & 1)] = acc;
                 Cl = vC; Dl = vD; Il = vI;
-                gCl = hasC ? nGO : 0; gIl = hasI ? gIz : 0;
-                Cd = Cu; Dd = Du; Id = Iu; gCd = gCu; gId = gIu;
+                if (GATED) { gCl = hasC ? nGO : 0; gIl = hasI ? gIz : 0; gCd = gCu; gId = gIu; }
+                Cd = Cu; Dd = Du; Id = Iu;
                 c16 += 16;
                 group_sync();
             }

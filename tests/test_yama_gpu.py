@@ -252,3 +252,45 @@ def test_two_devices_in_one_context_match_one_device(oracle):
     finally:
         one.close()
         two.close()
+
+
+def test_fill_variant_without_existence_multipliers_is_exact(oracle):
+    """Waves of small pairs run a fill kernel that charges candidates from non-existent nodes like any other (DESIGN
+    section 2: they are exactly MININT and can never win).  Same batch with the variant forced off (YB_UNGATED=0): every
+    result field and script must agree, and both must agree with the oracle; disconnected bands and pairs beyond the
+    size bound must fall back to the gated kernel by themselves."""
+    import os
+    from multiz_b200 import YamaB200
+    rng = np.random.default_rng(404)
+    probs = []
+    for it in range(400):
+        K, L = int(rng.integers(1, 9)), int(rng.integers(1, 5))
+        M, N = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        band = ("smooth", "ragged", "full")[it % 3]
+        if band == "full" and M * N > 4000:
+            M = max(1, 4000 // N)
+        probs.append(random_problem(rng, K, L, M, N, band=band, alphabet=("acgt", "mixed", "weird")[it % 3]))
+    sb = SynthBatch(9, [2, 3, 5, 8] * 30, [1, 1, 2, 4] * 30, list(rng.integers(30, 1500, 120)), R=30, lower=0.05)
+    probs += [tuple(np.array(x) for x in sb.problem(i)) for i in range(sb.n)]
+    on = YamaB200(devices=[0])
+    os.environ["YB_UNGATED"] = "0"
+    try:
+        off = YamaB200(devices=[0])
+    finally:
+        del os.environ["YB_UNGATED"]
+    try:
+        jobs, keep = on.make_jobs(probs)
+        ra, _ = on.run_batch(jobs)
+        rb, _ = off.run_batch(jobs)
+        for i in range(len(probs)):
+            assert tuple(ra[i][f] for f in ("status", "m_new", "C", "D", "I", "cells")) == \
+                   tuple(rb[i][f] for f in ("status", "m_new", "C", "D", "I", "cells")), i
+            assert np.array_equal(on.script_of(ra[i]), off.script_of(rb[i])), i
+        for i in range(0, len(probs), 5):
+            A, B, LB, RB = probs[i]
+            o = oracle.yama(A, B, LB, RB, want_tback=False)
+            assert np.array_equal(on.script_of(ra[i]), o["script"]), i
+            assert (int(ra[i]["C"]), int(ra[i]["D"]), int(ra[i]["I"])) == tuple(int(x) for x in o["cdi"]), i
+    finally:
+        on.close()
+        off.close()
