@@ -43,8 +43,10 @@ def _trans(prev, cur):        # counts of (previous is dash, this is dash); no p
     return t
 
 
-def count_form_yama(A, B, LB, RB, S6, GO, GE):
-    """A [M,K], B [N,L] -> (C, D, I at (M,N), traceback bytes in the reference's row-major band order)."""
+def count_form_yama(A, B, LB, RB, S6, GO, GE, gates=True):
+    """A [M,K], B [N,L] -> (C, D, I at (M,N), traceback bytes in the reference's row-major band order).
+    gates=False drops the reference's existence guards on candidates (the fill kernels' GATED=false variant): a candidate
+    from a node that does not exist -- exactly MININT -- is charged like any other."""
     M, K = A.shape
     N, L = B.shape
     cA = [None] + [_cls(A[r - 1]) for r in range(1, M + 1)]
@@ -73,10 +75,10 @@ def count_form_yama(A, B, LB, RB, S6, GO, GE):
                 dB = cB[c][5]; ndB = L - dB; b10 = b[c][1][0]
                 x, y, z = C, D, I
                 if r < M:
-                    if c > LB[r - 1] + 1:
+                    if not gates or c > LB[r - 1] + 1:
                         x -= GO * (ndA * ndB + dA * b10)
                     y -= GO * K * ndB
-                    if c > LB[r] + 1:
+                    if not gates or c > LB[r] + 1:
                         z -= GO * K * b10
                 nI, fi = _pick(_wrap(x), _wrap(y), _wrap(z))
                 nI = _wrap(nI - ndB * K * GE)
@@ -87,11 +89,11 @@ def count_form_yama(A, B, LB, RB, S6, GO, GE):
                 x, y, z = gc, gd, gi
                 if c > 1:
                     dB = cB[c][5]; ndB = L - dB; b01, b10 = b[c][0][1], b[c][1][0]
-                    if r > 1 and c > LB[r - 2] + 1:
+                    if r > 1 and (not gates or c > LB[r - 2] + 1):
                         x -= GO * (a00 * b01 + a01 * ndB + a10 * dB + a11 * b10)
                     if r > 1:
                         y -= GO * (dA * ndB + a10 * dB)
-                    if c > LB[r - 1] + 1:
+                    if not gates or c > LB[r - 1] + 1:
                         z -= GO * (ndA * dB + dA * b10)
                 nC, fc = _pick(_wrap(x), _wrap(y), _wrap(z))
                 nC = _wrap(nC + sum(w[r][l] * cB[c][l] for l in range(6)))
@@ -101,11 +103,11 @@ def count_form_yama(A, B, LB, RB, S6, GO, GE):
             x, y, z = dpC[c], dpD[c], dpI[c]
             if 0 < c < N:
                 dB = cB[c][5]; ndB = L - dB
-                if r > 1 and c > LB[r - 2]:
+                if r > 1 and (not gates or c > LB[r - 2]):
                     x -= GO * (ndA * ndB + a10 * dB)
                 if r > 1:
                     y -= GO * L * a10
-                if c > LB[r - 1]:
+                if not gates or c > LB[r - 1]:
                     z -= GO * L * ndA
             nD, fd = _pick(_wrap(x), _wrap(y), _wrap(z))
             nD = _wrap(nD - ndA * L * GE)
@@ -130,3 +132,49 @@ def test_count_vector_form_reproduces_every_traceback_byte(oracle, band):
         cdi, tb = count_form_yama(np.asarray(A), np.asarray(B), [int(v) for v in LB], [int(v) for v in RB], S6, GO, GE)
         assert cdi == tuple(int(v) for v in want["cdi"]), (band, it, K, L, M, N)
         assert np.array_equal(tb, want["tback"]), (band, it, K, L, M, N)
+
+
+def _script(tb, cdi, M, N, LB, RB):
+    """mz_yama.c:257-291 on the row-major band-compact traceback bytes."""
+    start = [0]
+    for r in range(M + 1):
+        start.append(start[-1] + RB[r] - LB[r] + 1)
+    C, D, I = cdi
+    node = FLAG_C if (C >= D and C >= I) else (FLAG_D if D >= I else FLAG_I)
+    r, c, out = M, N, []
+    while r > 0 or c > 0:
+        assert r >= 0 and LB[r] <= c <= RB[r]
+        st = int(tb[start[r] + c - LB[r]])
+        out.append(node)
+        if node == FLAG_I:
+            c -= 1; node = st >> 4
+        elif node == FLAG_D:
+            r -= 1; node = (st >> 2) & 3
+        else:
+            r -= 1; c -= 1; node = st & 3
+    return out
+
+
+def test_dropping_the_existence_guards_changes_no_script(oracle):
+    """The argument behind the fill kernels' GATED=false variant, executable: with connected bands
+    and scores far from 2^28, charging candidates from non-existent nodes can only change traceback bytes of unreachable
+    nodes -- the final scores and the edit script stay the reference's."""
+    reps = b"ACGTN-"
+    S6 = [[int(oracle.ss[x, y]) for y in reps] for x in reps]
+    GO, GE = int(oracle.gop[1]), int(oracle.gap_ext)
+    rng = np.random.default_rng(2718)
+    changed_bytes = 0
+    for it in range(240):
+        band = ("smooth", "full", "ragged")[it % 3]
+        K, L = int(rng.integers(1, 7)), int(rng.integers(1, 7))
+        M, N = int(rng.integers(1, 36)), int(rng.integers(1, 36))
+        A, B, LB, RB = random_problem(rng, K, L, M, N, band=band, alphabet=("acgt", "mixed", "weird")[it % 3])
+        LB, RB = [int(v) for v in LB], [int(v) for v in RB]
+        if any(LB[r] > RB[r - 1] + 1 for r in range(1, M + 1)):
+            continue                                   # (the library keeps the guards for disconnected bands)
+        want = oracle.yama(A, B, LB, RB, want_tback=True)
+        cdi, tb = count_form_yama(np.asarray(A), np.asarray(B), LB, RB, S6, GO, GE, gates=False)
+        assert cdi == tuple(int(v) for v in want["cdi"]), (band, it)
+        assert _script(tb, cdi, M, N, LB, RB) == [int(v) for v in want["script"]], (band, it)
+        changed_bytes += int((tb != want["tback"]).sum())
+    # (on connected bands the guards rarely decide even an unreachable node's byte: `changed_bytes` is usually 0)
