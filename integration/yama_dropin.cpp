@@ -115,6 +115,7 @@ struct Globals {
     int passes = 0;
     double child_ms = 0, final_ms = 0;      // wall time of the speculative passes / of the real pass
     double create_ms = 0, t_start = 0;      // yb_create (CUDA start-up), process start
+    double hit_ms = 0;                      // real pass: time inside yama() for table hits (hash + assemble)
     int scoreGpu = -1;                      // YB_SCORE=gpu: mafScoreRange on the device in the real pass
     uint64_t scoreCalls = 0;
     double score_ms = 0;
@@ -827,10 +828,10 @@ void print_stats() {
     if (!G.stats) return;
     fprintf(stderr,
             "yama_b200: passes=%d batches=%lld jobs=%lld failed=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
-            "gpu_ms=%.2f kernel_ms=%.2f create_ms=%.0f speculative_ms=%.0f final_ms=%.0f wall_ms=%.0f score_calls=%llu score_ms=%.1f stream_waits=%llu devices=%d\n",
+            "gpu_ms=%.2f kernel_ms=%.2f create_ms=%.0f speculative_ms=%.0f final_ms=%.0f wall_ms=%.0f hit_ms=%.0f score_calls=%llu score_ms=%.1f stream_waits=%llu devices=%d\n",
             G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.failed, (long long)G.cells, (unsigned long long)G.calls,
             (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.create_ms, G.child_ms, G.final_ms,
-            now_ms() - G.t_start, (unsigned long long)G.scoreCalls, G.score_ms, (unsigned long long)S.waits, R.enabled ? R.devices : (G.ctx ? yb_device_count(G.ctx) : 0));
+            now_ms() - G.t_start, G.hit_ms, (unsigned long long)G.scoreCalls, G.score_ms, (unsigned long long)S.waits, R.enabled ? R.devices : (G.ctx ? yb_device_count(G.ctx) : 0));
 }
 
 }  // namespace
@@ -900,6 +901,7 @@ double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_siz
 
 void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uchar ***OAL, int *OM) {
     ++G.calls;
+    const double tHit0 = (G.stats && G.mode == REPLAY) ? now_ms() : 0.0;
     std::vector<uint8_t> tmpA, tmpB;
     yb_job job;
     job.K = K; job.M = M; job.L = L; job.N = N;
@@ -934,6 +936,7 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
                 if (lk.owns_lock()) lk.unlock();
                 ++G.nHits;
                 emit(job, e.m_new, e.script, OAL, OM);
+                if (G.stats && G.mode == REPLAY) G.hit_ms += now_ms() - tHit0;
                 return;
             }
             // streamed: not answered yet?  Wait while the child may still ship it: it has not reached this call, or
