@@ -81,13 +81,24 @@ struct KeyHash {
     size_t operator()(const Key &k) const { return (size_t)(k.a ^ (k.b * 0x9e3779b97f4a7c15ull)); }
 };
 
+// What identifies a job besides its 128-bit key: the dimensions and a second, independently computed digest of the
+// content (CRC-32C lanes over A|B and over LB|RB).  A table hit is only trusted when these agree too, so a key
+// collision between two jobs degrades to a miss (a synchronous one-pair call), never to a wrong alignment.
+struct Proof {
+    int32_t K = 0, M = 0, L = 0, N = 0;
+    uint64_t chk = 0;
+    bool operator==(const Proof &o) const { return K == o.K && M == o.M && L == o.L && N == o.N && chk == o.chk; }
+};
+
 struct Entry {            // one aligned job: its edit script (packed 2 bits per op, see yama_b200.h)
     int32_t m_new = 0;
     const uint8_t *script = nullptr;   // into one of G.scriptChunks (a chunk per batch, never reallocated)
+    Proof proof;
 };
 
 struct Pending {          // a job shipped by a child, waiting for the GPU
     Key key;
+    Proof proof;
     int32_t K, M, L, N;
     size_t offA, offB, offLB, offRB;   // into G.arena
 };
@@ -103,7 +114,7 @@ struct Globals {
     std::unordered_map<Key, int, KeyHash> shipped;
     uchar **lastDummy = nullptr;
     int lastDummyRows = 0, lastDummyCols = 0;
-    uint64_t nTainted = 0, nShipped = 0, nHits = 0;
+    uint64_t nTainted = 0, nShipped = 0, nHits = 0, collisions = 0;
     // parent side
     std::vector<uint8_t> arena;
     std::vector<Pending> pending;
@@ -195,7 +206,47 @@ Key key_of(int K, int M, int L, int N, const uint8_t *A, const uint8_t *B, const
     h.bytes(B, (size_t)L * N);
     h.bytes(LB, (size_t)(M + 1) * sizeof(int));
     h.bytes(RB, (size_t)(M + 1) * sizeof(int));
+    // test hook: a deliberately weak key (dimensions only) makes same-shape jobs collide, so that the Proof check is
+    // what keeps the output right (tests/test_dropin_cpu.py)
+    static const bool weak = getenv("YB_DROPIN_WEAK_KEY") != nullptr;
+    if (weak) return Key{((uint64_t)(uint32_t)K << 32) | (uint32_t)L, 0x77ull};
     return h.done();
+}
+
+// the second digest (see Proof): bitwise CRC-32C tables, nothing shared with Hasher
+uint32_t g_crcTab[8][256];
+void crc_init() {
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82f63b78u & (0u - (c & 1u)));
+        g_crcTab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+        for (int t = 1; t < 8; ++t) g_crcTab[t][i] = (g_crcTab[t - 1][i] >> 8) ^ g_crcTab[0][g_crcTab[t - 1][i] & 0xffu];
+}
+uint32_t crc32c(uint32_t crc, const void *p, size_t n) {
+    const uint8_t *s = static_cast<const uint8_t *>(p);
+    crc = ~crc;
+    while (n >= 8) {                                   // slicing-by-8
+        uint64_t w;
+        memcpy(&w, s, 8);
+        w ^= crc;
+        crc = g_crcTab[7][w & 0xff] ^ g_crcTab[6][(w >> 8) & 0xff] ^ g_crcTab[5][(w >> 16) & 0xff] ^ g_crcTab[4][(w >> 24) & 0xff] ^
+              g_crcTab[3][(w >> 32) & 0xff] ^ g_crcTab[2][(w >> 40) & 0xff] ^ g_crcTab[1][(w >> 48) & 0xff] ^ g_crcTab[0][w >> 56];
+        s += 8; n -= 8;
+    }
+    while (n--) crc = (crc >> 8) ^ g_crcTab[0][(crc ^ *s++) & 0xffu];
+    return ~crc;
+}
+Proof proof_of(int K, int M, int L, int N, const uint8_t *A, const uint8_t *B, const int *LB, const int *RB) {
+    static const bool once = (crc_init(), true);
+    (void)once;
+    Proof p;
+    p.K = K; p.M = M; p.L = L; p.N = N;
+    const uint32_t text = crc32c(crc32c(0x59414d41u, A, (size_t)K * M), B, (size_t)L * N);
+    const uint32_t band = crc32c(crc32c(0x42414e44u, LB, (size_t)(M + 1) * sizeof(int)), RB, (size_t)(M + 1) * sizeof(int));
+    p.chk = ((uint64_t)text << 32) | band;
+    return p;
 }
 
 // score tables as the child saw them when it shipped its first job (the parent has not run the tool's
@@ -277,9 +328,8 @@ void remote_configure() {
     if (!e || !*e || !strcmp(e, "0") || !strcmp(e, "off")) return;
     R.enabled = true;
     if (!strcmp(e, "auto") || !strcmp(e, "1")) {
-        char b[128];
-        snprintf(b, sizeof b, "/tmp/yama_b200-%u.sock", (unsigned)getuid());
-        R.path = b;
+        R.path = ybwire::default_socket();
+        if (R.path.empty()) fatalf("yama_b200: YB_SERVER=auto needs $XDG_RUNTIME_DIR or a private /tmp/yama_b200-<uid>; name a socket path instead");
     } else R.path = e;
 }
 
@@ -291,6 +341,7 @@ int remote_try_connect() {
     int fd = socket(AF_UNIX, SOCK_STREAM, 0);
     if (fd < 0) return -1;
     if (connect(fd, reinterpret_cast<sockaddr *>(&addr), sizeof addr) != 0) { close(fd); return -1; }
+    if (!ybwire::peer_is_me(fd)) { close(fd); fatalf("yama_b200: the server on %s belongs to another user", R.path.c_str()); }
     return fd;
 }
 
@@ -311,9 +362,9 @@ void remote_spawn() {
     if (pid != 0) { if (pid > 0) { int st; while (waitpid(pid, &st, 0) < 0 && errno == EINTR) {} } return; }
     if (fork() != 0) _exit(0);                    // grandchild: not ours to wait for
     setsid();
-    char log[128];
-    snprintf(log, sizeof log, "/tmp/yama_b200d-%u.log", (unsigned)getuid());
-    int nul = open("/dev/null", O_RDWR), lg = open(log, O_WRONLY | O_CREAT | O_APPEND, 0600);
+    const std::string dir = ybwire::private_dir();
+    const std::string log = dir.empty() ? std::string("/dev/null") : dir + "/yama_b200d.log";
+    int nul = open("/dev/null", O_RDWR), lg = open(log.c_str(), O_WRONLY | O_CREAT | O_APPEND | O_NOFOLLOW, 0600);
     if (nul >= 0) { dup2(nul, 0); dup2(nul, 1); }
     if (lg >= 0) dup2(lg, 2); else if (nul >= 0) dup2(nul, 2);
     for (int fd = 3; fd < 256; ++fd) close(fd);
@@ -441,6 +492,7 @@ void emit(const yb_job &job, int m_new, const uint8_t *script, uchar ***OAL, int
     r.script = script;
     if (yb_assemble(&job, &r, al[1]) != YB_OK)
         fatalf("new_align: edit script does not consume both alignments (M=%d, N=%d, M_new=%d)", job.M, job.N, m_new);
+    G.lastDummy = nullptr;          // a real alignment: its address may be one a freed placeholder had
     *OAL = al;
     *OM = m_new;
 }
@@ -479,18 +531,18 @@ void put(const void *p, size_t n) {
     G.wbuf.insert(G.wbuf.end(), s, s + n);
     if (G.wbuf.size() > (1u << 20)) flush_pipe();
 }
-struct WireHdr { uint32_t magic; int32_t K, M, L, N; Key key; uint64_t call; };   // call: the child's yama() call index
+struct WireHdr { uint32_t magic; int32_t K, M, L, N; Key key; uint64_t call; uint64_t chk; };   // call: the child's yama() call index; chk: Proof::chk
 struct WireEnd { uint32_t magic; uint32_t pad; uint64_t tainted, shipped, hits; };
 constexpr uint32_t MAGIC_JOB = 0x4a4f4231u, MAGIC_END = 0x454e4431u, MAGIC_SCORES = 0x53434f31u;
 
-void ship(const Key &k, const yb_job &j) {
+void ship(const Key &k, const Proof &pr, const yb_job &j) {
     if (G.nShipped == 0) {
         put(&MAGIC_SCORES, 4);
         for (int c = 0; c < 128; ++c) put(ss[c], 128 * sizeof(int));
         put(gop, 16 * sizeof(int));
         put(&gap_extend, sizeof(int));
     }
-    WireHdr h{MAGIC_JOB, j.K, j.M, j.L, j.N, k, G.calls};
+    WireHdr h{MAGIC_JOB, j.K, j.M, j.L, j.N, k, G.calls, pr.chk};
     put(&h, sizeof h);
     put(j.A, (size_t)j.K * j.M);
     put(j.B, (size_t)j.L * j.N);
@@ -560,6 +612,7 @@ bool drain_child(int fd, WireEnd &end) {
         if (!read_full(fd, reinterpret_cast<uint8_t *>(&h) + 4, sizeof h - 4)) return false;
         Pending p;
         p.key = h.key; p.K = h.K; p.M = h.M; p.L = h.L; p.N = h.N;
+        p.proof.K = h.K; p.proof.M = h.M; p.proof.L = h.L; p.proof.N = h.N; p.proof.chk = h.chk;
         auto grab = [&](size_t bytes, size_t &off) {
             off = (G.arena.size() + 15) & ~(size_t)15;
             G.arena.resize(off + bytes);
@@ -619,6 +672,7 @@ void align_pending() {
         memcpy(chunk.data() + off, res[i].script, len);
         entries[i].m_new = res[i].m_new;
         entries[i].script = chunk.data() + off;
+        entries[i].proof = G.pending[i].proof;
         off += len;
     }
     backend.unlock();
@@ -711,12 +765,14 @@ constexpr uint32_t MAGIC_TABLE = 0x54424c31u;
     for (uint64_t i = 0; i < n; ++i) {
         Key k;
         int32_t m_new;
-        if (!read_full(ctl_r, &k, sizeof k) || !read_full(ctl_r, &m_new, 4)) _exit(0);
+        Proof pr;
+        if (!read_full(ctl_r, &k, sizeof k) || !read_full(ctl_r, &pr, sizeof pr) || !read_full(ctl_r, &m_new, 4)) _exit(0);
         const size_t len = (size_t)(m_new + 3) / 4;
         if (off + len > bytes || !read_full(ctl_r, base + off, len)) _exit(0);
         Entry e;
         e.m_new = m_new;
         e.script = base + off;
+        e.proof = pr;
         off += len;
         G.table.emplace(k, e);
     }
@@ -732,7 +788,7 @@ bool send_table(int fd) {
     bool ok = write_full(fd, &MAGIC_TABLE, 4) && write_full(fd, &n, 8) && write_full(fd, g_wireScores.data(), g_wireScores.size() * 4) &&
               write_full(fd, &bytes, 8);
     for (auto it = G.table.begin(); ok && it != G.table.end(); ++it)
-        ok = write_full(fd, &it->first, sizeof(Key)) && write_full(fd, &it->second.m_new, 4) &&
+        ok = write_full(fd, &it->first, sizeof(Key)) && write_full(fd, &it->second.proof, sizeof(Proof)) && write_full(fd, &it->second.m_new, 4) &&
              write_full(fd, it->second.script, (size_t)(it->second.m_new + 3) / 4);
     return ok;
 }
@@ -844,6 +900,10 @@ extern "C" {
 // made the real pass 1.7x slower than the same pass in a thread-free process.  Only one thread ever runs host
 // code, so its streams need no locking.
 FILE *yb_host_fopen(const char *path, const char *mode) {
+    // A speculative pass must never touch the tool's real outputs: multiz.c:242-243 opens out1/out2 with "w", which
+    // would truncate what the real pass (running beside it in streamed mode) has already written.  Its output goes
+    // nowhere anyway (mafWrite is skipped, stdout is /dev/null).
+    if (G.mode == RECORD && mode && strpbrk(mode, "wa+")) path = "/dev/null";
     FILE *f = fopen(path, mode);
     if (f) __fsetlocking(f, FSETLOCKING_BYCALLER);
     return f;
@@ -926,11 +986,18 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
     if (G.mode == DIRECT) { run_direct(job, OAL, OM); return; }
 
     const Key key = key_of(K, M, L, N, job.A, job.B, LB, RB);
+    const Proof proof = proof_of(K, M, L, N, job.A, job.B, LB, RB);
+    bool collided = false;
     {
         std::unique_lock<std::mutex> lk(S.mu, std::defer_lock);
         if (S.active) lk.lock();                // (only the streamed real pass shares the table with another thread)
         for (;;) {
             auto it = G.table.find(key);
+            if (it != G.table.end() && !(it->second.proof == proof)) {       // same key, another job: never trust it
+                collided = true;
+                ++G.collisions;
+                break;
+            }
             if (it != G.table.end()) {
                 const Entry e = it->second;
                 if (lk.owns_lock()) lk.unlock();
@@ -950,7 +1017,7 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
         }
     }
     if (G.mode == RECORD) {
-        if (G.shipped.emplace(key, 1).second) { ship(key, job); ++G.nShipped; }
+        if (!collided && G.shipped.emplace(key, 1).second) { ship(key, proof, job); ++G.nShipped; }
         emit_dummy(job, OAL, OM);
         return;
     }
@@ -987,8 +1054,18 @@ int main(int argc, char **argv) {
     G.stats = getenv("YB_DROPIN_STATS") != nullptr;
     G.debug = getenv("YB_DROPIN_DEBUG") != nullptr;
     const char *m = getenv("YB_DROPIN");
+    // Record/replay runs the tool's main() more than once, so its inputs must be re-readable.  The reference also
+    // takes /dev/stdin (maf.c:343), FIFOs and /dev/fd/N: with such an input the tool runs once, one pair per launch.
+    bool rereadable = true;
+    for (int i = 1, files = 0; i < argc && files < 2; ++i) {
+        if (argv[i][0] && argv[i][1] == '=') continue;              // R= M= L= S= ... flags (multiz.c:205, multic.c:290)
+        ++files;                                                    // file1 file2 are the first two positional arguments
+        struct stat sb;
+        if (stat(argv[i], &sb) == 0 && !S_ISREG(sb.st_mode)) rereadable = false;
+    }
+    if (!rereadable && G.stats) fprintf(stderr, "yama_b200: an input is not a regular file: one pair per launch (YB_DROPIN=direct)\n");
     int rc;
-    if (m && strcmp(m, "direct") == 0) {
+    if ((m && strcmp(m, "direct") == 0) || !rereadable) {
         G.mode = DIRECT;
         rc = ref_tool_main(argc, argv);
     } else if ((m && strcmp(m, "stream") == 0) || (R.enabled && !(m && strcmp(m, "batch") == 0))) {

@@ -52,12 +52,6 @@ bool write_full(int fd, const void *src, size_t n) {
     return true;
 }
 
-std::string default_socket() {
-    char b[128];
-    snprintf(b, sizeof b, "/tmp/yama_b200-%u.sock", (unsigned)getuid());
-    return b;
-}
-
 struct Server {
     yb_ctx *ctx = nullptr;
     std::vector<int32_t> scores;          // the tables the context currently holds
@@ -100,7 +94,8 @@ struct Server {
             const Job &w = wjobs[i];
             const uint64_t a = (uint64_t)(w.K > 0 ? w.K : 0) * (uint64_t)(w.M > 0 ? w.M : 0), b = (uint64_t)(w.L > 0 ? w.L : 0) * (uint64_t)(w.N > 0 ? w.N : 0);
             const uint64_t band = ((uint64_t)(w.M > 0 ? w.M : 0) + 1) * 4;
-            if (w.offA + a > rq.arenaBytes || w.offB + b > rq.arenaBytes || w.offLB + band > rq.arenaBytes || w.offRB + band > rq.arenaBytes ||
+            auto inside = [&](uint64_t off, uint64_t len) { return off <= rq.arenaBytes && len <= rq.arenaBytes - off; };   // (no wrap)
+            if (!inside(w.offA, a) || !inside(w.offB, b) || !inside(w.offLB, band) || !inside(w.offRB, band) ||
                 (w.offLB & 3) || (w.offRB & 3)) { ok = false; break; }
             jobs[i].K = w.K; jobs[i].M = w.M; jobs[i].L = w.L; jobs[i].N = w.N;
             jobs[i].A = arena.data() + w.offA; jobs[i].B = arena.data() + w.offB;
@@ -183,6 +178,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "--idle") && i + 1 < argc) idle_s = atoi(argv[++i]);
         else { fprintf(stderr, "usage: yama_b200d [--socket PATH] [--idle SECONDS]\n"); return 2; }
     }
+    if (path.empty()) { fprintf(stderr, "yama_b200d: no private directory for the default socket; give --socket PATH\n"); return 2; }
     sockaddr_un addr{};
     addr.sun_family = AF_UNIX;
     if (path.size() >= sizeof addr.sun_path) { fprintf(stderr, "yama_b200d: socket path too long\n"); return 2; }
@@ -196,7 +192,7 @@ int main(int argc, char **argv) {
     // clients found nobody at once) leaves, and its client finds the first
     {
         const std::string lock = path + ".lock";
-        int lf = open(lock.c_str(), O_CREAT | O_RDWR, 0600);
+        int lf = open(lock.c_str(), O_CREAT | O_RDWR | O_NOFOLLOW | O_CLOEXEC, 0600);
         if (lf < 0 || flock(lf, LOCK_EX | LOCK_NB) != 0) return 0;      // (kept open, hence locked, for our lifetime)
     }
     signal(SIGPIPE, SIG_IGN);
@@ -229,6 +225,7 @@ int main(int argc, char **argv) {
         if (r == 0) { if (clients.empty()) break; else continue; }      // idle with nobody connected: leave
         if (fds[0].revents & POLLIN) {
             int fd = accept(ls, nullptr, nullptr);
+            if (fd >= 0 && !peer_is_me(fd)) { close(fd); fd = -1; }          // only this user's processes are served
             if (fd >= 0) clients.push_back(Client{fd, false, {}});
         }
         for (size_t k = 1; k < fds.size(); ++k) {

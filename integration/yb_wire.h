@@ -12,6 +12,13 @@
 //   (close)
 #pragma once
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace ybwire {
 
@@ -35,5 +42,30 @@ struct BatchResp {
 struct Res { int32_t status, m_new; uint64_t scriptOff; };                 // scriptOff into the script bytes that follow
 struct ScoreReq { uint32_t magic; int32_t nrows, text_size, start, size, pad; };
 struct ScoreResp { uint32_t magic; int32_t rc; double score; uint32_t errLen, pad; };
+
+// Where the default socket, its lock and the server log live: a directory only this user can enter --
+// $XDG_RUNTIME_DIR when it is one, else /tmp/yama_b200-<uid> (created 0700; refused if it is a symlink, somebody
+// else's, or open to others).  Empty on failure: the caller then needs an explicit socket path.
+inline std::string private_dir() {
+    auto mine = [](const char *d) {
+        struct stat sb;
+        return lstat(d, &sb) == 0 && S_ISDIR(sb.st_mode) && sb.st_uid == getuid() && (sb.st_mode & 077) == 0;
+    };
+    if (const char *x = getenv("XDG_RUNTIME_DIR")) if (*x && mine(x)) return x;
+    char b[128];
+    snprintf(b, sizeof b, "/tmp/yama_b200-%u", (unsigned)getuid());
+    mkdir(b, 0700);                                  // (fails if it exists: judged by lstat either way)
+    return mine(b) ? std::string(b) : std::string();
+}
+inline std::string default_socket() {
+    const std::string d = private_dir();
+    return d.empty() ? std::string() : d + "/yama_b200.sock";
+}
+// the process at the other end of a connected unix socket runs as this user
+inline bool peer_is_me(int fd) {
+    struct ucred cr;
+    socklen_t len = sizeof cr;
+    return getsockopt(fd, SOL_SOCKET, SO_PEERCRED, &cr, &len) == 0 && cr.uid == getuid();
+}
 
 }  // namespace ybwire

@@ -100,3 +100,78 @@ def test_roast_driver_runs_the_dropin(tmp_path):
     want = run_roast(REF_MULTIZ, a, tree)
     got = run_roast(SHIM_MULTIZ, b, tree)
     assert len(want) > 10_000 and got == want
+
+
+def _drop_leading_blocks(src, dst, keep_from):
+    """Copy a MAF, leaving out the blocks before block number `keep_from` (header and trailer kept)."""
+    text = open(src, "rb").read()
+    head, *blocks = text.split(b"\na ")
+    tail = b""
+    if blocks and b"##eof" in blocks[-1]:
+        blocks[-1], tail = blocks[-1].split(b"##eof", 1)
+        tail = b"##eof" + tail
+    open(dst, "wb").write(head + b"".join(b"\na " + b for b in blocks[keep_from:]) + tail)
+    return len(blocks)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin/multiz not built")
+@pytest.mark.parametrize("v", [1, 0])
+def test_speculative_passes_never_touch_the_output_files(tmp_path, v):
+    """multiz opens out1/out2 with "w" (multiz.c:242-243).  A speculative pass that did the same would truncate what
+    the real pass -- running beside it in streamed mode -- has already flushed: file1 here carries hundreds of KB of
+    blocks before file2's first block, so out1 is far beyond one stdio buffer when the second speculative pass (v=0)
+    starts.  Every mode must give the reference's bytes."""
+    import shutil
+    from tools.mafsynth import make_dataset
+    from dropin_util import run_tool
+    da = str(tmp_path / "ref")
+    make_dataset(da, ref_len=400_000, n_species=2, seed=21)
+    n = _drop_leading_blocks(os.path.join(da, "ref.sp2.maf"), os.path.join(da, "late.maf"), keep_from=250)
+    assert n > 300
+    argv = ["ref.sp1.maf", "late.maf", str(v), "o1", "o2"]
+    rc, want, _ = run_tool(REF_MULTIZ, argv, da)
+    assert rc == 0
+    want1, want2 = (open(os.path.join(da, f), "rb").read() for f in ("o1", "o2"))
+    assert len(want1) > 200_000
+    for mode in ("stream", "batch", "direct"):
+        db = str(tmp_path / mode)
+        shutil.copytree(da, db)
+        os.remove(os.path.join(db, "o1")); os.remove(os.path.join(db, "o2"))
+        rc, out, err = run_tool(SHIM_MULTIZ, argv, db, {"YB_DROPIN": mode})
+        assert rc == 0, err.decode()[-300:]
+        assert out == want, mode
+        assert open(os.path.join(db, "o1"), "rb").read() == want1, mode
+        assert open(os.path.join(db, "o2"), "rb").read() == want2, mode
+
+
+def test_inputs_that_cannot_be_read_twice(tmp_path):
+    """The reference reads /dev/stdin (maf.c:343) and FIFOs; record/replay would run main() twice over them.  Such an
+    invocation runs once, one pair per launch, and still gives the reference's bytes."""
+    import shutil
+    import subprocess
+    from dropin_util import GOLD_MAF
+    for f in ("ref.sp1.maf", "ref.sp2.maf"):
+        shutil.copy(os.path.join(GOLD_MAF, f), tmp_path)
+    want = open(os.path.join(GOLD_MAF, "v1.stdout"), "rb").read()
+    strip = lambda b: b"".join(l for l in b.splitlines(keepends=True) if not l.startswith(b"#"))
+    with open(tmp_path / "ref.sp1.maf", "rb") as f:
+        p = subprocess.run([SHIM_MULTIZ, "/dev/stdin", "ref.sp2.maf", "1", "o1", "o2"], cwd=tmp_path, stdin=f,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert p.returncode == 0, p.stderr.decode()[-300:]
+    assert strip(p.stdout) == strip(want)
+    fifo = tmp_path / "in.fifo"
+    os.mkfifo(fifo)
+    feeder = subprocess.Popen(["sh", "-c", f"cat ref.sp2.maf > {fifo}"], cwd=tmp_path)
+    p = subprocess.run([SHIM_MULTIZ, "R=30", "ref.sp1.maf", str(fifo), "1", "o1", "o2"], cwd=tmp_path,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    feeder.wait(timeout=60)
+    assert p.returncode == 0, p.stderr.decode()[-300:]
+    assert strip(p.stdout) == strip(want)
+
+
+@pytest.mark.parametrize("mode", ["batch", "stream"])
+def test_replay_hits_are_verified(tmp_path, mode):
+    """A replay-table hit is trusted only if the job's dimensions and a second, independent digest match too.  With the
+    key deliberately weakened to (K, L) every job collides with the first one of its depth: all but one become misses,
+    aligned one at a time, and the output is still the reference's."""
+    check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_DROPIN": mode, "YB_DROPIN_WEAK_KEY": "1"})

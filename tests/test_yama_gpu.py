@@ -294,3 +294,51 @@ def test_fill_variant_without_existence_multipliers_is_exact(oracle):
     finally:
         on.close()
         off.close()
+
+
+def _oracle_many(oracle, problems, threads=8):
+    """The oracle on several large pairs at once (ctypes releases the GIL: one host core per pair)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(lambda p: oracle.yama(*p, want_tback=False), problems))
+
+
+def test_cfg5_shape_full_size(yama_ctx, oracle):
+    """BASELINE.json configs[4] at its stated shape: K=99,L=1 and K=90,L=10 blocks of M ~ 10^4 columns, R=300
+    (~6 M cells per pair, band rows of ~601 cells -> the CTA-per-pair kernels with existence multipliers and the
+    warp-per-path traceback).  Column scores reach 9*10^4, final scores 10^8..10^9 -- the upper end of the int32
+    range the reference computes in (mz_yama.c:29 MININT = INT_MIN/2).  Two pairs of each kind against the oracle:
+    final C/D/I, the whole edit script, the assembled columns."""
+    sb = SynthBatch(505, [99, 90, 99, 90], [1, 10, 1, 10], [10000, 10000, 9473, 10240], R=300)
+    probs = [tuple(np.array(x) for x in sb.problem(i)) for i in range(sb.n)]
+    # the largest scores the shape allows: 90 x 10 identical residues per column, 91 each -> C(M,N) = 8.19e8 of 2^30
+    M = 10000
+    LB, RB = oracle.smooth(np.concatenate([[0], np.arange(1, M + 1)]), np.concatenate([[M], np.arange(1, M + 1)]), M, M, 300)
+    probs.append((np.full((M, 90), ord("A"), np.uint8), np.full((M, 10), ord("A"), np.uint8), LB, RB))
+    jobs, keep = yama_ctx.make_jobs(probs)
+    res, st = yama_ctx.run_batch(jobs)
+    outs = _oracle_many(oracle, probs)
+    assert int(outs[-1]["cdi"][0]) == 91 * 900 * M
+    for i, o in enumerate(outs):
+        r = res[i]
+        assert r["status"] == 0, i
+        assert int(r["cells"]) == o["cells"] and o["cells"] > 5_000_000, i
+        assert (int(r["C"]), int(r["D"]), int(r["I"])) == tuple(int(x) for x in o["cdi"]), i
+        assert int(r["m_new"]) == o["m_new"], i
+        assert np.array_equal(yama_ctx.script_of(r), o["script"]), i
+        assert np.array_equal(yama_ctx.assemble(jobs[i], r), o["al"]), i
+
+
+def test_cfg3_depth64_r100(yama_ctx, oracle):
+    """BASELINE.json configs[2] at its deepest point: profile depth 64 split K ~ L (32 x 32) and K = 63, L = 1,
+    M = 500, band R = 100 (201-cell rows: the 512-entry ring bins, CTA-per-pair for M >= 192), plus R = 30."""
+    for R in (100, 30):
+        sb = SynthBatch(640 + R, [32, 63, 32, 16, 31], [32, 1, 32, 16, 1], [500, 500, 191, 500, 500], R=R)
+        probs = [sb.problem(i) for i in range(sb.n)]
+        res, _ = yama_ctx.run_batch(sb.jobs)
+        for i, o in enumerate(_oracle_many(oracle, probs)):
+            r = res[i]
+            assert r["status"] == 0, (R, i)
+            assert (int(r["C"]), int(r["D"]), int(r["I"])) == tuple(int(x) for x in o["cdi"]), (R, i)
+            assert np.array_equal(yama_ctx.script_of(r), o["script"]), (R, i)
+            assert np.array_equal(yama_ctx.assemble(sb.jobs[i], r), o["al"]), (R, i)
