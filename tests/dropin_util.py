@@ -157,3 +157,29 @@ def make_roast_dataset(workdir, ref_len, n_species, seed):
     for p in make_dataset(workdir, ref_len=ref_len, n_species=n_species, seed=seed):
         sp = os.path.basename(p).split(".")[1]
         os.replace(p, os.path.join(workdir, f"ref.{sp}.sing.maf"))
+
+
+def run_tba(multiz_tool, workdir, tree, files, env=None, extra=()):
+    """The reference's own tba driver (oracle/_ref/bin/tba, tba.c:114-276: per cross-subtree pair it shells out to
+    maf_project, pair2tb, `multiz ... 1 ...`, get_covered, all found on PATH) with `multiz_tool` as the multiz on PATH.
+    Returns the output MAF without '#' lines (they embed getpid() through the temp-file names, tba.c:299-302)."""
+    refbin = os.path.dirname(REF_MULTIZ)
+    bindir = os.path.join(workdir, "_bin")
+    os.makedirs(bindir, exist_ok=True)
+    for name, src in (("multiz", multiz_tool), ("maf_project", os.path.join(refbin, "maf_project")),
+                      ("pair2tb", os.path.join(refbin, "pair2tb")), ("get_covered", os.path.join(refbin, "get_covered")),
+                      ("tba", os.path.join(refbin, "tba"))):
+        dst = os.path.join(bindir, name)
+        if os.path.lexists(dst):
+            os.remove(dst)
+        os.symlink(src, dst)
+    e = dict(os.environ)
+    e.update(env or {})
+    e["PATH"] = bindir + os.pathsep + e.get("PATH", "")
+    out = os.path.join(workdir, "tba_out.maf")
+    if os.path.exists(out):
+        os.remove(out)
+    p = subprocess.run([os.path.join(bindir, "tba")] + list(extra) + [tree] + list(files) + [out], cwd=workdir, env=e,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800)
+    assert p.returncode == 0, p.stderr.decode()[-800:]
+    return b"".join(l for l in open(out, "rb").read().splitlines(keepends=True) if not l.startswith(b"#"))

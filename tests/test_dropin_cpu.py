@@ -175,3 +175,21 @@ def test_replay_hits_are_verified(tmp_path, mode):
     key deliberately weakened to (K, L) every job collides with the first one of its depth: all but one become misses,
     aligned one at a time, and the output is still the reference's."""
     check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_DROPIN": mode, "YB_DROPIN_WEAK_KEY": "1"})
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin not built")
+def test_tba_driver_runs_the_dropin(tmp_path):
+    """BASELINE configs[3], host logic: the reference's tba (tba.c:114-276) over a 4-species tree -- maf_project,
+    pair2tb, `multiz ... 1 out1 out2`, get_covered per cross-subtree pair -- with the drop-in as the multiz on PATH
+    gives the reference's threaded blockset (apart from '#' provenance lines), also with E=ref."""
+    import shutil
+    from dropin_util import run_tba
+    from tools.mafsynth import make_tba_dataset
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    files = make_tba_dataset(a, ["ref", "sp1", "sp2", "sp3"], ref_len=25_000, seed=12)
+    shutil.copytree(a, b)
+    tree = "((ref sp1) (sp2 sp3))"
+    for extra in ((), ("E=ref",)):
+        want = run_tba(REF_MULTIZ, a, tree, files, extra=extra)
+        got = run_tba(SHIM_MULTIZ, b, tree, files, extra=extra)
+        assert len(want) > 50_000 and got == want, extra

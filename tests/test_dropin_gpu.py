@@ -94,3 +94,27 @@ def test_roast_five_species_tree(tmp_path):
     want = run_roast(REF_MULTIZ, a, tree)
     got = run_roast(GPU_MULTIZ, b, tree)
     assert len(want) > 100_000 and got == want
+
+
+def test_tba_eight_species_tree(tmp_path):
+    """configs[3] (tba arm): the reference's tba driver (tba.c:114-276) over an 8-species tree on a 300 kb ancestor --
+    28 pairwise files, FASTA per species, maf_project / pair2tb / get_covered from the reference and the GPU multiz on
+    PATH (always v=1, with out1/out2 files).  The threaded blockset must equal the one the reference's multiz gives,
+    apart from '#' lines (they carry the temp-file names, which embed getpid())."""
+    import shutil
+    from dropin_util import run_tba
+    from tools.mafsynth import make_tba_dataset
+    _need(GPU_MULTIZ); _need(REF_MULTIZ)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    files = make_tba_dataset(a, ["ref"] + [f"sp{i}" for i in range(1, 8)], ref_len=300_000, seed=3)
+    shutil.copytree(a, b)
+    tree = "(((ref sp1) (sp2 sp3)) ((sp4 sp5) (sp6 sp7)))"
+    want = run_tba(REF_MULTIZ, a, tree, files)
+    got = run_tba(GPU_MULTIZ, b, tree, files)
+    assert len(want) > 3_000_000 and got == want
+    srv = server_env(tmp_path, GPU_SERVER, idle_s=60)
+    try:
+        got2 = run_tba(GPU_MULTIZ, b, tree, files, env=srv)       # the same pipeline behind the resident server
+    finally:
+        stop_server(srv)
+    assert got2 == want

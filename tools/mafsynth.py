@@ -121,6 +121,52 @@ def make_dataset(out, ref_len=100_000, n_species=2, seed=1, sub=0.10, indel=0.01
     return paths
 
 
+def species_sequence(sp: Species):
+    """The species' own sequence (what its FASTA file holds): its bases in ancestor order, insertions after their site."""
+    ins_bases = BASES[np.random.default_rng(sp.rng_seed).integers(0, 4, size=int(sp.ins.sum()))]
+    n = len(sp.base)
+    per = (sp.base != DASH).astype(np.int64) + sp.ins
+    off = np.concatenate([[0], np.cumsum(per)])
+    seq = np.zeros(int(off[-1]), np.uint8)
+    k = np.nonzero(sp.base != DASH)[0]
+    seq[off[k]] = sp.base[k]
+    s = np.nonzero(sp.ins)[0]
+    if len(s):
+        ln = sp.ins[s]
+        start = off[s] + (sp.base[s] != DASH)
+        pos = np.repeat(start - np.concatenate([[0], np.cumsum(ln)[:-1]]), ln) + np.arange(int(ln.sum()))
+        seq[pos] = ins_bases
+    del n
+    return seq
+
+
+def make_tba_dataset(out, names, ref_len=50_000, seed=1, sub=0.10, indel=0.01, blk=(200, 2000)):
+    """What the reference's `tba` wants in its working directory: for every ordered pair x < y of `names`
+    the single-coverage pairwise file x.y.sing.maf (top row x), plus a FASTA file named exactly as each species with the
+    header >name:chr:start:strand:srcSize (multi_util.c:311-322), which pair2tb reads to add the unaligned stretches."""
+    os.makedirs(out, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    anc = BASES[rng.integers(0, 4, size=ref_len)]
+    sp = {nm: Species(rng, anc, sub if i else sub / 2, indel if i else indel / 2) for i, nm in enumerate(names)}
+    for nm in names:
+        seq = species_sequence(sp[nm])
+        with open(os.path.join(out, nm), "w") as f:
+            f.write(f">{nm}:chr1:1:+:{len(seq)}\n")
+            txt = seq.tobytes().decode()
+            for i in range(0, len(txt), 60):
+                f.write(txt[i:i + 60] + "\n")
+    files = []
+    for i, x in enumerate(names):
+        for j, y in enumerate(names):
+            if i >= j:
+                continue
+            top, bot = pairwise_columns(sp[x], sp[y])
+            fn = f"{x}.{y}.sing.maf"
+            write_pairwise_maf(os.path.join(out, fn), f"{x}.chr1", f"{y}.chr1", top, bot, seed * 1000 + 37 * i + j, blk=blk)
+            files.append(fn)
+    return files
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
