@@ -178,7 +178,7 @@ constexpr int K1_THREADS = 128;
 
 __global__ void __launch_bounds__(K1_THREADS, 10)     // 48 registers: 10 CTAs per SM hide more of the load latency (0.97 -> 0.92 ms on cfg2)
 yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__restrict__ blob,
-                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int y16,
+                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int y16, int scale,
                   const __grid_constant__ ScoreConst c_sc) {
     const PairMeta pm = metas[blockIdx.x];
     const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
@@ -189,7 +189,9 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     RowRec *rows = rowPool + pm.rowBase;
     ColRec *cols = colPool + pm.colBase;
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
-    const int GE = c_sc.gap_ext;
+    // scale: 1, or 4 for the KEYED fill kernels (fill_body2), whose node values carry the tie-break priority in their
+    // low two bits: every weight that is ADDED to a node value is stored multiplied by it
+    const int GE = c_sc.gap_ext * scale;
 
     // ---- columns of B (c = 0..N) -------------------------------------------------------------
     for (int c = threadIdx.x; c <= N; c += K1_THREADS) {
@@ -233,7 +235,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
             //   D.x: ndA*ndB' + a10*dB'   D.y: a10*(ndB'+dB')   D.z: ndA*(ndB'+dB')   on bytes 2,3 of w2
             // The y candidates (from a D node) are never gated, so when K*gap_open fits 16 bits (y16) their weights are
             // stored already multiplied by -gap_open and K2 applies them with ONE dp2a on bytes 2,3.
-            const int nGO = -c_sc.gap_open;
+            const int nGO = -c_sc.gap_open * scale;             // (only the 16-bit y forms carry it)
             if (r > 1) {                                        // mz_yama.c:180-184, :218-221 (row>1)
                 rr.avXC = pack4(a00, a11, a01, a10);
                 rr.avYC = y16 ? pack16((int)dA * nGO, (int)a10 * nGO) : pack4(0, 0, dA, a10);
@@ -250,7 +252,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
                 int acc = 0;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) acc += n[k] * c_sc.S6[k][l];
-                w[l] = acc;
+                w[l] = acc * scale;
             }
             rr.w01 = pack16(w[0], w[1]); rr.w23 = pack16(w[2], w[3]); rr.w45 = pack16(w[4], w[5]);
         }
@@ -276,6 +278,12 @@ __device__ __forceinline__ void sts128(unsigned addr, int a, int b, int c, unsig
 __device__ __forceinline__ unsigned and_xor(unsigned a, unsigned b, unsigned c) {
     unsigned d;
     asm("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// (a & b) | c in one LOP3
+__device__ __forceinline__ unsigned and_or(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xea;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 __device__ __forceinline__ unsigned launder(unsigned x) {
@@ -323,7 +331,17 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
     const unsigned ringAddr = smem0 + grp * RING * 16;
     const unsigned boxAddr = smem0 + P * RING * 16 + grp * B * 32;
     const unsigned slotAddr = smem0 + P * RING * 16 + P * B * 32;
+    // Warp-sized wavefronts: the steps of the mailbox protocol are separated by __syncwarp().  ptxas proves the warp
+    // converged at every one of them (the only divergent region, the row switch, re-joins at its BSYNC before the barrier)
+    // and emits no instruction for it -- not even for bar.warp.sync with a mask it cannot see through -- so
+    // compute-sanitizer's racecheck sees no ordering.  -DYB_FORCE_WARPSYNC (the `make sanitize` build,
+    // profiles/r2_sanitizer.md) separates the steps with a named CTA barrier of 32 threads per warp instead, which is
+    // never elided: same protocol, visible to the tool.
+#ifdef YB_FORCE_WARPSYNC
+    auto group_sync = [&]() { if (G == 1) asm volatile("bar.sync %0, 32;" ::"r"(grp + 1) : "memory"); else __syncthreads(); };
+#else
     auto group_sync = [&]() { if (G == 1) __syncwarp(); else __syncthreads(); };
+#endif
     const int GO = gapOpen;
     const int nGO = -GO;
     const unsigned E_both = pack16(nGO, nGO);
@@ -512,12 +530,277 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 }
 
 // =================================================================================================
+// K2, bulk form: one warp per pair, bounded scores (the GATED = false conditions of fill_body), 16-bit weights.
+// Same wavefront and schedule as fill_body<RING,1,P,true,false>, rebuilt around what ncu showed of that kernel
+// (profiles/r1_fill_summary.md: 75 % issue slots, L1/shared data pipe 72 %, long-scoreboard stalls on the row records):
+//
+//  SHFL   (C,D,I) of the row above arrive by three warp shuffles from lane l-1's registers instead of a shared-memory
+//         mailbox (LDS.128 + STS.128 per lane and step: 8 crossbar cycles per warp step; three SHFL: 3).  Only lane 0
+//         reads and lane 31 writes the ring that carries a band row from one 32-row block to the next.  A lane that is
+//         not inside its row hands down MININT -- exactly the never-written dp[] entries of mz_yama.c:93-94 -- so a
+//         finished row needs no stale-record stores.
+//  ROWPF  a lane's NEXT row record is copied global -> shared (cp.async, a private 64-B slot per lane) while it walks
+//         its current row; the row switch reads it with four LDS.128 instead of four dependent global loads.
+//  KEYED  node values are carried as 4*value + p with p = 2 for a C node, 1 for an I node, 0 for a D node, and every
+//         weight is a multiple of 4.  A candidate inherits the p of the node it comes from, so ONE 3-way maximum
+//         decides value and tie-break together: 4x+2 > 4y and 4x+2 > 4z+1 iff x >= y and x >= z (from-C wins ties),
+//         4y > 4z+1 iff y > z (from-D beats from-I only strictly) -- the rule of mz_yama.c:138-154 -- and the low two
+//         bits of the maximum ARE the traceback pointer (2: from C, 0: from D, 1: from I): one funnel shift per node
+//         into the packed word instead of two compares and two predicated adds.  Needs 4*K*gap_open <= 32767 and
+//         real scores below 2^26 (host-checked per wave).
+// =================================================================================================
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// A KEYED node value back in the reference's units.  Values of nodes no alignment path reaches sit around the keyed
+// sentinel -2^30 = 4 * (-2^28): they are moved to where the reference has them, around MININT = -2^30 (the drift of such a
+// value away from its sentinel is kept: it is the reference's "MININT - penalty", mz_yama.c:93-94).
+template <bool KEYED>
+__device__ __forceinline__ int unkey(int v) {
+    if (!KEYED) return v;
+    const int u = v >> 2;
+    return v < -(1 << 29) ? u - 3 * (1 << 28) : u;
+}
+
+template <int RING, int P, bool KEYED, bool SHFL, bool ROWPF>
+__device__ __forceinline__ void
+fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
+           const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
+           const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, const int gapOpen, const int gapExt) {
+    constexpr int B = 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int SC = KEYED ? 4 : 1;                         // every weight is multiplied by SC
+    constexpr int PRC = KEYED ? 2 : 0, PRI = KEYED ? 1 : 0;   // low bits of a C / I node value (a D node carries 0)
+    constexpr int MIN_C = MININT | PRC, MIN_D = MININT, MIN_I = MININT | PRI;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [ P rings of RING records | P x 32 lanes x 2 mailbox records (not SHFL) | P x 32 row slots of 64 B (ROWPF) | pad ]
+    const int grp = (int)(threadIdx.x >> 5);
+    const int lane = (int)(threadIdx.x & 31);
+    const unsigned smem0 = (smem_u32(smem_raw) + RING * 16 - 1) & ~(unsigned)(RING * 16 - 1);
+    const unsigned ringAddr = smem0 + grp * RING * 16;
+    constexpr unsigned BOX_BYTES = SHFL ? 0u : (unsigned)(P * B * 32);
+    const unsigned boxAddr = smem0 + P * RING * 16 + grp * B * 32;
+    const unsigned rowSlot = smem0 + P * RING * 16 + BOX_BYTES + (unsigned)(grp * B + lane) * 64u;
+    const int nGO = -gapOpen * SC;
+    const unsigned keyMask = launder(~3u);                    // (in a register: LOP3 takes one immediate)
+    constexpr unsigned RMASK = (unsigned)(RING * 16 - 16);
+
+    // mailbox addressing of the non-SHFL form: as in fill_body
+    auto boxOf = [&](int l) { return boxAddr + 32u * l + (((unsigned)l >> 2) & 1u) * 16u; };
+    const unsigned rdBase = launder((lane == 0) ? ringAddr : boxOf(lane - 1));
+    const unsigned rdMask = (lane == 0) ? RMASK : 16u;
+    const unsigned wrBase = launder((lane == B - 1) ? ringAddr : boxOf(lane));
+    const unsigned wrMask = (lane == B - 1) ? RMASK : 16u;
+
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(queue, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= nPairs) break;
+        const int p = order[slot];
+        const PairMeta pm = metas[p];
+        const int M = pm.M;
+        const RowRec *rows = rowPool + pm.rowBase;
+        const ColRec *cols = colPool + pm.colBase;
+        unsigned char *tb = tbPool + __ldg(tbBase + p);
+        const unsigned nKGE_lo = launder((unsigned)(-(pm.K * gapExt * SC)) & 0xffffu);   // dp2a.hi weight of byte 2 (ndB)
+        const int KGE = pm.K * gapExt * SC;
+        const int nSteps = pm.nSteps;
+        const int N16 = pm.N * 16;
+        const int KnGO = pm.K * nGO;                        // I-node y / z charge per residue / per closing gap of B
+
+        // ---- row 0 (mz_yama.c:83-94) into the ring -------------------------------------------------------------
+        {
+            const int RB0 = rows[0].RB16 >> 4;
+            const int RB1 = rows[0].RBn;
+            int carry = 0;
+            for (int base = 0; base <= RB1; base += 32) {
+                int c = base + lane;
+                int nd = 0;
+                if (c >= 1 && c <= RB0) nd = (int)((__ldg(&cols[c].w0) >> 16) & 0xffu);
+                int inc = nd;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int o = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                unsigned a = and_xor((unsigned)c << 4, RMASK, ringAddr);
+                if (c <= RB0) {
+                    int I0 = -(carry + inc) * KGE + PRI;
+                    if (c == 0) sts128(a, PRC, 0, PRI, 0u);                    // (0,0): all three nodes are 0
+                    else sts128(a, MIN_C, MIN_D, I0, 0u);                      // only the I node exists in row 0
+                } else if (c <= RB1) {
+                    sts128(a, MIN_C, MIN_D, MIN_I, 0u);                        // stale dp[] entry, mz_yama.c:93-94
+                }
+                carry += __shfl_sync(FULL, inc, 31);
+            }
+        }
+
+        // ---- per-lane row state -----------------------------------------------------------------------------------
+        int r = lane + 1;
+        unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avXD = 0, avYD = 0, avZD = 0;
+        int gIrow = 0, gIz = 0;
+        unsigned w01 = 0, w23 = 0, w45 = 0;
+        // LBc16: the C node of (r,c) exists iff c >= LB[r] and c > LB[r-1], i.e. c16 > max(LB16 - 16, 16*LB[r-1]);
+        // LBst16: LB16 on the lane that feeds the ring, never reached on the others (one compare decides the ring store)
+        int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBc16 = 0x7fffffff, LBst16 = 0x7fffffff, c16 = 0;
+        auto unpack_row = [&](const uint4 &q0, const uint4 &q1, const uint4 &q2, const uint4 &q3, int t) {
+            avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
+            avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
+            w01 = q2.x; w23 = q2.y; w45 = q2.z; LB16 = (int)q2.w;
+            RB16 = (int)q3.x; LBc16 = max(LB16 - 16, (int)q3.y);
+            LBst16 = (lane == B - 1) ? LB16 : 0x7fffffff;
+            c16 = (t - (int)q3.z) * 16;
+            gIrow = r < M ? (KnGO & 0xffff) : 0;                    // mz_yama.c:123: no I-node gap-open on the last row
+            gIz = gIrow << 16;                                      // the z candidate's weight sits on byte 1 (b10)
+        };
+        auto prefetch_row = [&](int rr) {                           // row rr's record -> this lane's slot
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(rows + rr);
+            cp_async16(rowSlot, src); cp_async16(rowSlot + 16, src + 16);
+            cp_async16(rowSlot + 32, src + 32); cp_async16(rowSlot + 48, src + 48);
+            cp_async_commit();
+        };
+        if (r <= M) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
+            const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+            unpack_row(q0, q1, q2, q3, 0);
+            if (ROWPF && r + B <= M) prefetch_row(r + B);
+        }
+        unsigned acc = 0;
+        const size_t tbWord = (size_t)lane * 2;               // this lane's word inside an 8-step group (see tb_byte)
+        int Cl = MIN_C, Dl = MIN_D, Il = MIN_I;               // grid point (r, c-1)
+        int Cd = MIN_C, Dd = MIN_D, Id = MIN_I;               // grid point (r-1, c-1)
+        int oC = MIN_C, oD = MIN_D, oI = MIN_I;               // SHFL: what this lane hands down (its last cell, or MININT)
+        __syncwarp();
+
+        for (int t4 = 0; t4 < nSteps; t4 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // ---- grid point (r-1, c) ----------------------------------------------------------------------
+                int Cu, Du, Iu;
+                if (SHFL) {
+                    Cu = __shfl_up_sync(FULL, oC, 1); Du = __shfl_up_sync(FULL, oD, 1); Iu = __shfl_up_sync(FULL, oI, 1);
+                    if (lane == 0) {
+                        const uint4 up = lds128(and_xor((unsigned)c16, RMASK, ringAddr));
+                        Cu = (int)up.x; Du = (int)up.y; Iu = (int)up.z;
+                    }
+                } else {
+                    const uint4 up = lds128(and_xor((unsigned)c16, rdMask, rdBase));
+                    Cu = (int)up.x; Du = (int)up.y; Iu = (int)up.z;
+                }
+                {
+                    if (c16 > RB16) {
+                        // ---- this lane finished its row -----------------------------------------------------
+                        // the row below keeps reading us up to its own right bound: stale dp[] entries (mz_yama.c:93-94).
+                        // SHFL: an idle lane hands down MININT by itself; only the ring (lane 31) needs them written.
+                        if (lane == B - 1) {
+                            const int RBn = __ldg(reinterpret_cast<const int *>(rows + r) + 15);   // RowRec::RBn
+#pragma unroll 1
+                            for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
+                                sts128(and_xor((unsigned)cc << 4, RMASK, ringAddr), MIN_C, MIN_D, MIN_I, 0u);
+                        } else if (!SHFL) {
+                            sts128(wrBase, MIN_C, MIN_D, MIN_I, 0u);
+                            sts128(wrBase ^ 16u, MIN_C, MIN_D, MIN_I, 0u);
+                        }
+                        r += B;
+                        if (r <= M) {
+                            uint4 q0, q1, q2, q3;
+                            if (ROWPF) {
+                                cp_async_wait_all();
+                                q0 = lds128(rowSlot); q1 = lds128(rowSlot + 16); q2 = lds128(rowSlot + 32); q3 = lds128(rowSlot + 48);
+                            } else {
+                                const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
+                                q0 = __ldg(rp); q1 = __ldg(rp + 1); q2 = __ldg(rp + 2); q3 = __ldg(rp + 3);
+                            }
+                            unpack_row(q0, q1, q2, q3, t4 + u);
+                            if (ROWPF && r + B <= M) prefetch_row(r + B);      // (after the slot's words were consumed)
+                        } else {
+                            if (r - B == M) { outs[p].C = unkey<KEYED>(Cl); outs[p].D = unkey<KEYED>(Dl); outs[p].I = unkey<KEYED>(Il); }
+                            LB16 = 0x7fffffff; RB16 = 0x7fffffff; LBc16 = 0x7fffffff; LBst16 = 0x7fffffff;
+                        }
+                    }
+                }
+                const bool active = (c16 >= LB16);
+
+                // column record of column c; lanes outside their row read a clamped (valid) column and discard the result
+                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) +
+                                                                       (unsigned)__vimin_s32_relu(c16, N16)));
+                int vI, vC, vD;
+                const bool hasI = c16 > LB16, hasC = c16 > LBc16;
+                if (!KEYED) acc >>= 8;                       // make room for this cell's byte (bits 24..31)
+                // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
+                {
+                    int x = Cd + dp4a_uu(cw.w, avXC, 0) * nGO;
+                    int y = dp2a_hi_su(avYC, cw.w, Dd);
+                    int z = Id + dp4a_uu(cw.w, avZC, 0) * nGO;
+                    if (KEYED) {
+                        const int m = __vimax3_s32(x, y, z);
+                        acc = __funnelshift_r(acc, (unsigned)m, 2);
+                        vC = (int)and_or((unsigned)m, keyMask, (unsigned)PRC);
+                    } else vC = pick3<0>(x, y, z, hasC, acc);
+                    vC = dp2a_lo_su(w01, cw.y, vC);
+                    vC = dp2a_hi_su(w23, cw.y, vC);
+                    vC = dp2a_lo_su(w45, cw.z, vC);
+                }
+                vC = hasC ? vC : MIN_C;
+                // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
+                {
+                    int x = Cu + dp4a_uu(cw.z, avXD, 0) * nGO;
+                    int y = dp2a_hi_su(avYD, cw.z, Du);
+                    int z = Iu + dp4a_uu(cw.z, avZD, 0) * nGO;
+                    if (KEYED) {
+                        const int m = __vimax3_s32(x, y, z);
+                        acc = __funnelshift_r(acc, (unsigned)m, 2);
+                        vD = (m & ~3) - eD;
+                    } else vD = pick3<2>(x, y, z, true, acc) - eD;
+                }
+                if (SHFL) vD = active ? vD : MIN_D;
+                // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
+                {
+                    int x = Cl + dp4a_uu(cw.x, avXI, 0) * nGO;
+                    int y = dp2a_hi_su((unsigned)gIrow, cw.x, Dl);                  // K*ndB opens (mz_yama.c:131-134)
+                    int z = dp2a_lo_su((unsigned)gIz, cw.x, Il);                    // K*b10
+                    if (KEYED) {
+                        const int m = __vimax3_s32(x, y, z);
+                        acc = __funnelshift_r(acc, (unsigned)m, 4);                 // (bits 6,7 of the byte: don't care)
+                        vI = (int)and_or((unsigned)m, keyMask, (unsigned)PRI);
+                    } else vI = pick3<4>(x, y, z, hasI, acc);
+                    vI = dp2a_hi_su(nKGE_lo, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
+                }
+                vI = hasI ? vI : MIN_I;
+                if (SHFL) {
+                    if (c16 >= LBst16) sts128(and_xor((unsigned)c16, RMASK, ringAddr), vC, vD, vI, 0u);
+                    oC = vC; oD = vD; oI = vI;
+                } else if (active) {
+                    sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, 0u);
+                }
+                // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
+                if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * (2 * B) + tbWord + ((t4 >> 2) & 1)] = acc;
+                Cl = vC; Dl = vD; Il = vI;
+                Cd = Cu; Dd = Du; Id = Iu;
+                c16 += 16;
+                if (!SHFL) __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
 // K3: traceback (mz_yama.c:257-291), one thread per pair; threads of a warp get pairs of similar size
 // (the launch order is sorted by cell count).  The stored bytes are the reference's own, so a move is ONE
 // dependent byte load (>= 4 moves per 32-B sector, see tb_byte) plus branch-free integer work; the
 // band is not consulted.  Ops leave as 2-bit codes, 16 per 32-bit store, in the reference's (reversed)
 // order: op i sits in bits 2*(i&15) of word i>>4.
 // =================================================================================================
+// What a 2-bit traceback field means, as a 4 x 2-bit table of node codes (FLAG_C 0, FLAG_I 1, FLAG_D 2; 3 = invalid):
+//   fill_body:         e = notC | gt<<1        0,2 -> C   1 -> I   3 -> D
+//   fill_body2 KEYED:  low bits of the maximum  2 -> C     1 -> I   0 -> D   (3 never occurs)
+constexpr unsigned TB_DECODE_FLAGS = 0x84u, TB_DECODE_KEYED = 0xC6u;
 constexpr int TB_LONG = 2048;       // paths of at least this many moves get a warp of their own (the warp-per-path
                                     // kernel is bound by instruction issue, so only where the pointer chase is critical)
 
@@ -525,7 +808,7 @@ __global__ void __launch_bounds__(128)
 yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                     const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
                     const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
-                    PairOut *__restrict__ outs, int tbLong) {
+                    PairOut *__restrict__ outs, int tbLong, unsigned decode) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nPairs) return;
     const int p = order[idx];
@@ -576,7 +859,7 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
         const int shift = node == FLAG_I ? 4 : (node == FLAG_D ? 2 : 0);
         r -= (node != FLAG_I);
         c -= (node != FLAG_D);
-        node = (int)((0x84u >> (2u * ((st >> shift) & 3u))) & 3u);      // e = notC | gt<<1  ->  0,2: C   1: I   3: D
+        node = (int)((decode >> (2u * ((st >> shift) & 3u))) & 3u);     // TB_DECODE_FLAGS / TB_DECODE_KEYED
     }
     if (n & 15) script[n >> 4] = accw;
     o.m_new = n;
@@ -594,7 +877,7 @@ __global__ void __launch_bounds__(128)
 yb_traceback_long_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ longList, int nLong,
                          const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
                          const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
-                         PairOut *__restrict__ outs) {
+                         PairOut *__restrict__ outs, unsigned decode) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nLong) return;
@@ -641,7 +924,7 @@ yb_traceback_long_kernel(const PairMeta *__restrict__ metas, const int *__restri
         const int shift = node == FLAG_I ? 4 : (node == FLAG_D ? 2 : 0);
         r -= (node != FLAG_I);
         c -= (node != FLAG_D);
-        node = (int)((0x84u >> (2u * ((st >> shift) & 3u))) & 3u);      // e = notC | gt<<1  ->  0,2: C   1: I   3: D
+        node = (int)((decode >> (2u * ((st >> shift) & 3u))) & 3u);     // TB_DECODE_FLAGS / TB_DECODE_KEYED
     }
     if (lane == 0) {
         if (n & 15) script[n >> 4] = accw;

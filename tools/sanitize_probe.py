@@ -16,6 +16,11 @@ jobs, keep = ctx.make_jobs(probs)
 res, st = ctx.run_batch(jobs)
 assert int((res["status"] != 0).sum()) == 0
 print("pairs", len(jobs), "cells", st.cells, "launches", st.kernel_launches, "checksum", int(res["m_new"].sum()), int(res["C"].astype(np.int64).sum()))
+# a wave of small pairs with connected bands only: the bulk kernels' variant without existence multipliers (GATED = false)
+sb = SynthBatch(99, [2, 3, 4, 5, 2, 3] * 4, [1, 1, 1, 1, 2, 1] * 4, [40, 70, 130, 260, 33, 64] * 4, R=30)
+res2, st2 = ctx.run_batch(sb.jobs)
+assert int((res2["status"] != 0).sum()) == 0
+print("ungated wave: pairs", sb.n, "cells", st2.cells, "launches", st2.kernel_launches, "checksum", int(res2["m_new"].sum()), int(res2["C"].astype(np.int64).sum()))
 ctx.close()
 
 # block scoring (yb_score_kernel): unit seams, ranges starting inside the text, > 255 rows, many small blocks
