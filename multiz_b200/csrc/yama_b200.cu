@@ -143,12 +143,16 @@ class Pool {
     bool stop_ = false;
 };
 
-constexpr int NBINS = 5;
+constexpr int NBINS = 9;
 constexpr int NB = 160;                    // launch-order buckets per ring bin
 // Kernel bins: ring entries (>= widest band row + 32), warps per pair G, pairs per CTA P.  Narrow bands and short
 // pairs run one warp per pair; wide bands on long pairs run one CTA per pair (one ring per pair -> full occupancy).
+// Bins 5..8 are the bulk kernels (fill_body2) for pairs of kernel class 1 (bins 5, 6) and 2 (KEYED; bins 7, 8): same
+// rings as bins 0 and 1.
 struct BinCfg { int ring, G, P, minRows; };
-const BinCfg kBin[NBINS] = {{128, 1, 8, 0}, {512, 1, 8, 0}, {512, 4, 1, 192}, {2048, 8, 1, 0}, {4096, 8, 1, 0}};
+const BinCfg kBin[NBINS] = {{128, 1, 8, 0}, {512, 1, 8, 0}, {512, 4, 1, 192}, {2048, 8, 1, 0}, {4096, 8, 1, 0},
+                            {128, 1, F2_WARPS, 0}, {512, 1, F2_WARPS, 0}, {128, 1, F2_WARPS, 0}, {512, 1, F2_WARPS, 0}};
+constexpr int BULK_BIN0 = 5;
 constexpr int TB_GROUP = 3;               // waves per traceback launch group
 constexpr int NSLOTS = 2 * TB_GROUP;      // one group filling while the previous one drains
 
@@ -160,6 +164,7 @@ struct JobInfo {           // host-side facts about one pair
     int bin = 0;           // kernel bin (ring size, warps per pair)
     int bucket = 0;        // launch-order bucket: ring bin * NB + quarter-octave of the cell count, descending
     int connected = 0;     // every band row is reachable from the row above (LB[r] <= RB[r-1] + 1)
+    int cls = 0;           // kernel class (PairMeta::cls): 0 fill_body, 1 fill_body2, 2 fill_body2 KEYED
 };
 
 // One staging slot = one wave in flight.
@@ -187,10 +192,6 @@ struct Slot {
     int tbLong = TB_LONG;                  // ... those with at least this many moves
     bool y16 = false;                      // every pair has K*gap_open <= 32767: the kernels' 16-bit weight forms
     bool ungated = false;                  // every pair is small enough for the fill variant without existence multipliers
-    int fill2 = -1;                        // the context's bulk-kernel variant (yb_ctx::fill2) when this wave was packed
-    bool keyed = false;                    // ... and for the KEYED bulk kernels (values carry the tie-break in their low bits)
-    long double maxWork = 0;               // max over pairs of (M+N)*K*L
-    int maxK = 0;
     int nValid = 0;
     int binStart[NBINS + 1] = {};
 };
@@ -216,7 +217,6 @@ struct Device {
     int timeline = 0;
     ScoreConst sc{};                       // the owning context's score tables (kernel arguments)
     int fillBlocks[NBINS] = {};
-    int fill2Blocks[2][8] = {};            // bulk kernels (fill_body2), per bin and variant
     int helpers = 1;
     std::unique_ptr<Pool> pool;
     // accumulated stats of the current call
@@ -239,7 +239,7 @@ struct yb_ctx {
     int maxDepth = 255;
     int maxAbsS = 1;                        // max |S6|
     bool ungatedOk = true;                  // YB_UNGATED=0 keeps the existence multipliers in every fill kernel
-    int fill2 = 7;                          // bulk kernels: -1 off (YB_FILL2=0), else variant bits 0 KEYED (YB_KEYED), 1 SHFL (YB_SHFL), 2 ROWPF (YB_ROWPF)
+    int maxCls = 2;                         // highest kernel class handed out: YB_FILL2=0 -> 0 (fill_body only), YB_KEYED=0 -> 1
     int nThreads = 1;
     size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave (steady state)
     size_t waveMinBytes = (size_t)16 << 20; // first waves of a batch (the device idles while the first wave is packed)
@@ -359,6 +359,8 @@ int bin_of(int wmax, int M) {
     if (wmax + 32 <= kBin[4].ring) return 4;
     return -1;
 }
+// the bulk kernels take over the warp-per-pair bins for pairs of class 1 / 2
+inline int bin_of_cls(int bin, int cls) { return (cls >= 1 && bin >= 0 && bin <= 1) ? BULK_BIN0 + 2 * (cls - 1) + bin : bin; }
 int lanes_of(int wmax, int M) {          // wavefront width of the pair's bin (0: no kernel takes it)
     const int b = bin_of(wmax, M);
     return b < 0 ? 0 : 32 * kBin[b].G;
@@ -383,14 +385,17 @@ yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ ord
                  const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int gapOpen, int gapExt) {
     fill_body<RING, G, P, Y16, GATED>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
 }
-// bulk form (fill_body2): one warp per pair, waves of small pairs (Slot::ungated && Slot::y16)
-template <int RING, int P, bool KEYED, bool SHFL, bool ROWPF>
-__global__ void __launch_bounds__(P * 32, (RING <= 128 ? 4 : 1))
+// bulk form (fill_body2): one warp per pair, pairs of kernel class 1 / 2
+#ifndef YB_F2_MINCTAS
+#define YB_F2_MINCTAS 4
+#endif
+template <int RING, bool KEYED>
+__global__ void __launch_bounds__(F2_WARPS * 32, (RING <= 128 ? YB_F2_MINCTAS : 1))
 yb_fill2_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                 int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                 const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
-                const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int gapOpen, int gapExt) {
-    fill_body2<RING, P, KEYED, SHFL, ROWPF>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
+                const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int nGO, int gapExt) {
+    fill_body2<RING, KEYED>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, nGO, gapExt);
 }
 }  // namespace yb
 
@@ -411,26 +416,18 @@ FillFn fill_fn(int bin, bool y16, bool ungated = false) {
     }
 }
 
-// variant index of the bulk kernels: bit 0 KEYED, bit 1 SHFL, bit 2 ROWPF
-constexpr int NVAR2 = 8;
-template <int RING>
-FillFn fill2_of(int v) {
-    switch (v) {
-        case 0: return yb_fill2_kernel<RING, 8, false, false, false>;
-        case 1: return yb_fill2_kernel<RING, 8, true, false, false>;
-        case 2: return yb_fill2_kernel<RING, 8, false, true, false>;
-        case 3: return yb_fill2_kernel<RING, 8, true, true, false>;
-        case 4: return yb_fill2_kernel<RING, 8, false, false, true>;
-        case 5: return yb_fill2_kernel<RING, 8, true, false, true>;
-        case 6: return yb_fill2_kernel<RING, 8, false, true, true>;
-        default: return yb_fill2_kernel<RING, 8, true, true, true>;
+FillFn fill_fn2(int bin) {
+    switch (bin - BULK_BIN0) {
+        case 0: return yb_fill2_kernel<128, false>;
+        case 1: return yb_fill2_kernel<512, false>;
+        case 2: return yb_fill2_kernel<128, true>;
+        default: return yb_fill2_kernel<512, true>;
     }
 }
-FillFn fill_fn2(int bin, int v) { return bin == 0 ? fill2_of<128>(v) : fill2_of<512>(v); }
-size_t fill2_smem(int bin, int v) {
-    // rings (RING*16-aligned, hence the slack) + mailboxes unless SHFL + a 64-B row slot per lane with ROWPF
+size_t fill2_smem(int bin) {
+    // rings (RING*16-aligned, hence the slack) + a 64-B row slot per lane + a stash word per warp
     const size_t ring = (size_t)kBin[bin].ring * 16;
-    return 8 * ring + ((v & 2) ? 0 : 8 * 1024) + ((v & 4) ? 8 * 2048 : 0) + ring + 16;
+    return F2_WARPS * (ring + 32 * 64 + 16) + ring + 16;
 }
 
 int device_init(Device &d) {
@@ -446,7 +443,7 @@ int device_init(Device &d) {
             CUDA_TRY(d, cudaEventCreateWithFlags(&s.binDone[b], cudaEventDisableTiming));
         }
     }
-    for (int b = 0; b < NBINS; ++b) {
+    for (int b = 0; b < BULK_BIN0; ++b) {
         FillFn fn = fill_fn(b, true);
         size_t sm = fill_smem(b);
         CUDA_TRY(d, cudaFuncSetAttribute(fill_fn(b, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -458,15 +455,14 @@ int device_init(Device &d) {
         if (occ < 1) occ = 1;
         d.fillBlocks[b] = occ * d.sms;
     }
-    for (int b = 0; b < 2; ++b)
-        for (int v = 0; v < NVAR2; ++v) {
-            FillFn fn = fill_fn2(b, v);
-            const size_t sm = fill2_smem(b, v);
-            CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            int occ = 0;
-            CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, sm));
-            d.fill2Blocks[b][v] = std::max(occ, 1) * d.sms;
-        }
+    for (int b = BULK_BIN0; b < NBINS; ++b) {
+        FillFn fn = fill_fn2(b);
+        const size_t sm = fill2_smem(b);
+        CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        int occ = 0;
+        CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, F2_WARPS * 32, sm));
+        d.fillBlocks[b] = std::max(occ, 1) * d.sms;
+    }
     return YB_OK;
 }
 
@@ -548,6 +544,18 @@ void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, ch
     }
     ji.bin = bin_of(ji.wmax, j.M);
     ji.nSteps = nSteps;
+    // Kernel class.  Without existence multipliers (classes 1, 2) a candidate from a node that does not exist (exactly
+    // MININT = -2^30) is charged a gap-open the reference skips.  That cannot change any real value, flag or script as long
+    // as real scores stay within +-2^28 and unreal ones within [-2^31, -2^29): both follow from
+    // (M+N)*K*L*(gap_open+gap_extend+max|S|) < 2^28 and a connected band.  The KEYED class carries
+    // 4*value + priority, hence 2^26; both need every pre-multiplied weight of the bulk row record to fit 16 bits.
+    if (ctx->maxCls >= 1 && ji.bin <= 1 && ji.connected) {
+        const long double work = (long double)((int64_t)j.M + j.N) * j.K * j.L * (ctx->sc.gap_open + ctx->sc.gap_ext + ctx->maxAbsS);
+        const long long w16 = std::max<long long>((long long)j.K * (ctx->sc.gap_open + ctx->sc.gap_ext), 2ll * j.K * ctx->maxAbsS);
+        if (ctx->maxCls >= 2 && 4 * w16 <= 32767 && work < (long double)(1 << 26)) ji.cls = 2;
+        else if (w16 <= 32767 && work < (long double)(1 << 28)) ji.cls = 1;
+        ji.bin = bin_of_cls(ji.bin, ji.cls);
+    }
 }
 
 inline bool dims_ok(const yb_job &j) { return j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1 && j.A && j.B && j.LB && j.RB; }
@@ -589,9 +597,6 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     // gap-open the reference skips.  That cannot change any real value, flag or script as long as real scores stay
     // within +-2^28 and unreal ones within [-2^31, -2^29): both follow from (M+N)*K*L*(gap_open+gap_extend+max|S|) < 2^28.
     s.ungated = ctx->ungatedOk && (long double)maxWork * (ctx->sc.gap_open + ctx->sc.gap_ext + ctx->maxAbsS) < (long double)(1 << 28);
-    s.maxWork = (long double)maxWork;
-    s.maxK = maxK;
-    s.fill2 = ctx->fill2;
     s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
     s.orderOff = s.metaBytes;
     s.longOff = s.orderOff + align_up((size_t)count * 4, 256);
@@ -682,6 +687,7 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
                 pm.offSched = oSched;
                 pm.nSteps = ji.nSteps;
                 pm.lgLanes = lg_of(32 * kBin[ji.bin].G);
+                pm.cls = ji.cls;
                 pm.rowBase = of.row;
                 pm.colBase = of.col;
                 pm.scriptBase = of.script;
@@ -740,12 +746,6 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
         }
         s.binStart[NBINS] = acc;
         s.nValid = acc;
-        // KEYED bulk kernels: the whole wave's row records are written with weights x 4 (K1), so every pair of the wave must
-        // run a bulk kernel (bins 0, 1), every 16-bit weight must still fit, and real scores must stay below 2^26
-        const long long k4 = 4ll * std::max(s.maxK, 1);
-        s.keyed = ctx->fill2 >= 0 && (ctx->fill2 & 1) && s.ungated && s.y16 && s.binStart[2] == s.binStart[NBINS] &&
-                  k4 * ctx->sc.gap_open <= 32767 && k4 * ctx->sc.gap_ext <= 32767 && k4 * ctx->maxAbsS <= 32767 &&
-                  s.maxWork * (ctx->sc.gap_open + ctx->sc.gap_ext + ctx->maxAbsS) < (long double)(1 << 26);
         int *longList = reinterpret_cast<int *>(h + s.longOff);
         s.nLong = 0;
         s.tbLong = ctx->tbLong;
@@ -760,7 +760,12 @@ int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first
     d.t_post += t3 - t2;
     CUDA_TRY(d, s.dIn.reserve(s.blobBytes));
     CUDA_TRY(d, s.dRow.reserve(rows * sizeof(RowRec) + 64));
-    CUDA_TRY(d, s.dCol.reserve(cols * sizeof(ColRec) + 64));
+    {   // column records sit between two COL_PAD margins (see fill_body2); a fresh buffer is zeroed once so that what idle
+        // lanes read there is initialised memory
+        const void *before = s.dCol.p;
+        CUDA_TRY(d, s.dCol.reserve(cols * sizeof(ColRec) + 2 * COL_PAD + 64));
+        if (s.dCol.p != before) CUDA_TRY(d, cudaMemsetAsync(s.dCol.p, 0, s.dCol.cap, s.stream));
+    }
     CUDA_TRY(d, s.dTb.reserve(tb + 256));
     CUDA_TRY(d, s.dScript.reserve(words * 4 + 64));
     CUDA_TRY(d, s.dOut.reserve((size_t)count * sizeof(PairOut) + 64));
@@ -779,7 +784,7 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     const PairMeta *metas = static_cast<const PairMeta *>(s.dIn.p);
     const unsigned char *blob = static_cast<const unsigned char *>(s.dIn.p);
     RowRec *rows = static_cast<RowRec *>(s.dRow.p);
-    ColRec *cols = static_cast<ColRec *>(s.dCol.p);
+    ColRec *cols = reinterpret_cast<ColRec *>(static_cast<unsigned char *>(s.dCol.p) + COL_PAD);
     unsigned char *tb = static_cast<unsigned char *>(s.dTb.p);
     PairOut *outs = static_cast<PairOut *>(s.dOut.p);
     const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
@@ -803,7 +808,7 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
     // a script region holds ceil((M+N)/16) words but a path has m_new <= M+N ops: the unwritten tail is copied back too
     if (s.scriptWords) CUDA_TRY(d, cudaMemsetAsync(s.dScript.p, 0, s.scriptWords * 4, st));
     if (s.nValid > 0) {
-        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0, s.keyed ? 4 : 1, d.sc);
+        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0, d.sc);
         d.launches++;
     }
     CUDA_TRY(d, cudaEventRecord(s.ev[2], st));
@@ -815,13 +820,13 @@ int slot_launch_fill(Device &d, Slot &s, bool h2d) {
         const BinCfg &bc = kBin[b];
         cudaStream_t bs = b == 0 ? st : s.binStream[b];
         if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
-        const bool bulk = b < 2 && s.fill2 >= 0 && s.ungated && s.y16;     // fill_body2: bounded scores, 16-bit weights
-        const int var = bulk ? ((s.fill2 & ~1) | (s.keyed ? 1 : 0)) : 0;
-        FillFn fn = bulk ? fill_fn2(b, var) : fill_fn(b, s.y16, s.ungated);
-        const size_t smem = bulk ? fill2_smem(b, var) : fill_smem(b);
-        const int blocks = std::min((n + bc.P - 1) / bc.P, bulk ? d.fill2Blocks[b][var] : d.fillBlocks[b]);
+        const bool bulk = b >= BULK_BIN0;
+        FillFn fn = bulk ? fill_fn2(b) : fill_fn(b, s.y16, s.ungated);
+        const size_t smem = bulk ? fill2_smem(b) : fill_smem(b);
+        const int blocks = std::min((n + bc.P - 1) / bc.P, d.fillBlocks[b]);
         fn<<<blocks, bc.G * bc.P * 32, smem, bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
-                                                    reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs, d.sc.gap_open, d.sc.gap_ext);
+                                                    reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs,
+                                                    bulk ? -d.sc.gap_open * (b >= BULK_BIN0 + 2 ? 4 : 1) : d.sc.gap_open, d.sc.gap_ext);
         if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
         d.launches++;
     }
@@ -857,14 +862,14 @@ int slot_launch_traceback(Device &d, Slot &s, bool d2h) {
         CUDA_TRY(d, cudaStreamWaitEvent(ls, s.ev[6], 0));
         yb_traceback_long_kernel<<<(unsigned)((s.nLong + 3) / 4), 128, 0, ls>>>(
             metas, reinterpret_cast<const int *>(blob + s.longOff), s.nLong, blob, tb,
-            reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs, s.keyed ? TB_DECODE_KEYED : TB_DECODE_FLAGS);
+            reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs);
         CUDA_TRY(d, cudaEventRecord(s.binDone[1], ls));
         d.launches++;
     }
     if (s.nValid > s.nLong) {
         yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(
             metas, order, s.nValid, blob, tb, reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs,
-            s.tbLong, s.keyed ? TB_DECODE_KEYED : TB_DECODE_FLAGS);
+            s.tbLong);
         d.launches++;
     }
     if (s.nLong > 0) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[1], 0));
@@ -1214,10 +1219,8 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_NT")) ctx->ntStores = atoi(e) != 0;
     if (const char *e = getenv("YB_EARLY_H2D")) ctx->earlyH2D = atoi(e) != 0;
     if (const char *e = getenv("YB_UNGATED")) ctx->ungatedOk = atoi(e) != 0;
-    if (const char *e = getenv("YB_KEYED")) ctx->fill2 = (ctx->fill2 & ~1) | (atoi(e) ? 1 : 0);
-    if (const char *e = getenv("YB_SHFL")) ctx->fill2 = (ctx->fill2 & ~2) | (atoi(e) ? 2 : 0);
-    if (const char *e = getenv("YB_ROWPF")) ctx->fill2 = (ctx->fill2 & ~4) | (atoi(e) ? 4 : 0);
-    if (const char *e = getenv("YB_FILL2")) if (atoi(e) == 0) ctx->fill2 = -1;
+    if (const char *e = getenv("YB_KEYED")) if (atoi(e) == 0) ctx->maxCls = std::min(ctx->maxCls, 1);
+    if (const char *e = getenv("YB_FILL2")) if (atoi(e) == 0) ctx->maxCls = 0;
     if (const char *e = getenv("YB_TB_LONG")) ctx->tbLong = std::max(1, atoi(e));
     if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
     for (auto &d : ctx->devs) {

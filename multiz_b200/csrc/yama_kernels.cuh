@@ -56,7 +56,7 @@ struct PairMeta {
     int nSteps;                        // wavefront steps of this pair (host computed from the schedule)
     int bandFmt;                       // 0: M+1 words LB | RB<<16 (N < 65536);  1: M+1 ints LB, then M+1 ints RB
     int lgLanes;                       // log2 of the wavefront width: 32 lanes (one warp) ... 256 lanes (a CTA) per pair
-    int pad;
+    int cls;                           // kernel class: 0 fill_body (RowRec / ColRec), 1 fill_body2, 2 fill_body2 KEYED (RowRec2 / bulk ColRec)
 };
 
 // LB[r] / RB[r] of a pair, whichever way the host packed them
@@ -175,10 +175,13 @@ __device__ __forceinline__ Census census(const unsigned char *now, const unsigne
 // K1: column / row profiles, traceback row offsets, wavefront schedule.  One CTA per pair.
 // =================================================================================================
 constexpr int K1_THREADS = 128;
+struct RowRec2;
+__device__ __forceinline__ void profile_bulk(const PairMeta &pm, const unsigned char *__restrict__ blob, RowRec *__restrict__ rowPool,
+                                             ColRec *__restrict__ colPool, const ScoreConst &c_sc);
 
 __global__ void __launch_bounds__(K1_THREADS, 10)     // 48 registers: 10 CTAs per SM hide more of the load latency (0.97 -> 0.92 ms on cfg2)
 yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__restrict__ blob,
-                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int y16, int scale,
+                  RowRec *__restrict__ rowPool, ColRec *__restrict__ colPool, int y16,
                   const __grid_constant__ ScoreConst c_sc) {
     const PairMeta pm = metas[blockIdx.x];
     const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
@@ -189,9 +192,8 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
     RowRec *rows = rowPool + pm.rowBase;
     ColRec *cols = colPool + pm.colBase;
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
-    // scale: 1, or 4 for the KEYED fill kernels (fill_body2), whose node values carry the tie-break priority in their
-    // low two bits: every weight that is ADDED to a node value is stored multiplied by it
-    const int GE = c_sc.gap_ext * scale;
+    const int GE = c_sc.gap_ext;
+    if (pm.cls != 0) { profile_bulk(pm, blob, rowPool, colPool, c_sc); return; }
 
     // ---- columns of B (c = 0..N) -------------------------------------------------------------
     for (int c = threadIdx.x; c <= N; c += K1_THREADS) {
@@ -235,7 +237,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
             //   D.x: ndA*ndB' + a10*dB'   D.y: a10*(ndB'+dB')   D.z: ndA*(ndB'+dB')   on bytes 2,3 of w2
             // The y candidates (from a D node) are never gated, so when K*gap_open fits 16 bits (y16) their weights are
             // stored already multiplied by -gap_open and K2 applies them with ONE dp2a on bytes 2,3.
-            const int nGO = -c_sc.gap_open * scale;             // (only the 16-bit y forms carry it)
+            const int nGO = -c_sc.gap_open;
             if (r > 1) {                                        // mz_yama.c:180-184, :218-221 (row>1)
                 rr.avXC = pack4(a00, a11, a01, a10);
                 rr.avYC = y16 ? pack16((int)dA * nGO, (int)a10 * nGO) : pack4(0, 0, dA, a10);
@@ -252,7 +254,7 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
                 int acc = 0;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) acc += n[k] * c_sc.S6[k][l];
-                w[l] = acc * scale;
+                w[l] = acc;
             }
             rr.w01 = pack16(w[0], w[1]); rr.w23 = pack16(w[2], w[3]); rr.w45 = pack16(w[4], w[5]);
         }
@@ -530,25 +532,55 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int
 }
 
 // =================================================================================================
-// K2, bulk form: one warp per pair, bounded scores (the GATED = false conditions of fill_body), 16-bit weights.
-// Same wavefront and schedule as fill_body<RING,1,P,true,false>, rebuilt around what ncu showed of that kernel
-// (profiles/r1_fill_summary.md: 75 % issue slots, L1/shared data pipe 72 %, long-scoreboard stalls on the row records):
+// K2, bulk form (fill_body2): one warp per pair, for pairs of kernel class 1 and 2 (PairMeta::cls; the host admits a pair
+// when its band is connected, its scores are bounded -- the GATED = false argument of fill_body, DESIGN section 2 -- and
+// every pre-multiplied weight below fits 16 bits).  Same wavefront and schedule as fill_body<RING,1,P>, rebuilt around
+// what ncu showed of that kernel (profiles/r1_fill_summary.md: 75 % issue slots, L1/shared data pipe 72 %, long-scoreboard
+// stalls on the row records, 89 issue slots per cell):
 //
-//  SHFL   (C,D,I) of the row above arrive by three warp shuffles from lane l-1's registers instead of a shared-memory
-//         mailbox (LDS.128 + STS.128 per lane and step: 8 crossbar cycles per warp step; three SHFL: 3).  Only lane 0
-//         reads and lane 31 writes the ring that carries a band row from one 32-row block to the next.  A lane that is
-//         not inside its row hands down MININT -- exactly the never-written dp[] entries of mz_yama.c:93-94 -- so a
-//         finished row needs no stale-record stores.
-//  ROWPF  a lane's NEXT row record is copied global -> shared (cp.async, a private 64-B slot per lane) while it walks
-//         its current row; the row switch reads it with four LDS.128 instead of four dependent global loads.
-//  KEYED  node values are carried as 4*value + p with p = 2 for a C node, 1 for an I node, 0 for a D node, and every
-//         weight is a multiple of 4.  A candidate inherits the p of the node it comes from, so ONE 3-way maximum
-//         decides value and tie-break together: 4x+2 > 4y and 4x+2 > 4z+1 iff x >= y and x >= z (from-C wins ties),
-//         4y > 4z+1 iff y > z (from-D beats from-I only strictly) -- the rule of mz_yama.c:138-154 -- and the low two
-//         bits of the maximum ARE the traceback pointer (2: from C, 0: from D, 1: from I): one funnel shift per node
-//         into the packed word instead of two compares and two predicated adds.  Needs 4*K*gap_open <= 32767 and
-//         real scores below 2^26 (host-checked per wave).
+//  * (C,D,I) of the row above arrive by three warp shuffles from lane l-1's registers instead of a shared-memory mailbox
+//    (LDS.128 + STS.128 per lane and step = 8 crossbar cycles per warp step; three SHFL = 3).  Only lane 0 reads and lane 31
+//    writes the ring that carries a band row from one 32-row block to the next.  A lane that is not inside its row hands
+//    down MININT -- exactly the never-written dp[] entries of mz_yama.c:93-94 -- so a finished row needs no stale stores.
+//  * a lane's NEXT row record is copied global -> shared (cp.async, a private 64-B slot per lane) while it walks its
+//    current row; the row switch reads it with four LDS.128 instead of four dependent global loads.
+//  * records in the bulk layout (RowRec2 / ColRec2): every two-term gap-open count is ONE dp2a with 16-bit weights already
+//    multiplied by -gap_open, accumulated straight onto the predecessor's value; the I node's extension charge rides on its
+//    three candidates (max(x,y,z) - e = max(x-e, y-e, z-e)); the class "other" is eliminated from the sum-of-pairs dot
+//    product (n_X = ndB - n_A - n_C - n_G - n_T), which frees the column bytes the pairs need.
+//  * KEYED (class 2): node values are carried as 4*value + p with p = 2 for a C node, 1 for an I node, 0 for a D node, and
+//    every weight is a multiple of 4.  A candidate inherits the p of the node it comes from, so ONE 3-way maximum decides
+//    value and tie-break together: 4x+2 > 4y and 4x+2 > 4z+1 iff x >= y and x >= z (from-C wins ties), 4y > 4z+1 iff y > z
+//    (from-D beats from-I only strictly) -- the rule of mz_yama.c:138-154 -- and the low two bits of the maximum ARE the
+//    traceback pointer (2: from C, 0: from D, 1: from I): one funnel shift per node into the packed word instead of two
+//    compares and two predicated adds.  Needs real scores below 2^26 (host-checked per pair).
 // =================================================================================================
+// Column record of the bulk layout, 16 B.  "m": zeroed for c == 1 (mz_yama.c:173, no gap-open at the start);
+// ndB', dB': zeroed for c == 0 and c == N (mz_yama.c:211, end gaps free).
+//  w0 = (n_A, n_C, n_G, n_T)            class counts
+//  w1 = (ndB, dB, ndB, b10)             lo: sum-of-pairs terms of "other" and dash; hi: the I node's pair
+//  w2 = (b01, b10, ndB, dB) m           C node: x (all four, dp4a), y (hi)
+//  w3 = (dB m, b10 m, ndB', dB')        lo: C node z; hi: D node x, y, z
+// Row record of the bulk layout, 64 B.  p16(lo, hi) are 16-bit weights, g = -gap_open * scale, e = K * gap_extend * scale.
+struct __align__(16) RowRec2 {
+    unsigned avXC;      // bytes (a00, a11, a01, a10), row > 1
+    unsigned wYC;       // p16(dA*g, a10*g) on (ndB, dB), row > 1
+    unsigned wZC;       // p16(ndA*g, dA*g) on (dB, b10)
+    unsigned wXI;       // p16(ndA*g - e, dA*g) on (ndB, b10); row M: p16(-e, 0)  (mz_yama.c:123)
+    unsigned wXD;       // p16(ndA*g, a10*g) on (ndB', dB'), row > 1
+    unsigned wYD;       // p16(a10*g, a10*g), row > 1
+    unsigned wZD;       // p16(ndA*g, ndA*g)
+    int eD;             // ndA * L * gap_extend * scale  (mz_yama.c:239-242)
+    unsigned w01, w23;  // p16 of S6^T * classcount(A row) minus its "other" entry, classes A C | G T, times scale
+    unsigned w45;       // p16(other, dash) entries, times scale, on (ndB, dB)
+    int LB16;           // 16*LB[r]
+    int RB16;           // 16*RB[r]
+    int LBc16;          // the C node of (r,c) exists iff 16*c > LBc16 = max(16*LB[r] - 16, 16*LB[r-1])
+    int off16;          // wavefront schedule: this row computes column (step - off), times 16
+    int RBn;            // RB[r+1] (RB[r] on the last row): how far the row below reads us
+};
+static_assert(sizeof(RowRec2) == sizeof(RowRec), "both layouts share the row pool");
+
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -565,36 +597,106 @@ __device__ __forceinline__ int unkey(int v) {
     return v < -(1 << 29) ? u - 3 * (1 << 28) : u;
 }
 
-template <int RING, int P, bool KEYED, bool SHFL, bool ROWPF>
+// K1 for a pair of class 1 / 2: the same census, written in the bulk layout (see RowRec2 above)
+__device__ __forceinline__ void profile_bulk(const PairMeta &pm, const unsigned char *__restrict__ blob, RowRec *__restrict__ rowPool,
+                                             ColRec *__restrict__ colPool, const ScoreConst &c_sc) {
+    const int K = pm.K, M = pm.M, L = pm.L, N = pm.N;
+    const int scale = pm.cls == 2 ? 4 : 1;
+    const unsigned char *A = blob + pm.offA;
+    const unsigned char *B = blob + pm.offB;
+    const BandView band(blob, pm);
+    RowRec2 *rows = reinterpret_cast<RowRec2 *>(rowPool + pm.rowBase);
+    ColRec *cols = colPool + pm.colBase;
+    const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
+    const int g = -c_sc.gap_open * scale, e = K * c_sc.gap_ext * scale;
+    for (int c = threadIdx.x; c <= N; c += K1_THREADS) {
+        ColRec cr = {0u, 0u, 0u, 0u};
+        if (c >= 1) {
+            const unsigned char *now = B + (size_t)(c - 1) * L;
+            const Census q = census(now, c > 1 ? now - L : nullptr, L);    // mz_yama.c:128 (t==0 when col==1)
+            const unsigned *n = q.n;
+            const unsigned b01 = q.t01, b10 = q.t10, dB = n[5], ndB = (unsigned)L - dB;
+            const bool inner = (c < N), later = (c > 1);                   // mz_yama.c:211, :173
+            cr.w0 = pack4(n[0], n[1], n[2], n[3]);
+            cr.w1 = pack4(ndB, dB, ndB, b10);
+            cr.w2 = later ? pack4(b01, b10, ndB, dB) : 0u;
+            cr.w3 = pack4(later ? dB : 0u, later ? b10 : 0u, inner ? ndB : 0u, inner ? dB : 0u);
+        }
+        cols[c] = cr;
+    }
+    for (int r = threadIdx.x; r <= M; r += K1_THREADS) {
+        RowRec2 rr;
+        rr.avXC = rr.wYC = rr.wZC = rr.wXI = rr.wXD = rr.wYD = rr.wZD = 0u;
+        rr.eD = 0; rr.w01 = rr.w23 = rr.w45 = 0u;
+        const int lb = band.lb(r), lbp = r > 0 ? band.lb(r - 1) : 0;
+        rr.LB16 = lb * 16; rr.RB16 = band.rb(r) * 16;
+        rr.LBc16 = max(lb * 16 - 16, lbp * 16);
+        rr.off16 = r >= 1 ? 16 * (sched[(r - 1) >> 5] + ((r - 1) & 31)) : 0;
+        rr.RBn = r < M ? band.rb(r + 1) : band.rb(r);
+        if (r >= 1) {
+            const unsigned char *now = A + (size_t)(r - 1) * K;
+            const Census q = census(now, r > 1 ? now - K : nullptr, K);    // mz_yama.c:175,213 (s==0 when row==1)
+            int n[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) n[k] = (int)q.n[k];
+            const int a00 = (int)q.t00, a01 = (int)q.t01, a10 = (int)q.t10, a11 = (int)q.t11;
+            const int dA = n[5], ndA = K - dA;
+            // gap-open counts:  C.x: a00*b01 + a11*b10 + a01*ndB + a10*dB   C.y: dA*ndB + a10*dB   C.z: ndA*dB + dA*b10
+            //   I.x: ndA*ndB + dA*b10   I.y: K*ndB   I.z: K*b10   D.x: ndA*ndB' + a10*dB'   D.y: a10*(ndB'+dB')   D.z: ndA*(ndB'+dB')
+            if (r > 1) {                                        // mz_yama.c:180-184, :218-221 (row>1)
+                rr.avXC = pack4((unsigned)a00, (unsigned)a11, (unsigned)a01, (unsigned)a10);
+                rr.wYC = pack16(dA * g, a10 * g);
+                rr.wXD = pack16(ndA * g, a10 * g);
+                rr.wYD = pack16(a10 * g, a10 * g);
+            }
+            rr.wZC = pack16(ndA * g, dA * g);
+            rr.wZD = pack16(ndA * g, ndA * g);
+            rr.wXI = r < M ? pack16(ndA * g - e, dA * g) : pack16(-e, 0);      // mz_yama.c:123 (row<M), :158-161
+            rr.eD = ndA * L * c_sc.gap_ext * scale;
+            int w[6];
+#pragma unroll
+            for (int l = 0; l < 6; ++l) {
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc += n[k] * c_sc.S6[k][l];
+                w[l] = acc * scale;
+            }
+            // n_X = ndB - n_A - n_C - n_G - n_T: the "other" weight moves onto ndB
+            rr.w01 = pack16(w[0] - w[4], w[1] - w[4]); rr.w23 = pack16(w[2] - w[4], w[3] - w[4]); rr.w45 = pack16(w[4], w[5]);
+        }
+        rows[r] = rr;
+    }
+}
+
+#ifndef YB_F2_WARPS
+#define YB_F2_WARPS 8
+#endif
+constexpr int F2_WARPS = YB_F2_WARPS;                         // pairs in flight per CTA
+constexpr size_t COL_PAD = 32768;                             // bytes of slack before and after a wave's column records: lanes outside
+                                                              // their row read (and discard) up to about two band rows off either end
+
+template <int RING, bool KEYED>
 __device__ __forceinline__ void
 fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
            int *__restrict__ queue, const RowRec *__restrict__ rowPool,
            const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
-           const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, const int gapOpen, const int gapExt) {
-    constexpr int B = 32;
+           const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, const int nGO, const int gapExt) {
+    // nGO: -gap_open * SC, from the host (a kernel parameter is an operand, not an instruction)
+    constexpr int B = 32, P = F2_WARPS;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int SC = KEYED ? 4 : 1;                         // every weight is multiplied by SC
     constexpr int PRC = KEYED ? 2 : 0, PRI = KEYED ? 1 : 0;   // low bits of a C / I node value (a D node carries 0)
     constexpr int MIN_C = MININT | PRC, MIN_D = MININT, MIN_I = MININT | PRI;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [ P rings of RING records | P x 32 lanes x 2 mailbox records (not SHFL) | P x 32 row slots of 64 B (ROWPF) | pad ]
+    // layout: [ P rings of RING records | P x 32 row slots of 64 B | P stash words | pad ]; rings are RING*16-aligned
     const int grp = (int)(threadIdx.x >> 5);
     const int lane = (int)(threadIdx.x & 31);
     const unsigned smem0 = (smem_u32(smem_raw) + RING * 16 - 1) & ~(unsigned)(RING * 16 - 1);
     const unsigned ringAddr = smem0 + grp * RING * 16;
-    constexpr unsigned BOX_BYTES = SHFL ? 0u : (unsigned)(P * B * 32);
-    const unsigned boxAddr = smem0 + P * RING * 16 + grp * B * 32;
-    const unsigned rowSlot = smem0 + P * RING * 16 + BOX_BYTES + (unsigned)(grp * B + lane) * 64u;
-    const int nGO = -gapOpen * SC;
+    const unsigned rowSlot = smem0 + P * RING * 16 + (unsigned)(grp * B + lane) * 64u;
+    const unsigned stash = smem0 + P * RING * 16 + P * B * 64 + grp * 16;      // lane 31's RB[r+1], see the row switch
     const unsigned keyMask = launder(~3u);                    // (in a register: LOP3 takes one immediate)
     constexpr unsigned RMASK = (unsigned)(RING * 16 - 16);
-
-    // mailbox addressing of the non-SHFL form: as in fill_body
-    auto boxOf = [&](int l) { return boxAddr + 32u * l + (((unsigned)l >> 2) & 1u) * 16u; };
-    const unsigned rdBase = launder((lane == 0) ? ringAddr : boxOf(lane - 1));
-    const unsigned rdMask = (lane == 0) ? RMASK : 16u;
-    const unsigned wrBase = launder((lane == B - 1) ? ringAddr : boxOf(lane));
-    const unsigned wrMask = (lane == B - 1) ? RMASK : 16u;
 
     for (;;) {
         int slot = 0;
@@ -604,14 +706,15 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ order, in
         const int p = order[slot];
         const PairMeta pm = metas[p];
         const int M = pm.M;
-        const RowRec *rows = rowPool + pm.rowBase;
+        const RowRec2 *rows = reinterpret_cast<const RowRec2 *>(rowPool + pm.rowBase);
         const ColRec *cols = colPool + pm.colBase;
         unsigned char *tb = tbPool + __ldg(tbBase + p);
-        const unsigned nKGE_lo = launder((unsigned)(-(pm.K * gapExt * SC)) & 0xffffu);   // dp2a.hi weight of byte 2 (ndB)
         const int KGE = pm.K * gapExt * SC;
         const int nSteps = pm.nSteps;
         const int N16 = pm.N * 16;
-        const int KnGO = pm.K * nGO;                        // I-node y / z charge per residue / per closing gap of B
+        // the I node's y and z weights on (ndB, b10): K*ndB opens and K*b10 opens (mz_yama.c:131-137), extension folded in;
+        // on the last row only the extension is charged (mz_yama.c:123)
+        const unsigned cYI = pack16(pm.K * nGO - KGE, 0), cZI = pack16(-KGE, pm.K * nGO), cLast = pack16(-KGE, 0);
 
         // ---- row 0 (mz_yama.c:83-94) into the ring -------------------------------------------------------------
         {
@@ -621,7 +724,7 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ order, in
             for (int base = 0; base <= RB1; base += 32) {
                 int c = base + lane;
                 int nd = 0;
-                if (c >= 1 && c <= RB0) nd = (int)((__ldg(&cols[c].w0) >> 16) & 0xffu);
+                if (c >= 1 && c <= RB0) nd = (int)(__ldg(&cols[c].w1) & 0xffu);          // ndB
                 int inc = nd;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -642,149 +745,133 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ order, in
 
         // ---- per-lane row state -----------------------------------------------------------------------------------
         int r = lane + 1;
-        unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avXD = 0, avYD = 0, avZD = 0;
-        int gIrow = 0, gIz = 0;
+        unsigned avXC = 0, wYC = 0, wZC = 0, wXI = 0, wXD = 0, wYD = 0, wZD = 0, wYI = 0, wZI = 0;
         unsigned w01 = 0, w23 = 0, w45 = 0;
-        // LBc16: the C node of (r,c) exists iff c >= LB[r] and c > LB[r-1], i.e. c16 > max(LB16 - 16, 16*LB[r-1]);
         // LBst16: LB16 on the lane that feeds the ring, never reached on the others (one compare decides the ring store)
         int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBc16 = 0x7fffffff, LBst16 = 0x7fffffff, c16 = 0;
-        auto unpack_row = [&](const uint4 &q0, const uint4 &q1, const uint4 &q2, const uint4 &q3, int t) {
-            avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
-            avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
+        // cp: address of this lane's column record at the first step of the current group of eight (the loads of the group
+        // use immediate offsets; a row switch re-bases it).  Lanes outside their row read whatever lies there -- the column
+        // pool is padded on both sides (COL_PAD) -- and discard it.
+        const unsigned char *const colBase = reinterpret_cast<const unsigned char *>(cols);
+        const unsigned char *cp = colBase;
+        const unsigned char *pf = reinterpret_cast<const unsigned char *>(rows + r + B);     // the record the next switch prefetches
+        auto unpack_row = [&](const uint4 &q0, const uint4 &q1, const uint4 &q2, const uint4 &q3, int t16, int u) {
+            avXC = q0.x; wYC = q0.y; wZC = q0.z; wXI = q0.w;
+            wXD = q1.x; wYD = q1.y; wZD = q1.z; eD = (int)q1.w;
             w01 = q2.x; w23 = q2.y; w45 = q2.z; LB16 = (int)q2.w;
-            RB16 = (int)q3.x; LBc16 = max(LB16 - 16, (int)q3.y);
+            RB16 = (int)q3.x; LBc16 = (int)q3.y;
+            c16 = t16 - (int)q3.z;
+            cp = colBase + (c16 - 16 * u);
             LBst16 = (lane == B - 1) ? LB16 : 0x7fffffff;
-            c16 = (t - (int)q3.z) * 16;
-            gIrow = r < M ? (KnGO & 0xffff) : 0;                    // mz_yama.c:123: no I-node gap-open on the last row
-            gIz = gIrow << 16;                                      // the z candidate's weight sits on byte 1 (b10)
+            wYI = r < M ? cYI : cLast;
+            wZI = r < M ? cZI : cLast;
+            if (lane == B - 1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(stash), "r"(q3.w) : "memory");
         };
-        auto prefetch_row = [&](int rr) {                           // row rr's record -> this lane's slot
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(rows + rr);
-            cp_async16(rowSlot, src); cp_async16(rowSlot + 16, src + 16);
-            cp_async16(rowSlot + 32, src + 32); cp_async16(rowSlot + 48, src + 48);
+        auto prefetch_row = [&]() {                                 // the record at pf -> this lane's slot
+            cp_async16(rowSlot, pf); cp_async16(rowSlot + 16, pf + 16);
+            cp_async16(rowSlot + 32, pf + 32); cp_async16(rowSlot + 48, pf + 48);
             cp_async_commit();
+            pf += B * sizeof(RowRec2);
         };
         if (r <= M) {
             const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
             const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
-            unpack_row(q0, q1, q2, q3, 0);
-            if (ROWPF && r + B <= M) prefetch_row(r + B);
+            unpack_row(q0, q1, q2, q3, 0, 0);
+            if (r + B <= M) prefetch_row();
         }
         unsigned acc = 0;
-        const size_t tbWord = (size_t)lane * 2;               // this lane's word inside an 8-step group (see tb_byte)
-        int Cl = MIN_C, Dl = MIN_D, Il = MIN_I;               // grid point (r, c-1)
+        unsigned *tbp = reinterpret_cast<unsigned *>(tb) + lane * 2;      // this lane's two words of an 8-step group (see tb_byte)
+        int Cl = MIN_C, Dl = MIN_D, Il = MIN_I;               // grid point (r, c-1); also what this lane hands down
         int Cd = MIN_C, Dd = MIN_D, Id = MIN_I;               // grid point (r-1, c-1)
-        int oC = MIN_C, oD = MIN_D, oI = MIN_I;               // SHFL: what this lane hands down (its last cell, or MININT)
         __syncwarp();
 
-        for (int t4 = 0; t4 < nSteps; t4 += 4) {
+        for (int t8 = 0; t8 < nSteps; t8 += 8) {              // (nSteps is a multiple of 8)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                // ---- grid point (r-1, c) ----------------------------------------------------------------------
-                int Cu, Du, Iu;
-                if (SHFL) {
-                    Cu = __shfl_up_sync(FULL, oC, 1); Du = __shfl_up_sync(FULL, oD, 1); Iu = __shfl_up_sync(FULL, oI, 1);
-                    if (lane == 0) {
-                        const uint4 up = lds128(and_xor((unsigned)c16, RMASK, ringAddr));
-                        Cu = (int)up.x; Du = (int)up.y; Iu = (int)up.z;
-                    }
-                } else {
-                    const uint4 up = lds128(and_xor((unsigned)c16, rdMask, rdBase));
+            for (int u = 0; u < 8; ++u) {
+                // ---- grid point (r-1, c): the last cell of the lane above, or MININT if it is outside its row --------
+                int Cu = __shfl_up_sync(FULL, Cl, 1), Du = __shfl_up_sync(FULL, Dl, 1), Iu = __shfl_up_sync(FULL, Il, 1);
+                if (lane == 0) {
+                    const uint4 up = lds128(and_xor((unsigned)c16, RMASK, ringAddr));
                     Cu = (int)up.x; Du = (int)up.y; Iu = (int)up.z;
                 }
-                {
-                    if (c16 > RB16) {
-                        // ---- this lane finished its row -----------------------------------------------------
-                        // the row below keeps reading us up to its own right bound: stale dp[] entries (mz_yama.c:93-94).
-                        // SHFL: an idle lane hands down MININT by itself; only the ring (lane 31) needs them written.
-                        if (lane == B - 1) {
-                            const int RBn = __ldg(reinterpret_cast<const int *>(rows + r) + 15);   // RowRec::RBn
+                if (c16 > RB16) {
+                    // ---- this lane finished its row: move one wavefront width down -----------------------------------
+                    // the row below keeps reading us up to its own right bound and must find never-written dp[] entries
+                    // there (mz_yama.c:93-94): an idle lane hands down MININT by itself, the ring needs them written
+                    if (lane == B - 1) {
+                        int RBn;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(RBn) : "r"(stash) : "memory");
 #pragma unroll 1
-                            for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
-                                sts128(and_xor((unsigned)cc << 4, RMASK, ringAddr), MIN_C, MIN_D, MIN_I, 0u);
-                        } else if (!SHFL) {
-                            sts128(wrBase, MIN_C, MIN_D, MIN_I, 0u);
-                            sts128(wrBase ^ 16u, MIN_C, MIN_D, MIN_I, 0u);
-                        }
-                        r += B;
-                        if (r <= M) {
-                            uint4 q0, q1, q2, q3;
-                            if (ROWPF) {
-                                cp_async_wait_all();
-                                q0 = lds128(rowSlot); q1 = lds128(rowSlot + 16); q2 = lds128(rowSlot + 32); q3 = lds128(rowSlot + 48);
-                            } else {
-                                const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
-                                q0 = __ldg(rp); q1 = __ldg(rp + 1); q2 = __ldg(rp + 2); q3 = __ldg(rp + 3);
-                            }
-                            unpack_row(q0, q1, q2, q3, t4 + u);
-                            if (ROWPF && r + B <= M) prefetch_row(r + B);      // (after the slot's words were consumed)
-                        } else {
-                            if (r - B == M) { outs[p].C = unkey<KEYED>(Cl); outs[p].D = unkey<KEYED>(Dl); outs[p].I = unkey<KEYED>(Il); }
-                            LB16 = 0x7fffffff; RB16 = 0x7fffffff; LBc16 = 0x7fffffff; LBst16 = 0x7fffffff;
-                        }
+                        for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
+                            sts128(and_xor((unsigned)cc << 4, RMASK, ringAddr), MIN_C, MIN_D, MIN_I, 0u);
+                    }
+                    r += B;
+                    if (r <= M) {
+                        cp_async_wait_all();
+                        const uint4 q0 = lds128(rowSlot), q1 = lds128(rowSlot + 16), q2 = lds128(rowSlot + 32), q3 = lds128(rowSlot + 48);
+                        unpack_row(q0, q1, q2, q3, (t8 + u) * 16, u);
+                        if (r + B <= M) prefetch_row();               // (after the slot's words were consumed)
+                    } else {
+                        // a lane that runs out of rows idles; the one that just finished row M leaves the final scores
+                        if (r - B == M) { outs[p].C = unkey<KEYED>(Cl); outs[p].D = unkey<KEYED>(Dl); outs[p].I = unkey<KEYED>(Il); }
+                        LB16 = 0x7fffffff; RB16 = 0x7fffffff; LBc16 = 0x7fffffff; LBst16 = 0x7fffffff;
+                        cp = colBase - 16 * u;                        // (idles over the pair's first columns)
                     }
                 }
                 const bool active = (c16 >= LB16);
-
-                // column record of column c; lanes outside their row read a clamped (valid) column and discard the result
-                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) +
-                                                                       (unsigned)__vimin_s32_relu(c16, N16)));
+                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(cp + 16 * u));       // column record of column c
                 int vI, vC, vD;
                 const bool hasI = c16 > LB16, hasC = c16 > LBc16;
                 if (!KEYED) acc >>= 8;                       // make room for this cell's byte (bits 24..31)
                 // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
                 {
-                    int x = Cd + dp4a_uu(cw.w, avXC, 0) * nGO;
-                    int y = dp2a_hi_su(avYC, cw.w, Dd);
-                    int z = Id + dp4a_uu(cw.w, avZC, 0) * nGO;
+                    const int x = Cd + dp4a_uu(cw.z, avXC, 0) * nGO;
+                    const int y = dp2a_hi_su(wYC, cw.z, Dd);
+                    const int z = dp2a_lo_su(wZC, cw.w, Id);
                     if (KEYED) {
                         const int m = __vimax3_s32(x, y, z);
                         acc = __funnelshift_r(acc, (unsigned)m, 2);
                         vC = (int)and_or((unsigned)m, keyMask, (unsigned)PRC);
                     } else vC = pick3<0>(x, y, z, hasC, acc);
-                    vC = dp2a_lo_su(w01, cw.y, vC);
-                    vC = dp2a_hi_su(w23, cw.y, vC);
-                    vC = dp2a_lo_su(w45, cw.z, vC);
+                    vC = dp2a_lo_su(w01, cw.x, vC);
+                    vC = dp2a_hi_su(w23, cw.x, vC);
+                    vC = dp2a_lo_su(w45, cw.y, vC);
                 }
                 vC = hasC ? vC : MIN_C;
                 // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
                 {
-                    int x = Cu + dp4a_uu(cw.z, avXD, 0) * nGO;
-                    int y = dp2a_hi_su(avYD, cw.z, Du);
-                    int z = Iu + dp4a_uu(cw.z, avZD, 0) * nGO;
+                    const int x = dp2a_hi_su(wXD, cw.w, Cu);
+                    const int y = dp2a_hi_su(wYD, cw.w, Du);
+                    const int z = dp2a_hi_su(wZD, cw.w, Iu);
                     if (KEYED) {
                         const int m = __vimax3_s32(x, y, z);
                         acc = __funnelshift_r(acc, (unsigned)m, 2);
-                        vD = (m & ~3) - eD;
+                        vD = (int)((unsigned)m & keyMask) - eD;
                     } else vD = pick3<2>(x, y, z, true, acc) - eD;
                 }
-                if (SHFL) vD = active ? vD : MIN_D;
+                vD = active ? vD : MIN_D;
                 // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
                 {
-                    int x = Cl + dp4a_uu(cw.x, avXI, 0) * nGO;
-                    int y = dp2a_hi_su((unsigned)gIrow, cw.x, Dl);                  // K*ndB opens (mz_yama.c:131-134)
-                    int z = dp2a_lo_su((unsigned)gIz, cw.x, Il);                    // K*b10
+                    const int x = dp2a_hi_su(wXI, cw.y, Cl);
+                    const int y = dp2a_hi_su(wYI, cw.y, Dl);
+                    const int z = dp2a_hi_su(wZI, cw.y, Il);
                     if (KEYED) {
                         const int m = __vimax3_s32(x, y, z);
                         acc = __funnelshift_r(acc, (unsigned)m, 4);                 // (bits 6,7 of the byte: don't care)
                         vI = (int)and_or((unsigned)m, keyMask, (unsigned)PRI);
                     } else vI = pick3<4>(x, y, z, hasI, acc);
-                    vI = dp2a_hi_su(nKGE_lo, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
                 }
                 vI = hasI ? vI : MIN_I;
-                if (SHFL) {
-                    if (c16 >= LBst16) sts128(and_xor((unsigned)c16, RMASK, ringAddr), vC, vD, vI, 0u);
-                    oC = vC; oD = vD; oI = vI;
-                } else if (active) {
-                    sts128(and_xor((unsigned)c16, wrMask, wrBase), vC, vD, vI, 0u);
-                }
+                if (c16 >= LBst16) sts128(and_xor((unsigned)c16, RMASK, ringAddr), vC, vD, vI, 0u);
                 // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
-                if (u == 3) reinterpret_cast<unsigned *>(tb)[(size_t)(t4 >> 3) * (2 * B) + tbWord + ((t4 >> 2) & 1)] = acc;
+                if (u == 3) tbp[0] = acc;
+                if (u == 7) tbp[1] = acc;
                 Cl = vC; Dl = vD; Il = vI;
                 Cd = Cu; Dd = Du; Id = Iu;
                 c16 += 16;
-                if (!SHFL) __syncwarp();
             }
+            cp += 128;
+            tbp += 2 * B;
         }
         __syncwarp();
     }
@@ -808,12 +895,13 @@ __global__ void __launch_bounds__(128)
 yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
                     const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
                     const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
-                    PairOut *__restrict__ outs, int tbLong, unsigned decode) {
+                    PairOut *__restrict__ outs, int tbLong) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nPairs) return;
     const int p = order[idx];
     const PairMeta pm = metas[p];
     if (pm.M + pm.N >= tbLong) return;                  // walked by yb_traceback_long_kernel, one warp per pair
+    const unsigned decode = pm.cls == 2 ? TB_DECODE_KEYED : TB_DECODE_FLAGS;
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
     const unsigned char *tb = tbPool + __ldg(tbBase + p);
     unsigned *script = scriptPool + pm.scriptBase;
@@ -877,12 +965,13 @@ __global__ void __launch_bounds__(128)
 yb_traceback_long_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ longList, int nLong,
                          const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
                          const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
-                         PairOut *__restrict__ outs, unsigned decode) {
+                         PairOut *__restrict__ outs) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nLong) return;
     const int p = longList[w];
     const PairMeta pm = metas[p];
+    const unsigned decode = pm.cls == 2 ? TB_DECODE_KEYED : TB_DECODE_FLAGS;
     const int *sched = reinterpret_cast<const int *>(blob + pm.offSched);
     const unsigned char *tb = tbPool + __ldg(tbBase + p);
     unsigned *script = scriptPool + pm.scriptBase;
