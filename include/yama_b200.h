@@ -67,6 +67,8 @@ typedef struct {
     int32_t kernel_launches;
     int32_t n_devices;
     double fill_ms, profile_ms, traceback_ms;   /* device time split, device 0 */
+    double plan_ms;      /* device time of the planning kernels (band checks, schedule, launch order), max over devices */
+    int64_t staged_bytes; /* input bytes that were copied once on the host (callers outside yb_host_alloc memory)     */
 } yb_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -77,6 +79,13 @@ int yb_create(const int *devices, int ndev, yb_ctx **out);
 void yb_destroy(yb_ctx *ctx);
 const char *yb_last_error(const yb_ctx *ctx);   /* message in the reference's own wording */
 int yb_device_count(const yb_ctx *ctx);
+
+/* Pinned host memory owned by the context.  A caller that builds its jobs' A, B, LB and RB inside such blocks (any
+ * layout; one block or several) lets yb_run_batch copy them to the device as they are, with no pass over them on the
+ * host; inputs anywhere else are staged through one memcpy.  Results are identical either way.  The reference has no
+ * counterpart (its yama() reads malloc'd buffers in place, mz_preyama.c:174-205). */
+void *yb_host_alloc(yb_ctx *ctx, size_t bytes);
+void yb_host_free(yb_ctx *ctx, void *p);
 
 /* ---- score tables (replaces reading the globals of mz_scores.h:8-11) ----------------------- */
 /* ss: 128*128 ints row-major (ss[c][d] of the reference), gop: 16 ints, gap_extend.

@@ -13,6 +13,7 @@
 // There is no CPU implementation of the DP in this library.
 #include "../../include/yama_b200.h"
 #include "yama_kernels.cuh"
+#include "plan_kernels.cuh"
 #include "score_kernels.cuh"
 
 #include <emmintrin.h>
@@ -22,6 +23,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <cstdarg>
 #include <cstdio>
@@ -153,47 +155,39 @@ struct BinCfg { int ring, G, P, minRows; };
 const BinCfg kBin[NBINS] = {{128, 1, 8, 0}, {512, 1, 8, 0}, {512, 4, 1, 192}, {2048, 8, 1, 0}, {4096, 8, 1, 0},
                             {128, 1, F2_WARPS, 0}, {512, 1, F2_WARPS, 0}, {128, 1, F2_WARPS, 0}, {512, 1, F2_WARPS, 0}};
 constexpr int BULK_BIN0 = 5;
-constexpr int TB_GROUP = 3;               // waves per traceback launch group
-constexpr int NSLOTS = 2 * TB_GROUP;      // one group filling while the previous one drains
+constexpr int NSLOTS = 8;                 // waves in flight per device (each on its own stream, queued in one go)
 
-struct JobInfo {           // host-side facts about one pair
-    int64_t cells = 0;     // tback_size of the reference
-    int nSteps = 0;        // wavefront steps (schedule below); traceback bytes = 32 * nSteps
-    int wmax = 0;          // widest band row
-    int status = YB_OK;
-    int bin = 0;           // kernel bin (ring size, warps per pair)
-    int bucket = 0;        // launch-order bucket: ring bin * NB + quarter-octave of the cell count, descending
-    int connected = 0;     // every band row is reachable from the row above (LB[r] <= RB[r-1] + 1)
-    int cls = 0;           // kernel class (PairMeta::cls): 0 fill_body, 1 fill_body2, 2 fill_body2 KEYED
-};
+static_assert(NBINS == PLAN_NBINS && NB == PLAN_NB && BULK_BIN0 == PLAN_BULK_BIN0, "plan_kernels.cuh mirrors the bin table");
 
 // One staging slot = one wave in flight.
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t binStream[NBINS] = {};    // fill kernels of the wider ring bins run beside the main one
     cudaEvent_t binDone[NBINS] = {};
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};                // 0 copy start, 1 copy end, 7 K0 end | 2 K1 start, 3 K1 end, 8 fill end | 6 K3 start, 4 K3 end, 5 results on the host
     DevBuf dIn, dRow, dCol, dTb, dScript, dOut, dQueue;
-    PinBuf hIn, hOut;
+    PinBuf hIn, hOut, hPlan;               // hIn: pair descriptors + staged input streams; hPlan: the wave summary of K0
     uint8_t *scriptDst = nullptr;          // where this wave's packed scripts go in the context's pinned store
-    bool filled = false;                   // H2D + K1 + K2 queued, K3 not yet
-    bool busy = false;                     // K3 + D2H queued, results not yet unpacked
-    size_t sentLo = 0, sentHi = 0;         // bytes [sentLo, sentHi) of the blob were queued for H2D while the rest was packed
-    double tPack0 = 0, tPack1 = 0, tTbLaunch = 0;   // host times (ms) of the wave: pack start/end, traceback launch
+    bool busy = false;                     // the wave is queued; results not yet unpacked
+    bool fresh = false;                    // prepared (copies + K0) since the last slot_wait: their times are still to be counted
+    double tPack0 = 0, tPack1 = 0, tTbLaunch = 0;   // host times (ms) of the wave: prepare start/end, traceback launch
     // the wave it holds
     int64_t first = 0, count = 0;
-    std::vector<JobInfo> info;
-    std::vector<uint32_t> scriptOff;       // per pair, word offset in the wave's script pool
-    struct Off { size_t blob, row, col; uint32_t script; };
-    std::vector<Off> off;                  // per pair, dimension-only offsets into the pools
-    std::vector<int> bucketCount;
-    size_t blobBytes = 0, metaBytes = 0, orderOff = 0, longOff = 0, tbBaseOff = 0, scriptWords = 0;
+    struct Off { size_t a, b, lb, rb, row, col, sched; uint32_t script; };
+    std::vector<Off> off;                  // per pair, dimension-only offsets (streams, pools)
+    // layout of dIn: [descriptors | stream A | stream B | stream LB | stream RB] copied from the host, then
+    // [traceback offsets | launch order | long-path list | bucket of each pair | schedules | counters | summary] written by K0
+    size_t metaBytes = 0, tbBaseOff = 0, orderOff = 0, longOff = 0, bucketOfOff = 0, schedOff = 0, countersOff = 0, summaryOff = 0;
+    size_t h2dBytes = 0, scriptWords = 0;
+    int maxN = 0, minK = 0, nLongMax = 0;  // dimension facts that bound which kernels the wave can need
+    unsigned launchMask = 0;               // kernel bins whose fill is queued for this wave
+    PlanSummary sum{};                     // what K0 found (read back before the fill is queued)
     int nLong = 0;                         // pairs whose traceback path gets a warp of its own
     int tbLong = TB_LONG;                  // ... those with at least this many moves
-    bool y16 = false;                      // every pair has K*gap_open <= 32767: the kernels' 16-bit weight forms
-    bool ungated = false;                  // every pair is small enough for the fill variant without existence multipliers
+    bool y16 = false;                      // every pair has K*gap_open <= 32767: the 16-bit weight forms of fill_body
     int nValid = 0;
     int binStart[NBINS + 1] = {};
+    bool binOnSide[NBINS] = {};            // the bin's fill kernel was queued on its side stream
 };
 
 // Block scoring (yb_score_blocks): one wave of blocks in flight per stage, two stages so that packing the next
@@ -216,6 +210,11 @@ struct Device {
     double tBase = 0;
     int timeline = 0;
     ScoreConst sc{};                       // the owning context's score tables (kernel arguments)
+    int onlyBins = 0;
+    unsigned recentBins[4] = {0, 0, 0, 0}; // bins that held pairs in the last waves whose summaries came back (ring)
+    int recentAt = 0, summaries = 0;
+    int fillSplit = 2;                     // a wave's fill takes 1/fillSplit of the machine, so that consecutive waves' fills overlap
+    int maxCls = 2, keyedMaxK = 0;         // kernel classes on offer; deepest first profile the KEYED class takes (yb_set_scores)
     int fillBlocks[NBINS] = {};
     int helpers = 1;
     std::unique_ptr<Pool> pool;
@@ -227,7 +226,14 @@ struct Device {
     int64_t errJob = 0;
     bool hasResident = false;
     double t_layout = 0, t_par = 0, t_post = 0, t_reserve = 0, t_wait = 0, t_launch = 0;   // YB_PROFILE breakdown
+    double plan_ms = 0;                    // device time of K0 (plan, scan, scatter)
+    int64_t staged_bytes = 0;              // input bytes that went through a host copy (callers outside yb_host_alloc memory)
+    int64_t firstFailed = -1;              // lowest failing job of the batch on this device
+    std::vector<int64_t> deferred;         // jobs whose traceback matrix did not fit their wave's pool: run again at the end
 };
+
+// The pinned blocks handed out by yb_host_alloc: a caller that builds its jobs inside them is copied from directly.
+struct HostBlock { const unsigned char *base; size_t bytes; };
 
 }  // namespace
 
@@ -239,6 +245,7 @@ struct yb_ctx {
     int maxDepth = 255;
     int maxAbsS = 1;                        // max |S6|
     bool ungatedOk = true;                  // YB_UNGATED=0 keeps the existence multipliers in every fill kernel
+    int slackBulk = 3;                      // YB_SLACK: schedule slack of the shuffle kernels (development)
     int maxCls = 2;                         // highest kernel class handed out: YB_FILL2=0 -> 0 (fill_body only), YB_KEYED=0 -> 1
     int nThreads = 1;
     size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave (steady state)
@@ -248,8 +255,8 @@ struct yb_ctx {
     size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
     int64_t wavePairs = 1 << 20;
     int tbLong = TB_LONG;                   // paths of at least this many moves: warp-per-path traceback (YB_TB_LONG)
-    bool ntStores = true;                   // full-line non-temporal staging stores (YB_NT=0 turns them off)
-    bool earlyH2D = true;                   // a wave's parts are copied while the rest is packed (YB_EARLY_H2D=0 turns it off)
+    bool directCopy = true;                 // inputs inside yb_host_alloc memory are copied from where they are (YB_DIRECT=0: always staged)
+    std::vector<HostBlock> hostBlocks;      // yb_host_alloc
     // results of the last batch
     uint8_t *scriptStore = nullptr;         // pinned (portable): the D2H copies of the waves land here directly
     size_t scriptStoreCap = 0;
@@ -318,32 +325,6 @@ inline void copy_nt64(unsigned char *dst, const unsigned char *src, size_t n) {
             _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + k), _mm_load_si128(reinterpret_cast<const __m128i *>(line + k)));
     }
 }
-inline void pack_band_nt64(uint32_t *dst, const int32_t *lb, const int32_t *rb, int rowsTotal) {
-    int r = 0;
-    for (; r + 16 <= rowsTotal; r += 16)
-        for (int k = 0; k < 16; k += 4) {
-            __m128i l = _mm_loadu_si128(reinterpret_cast<const __m128i *>(lb + r + k));
-            __m128i h = _mm_loadu_si128(reinterpret_cast<const __m128i *>(rb + r + k));
-            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + r + k), _mm_or_si128(l, _mm_slli_epi32(h, 16)));
-        }
-    if (r < rowsTotal) {
-        alignas(64) uint32_t line[16] = {0};
-        for (int k = 0; r + k < rowsTotal; ++k) line[k] = (uint32_t)lb[r + k] | ((uint32_t)rb[r + k] << 16);
-        for (int k = 0; k < 16; k += 4)
-            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + r + k), _mm_load_si128(reinterpret_cast<const __m128i *>(line + k)));
-    }
-}
-// band rows as LB | RB<<16 (both < 65536).  (Non-temporal stores were tried for the staging copies and lost:
-// the sections are small and rarely cache-line aligned, so write-combining buffers flush partially filled.)
-inline void pack_band(uint32_t *dst, const int32_t *lb, const int32_t *rb, int rowsTotal) {
-    int r = 0;
-    for (; r + 4 <= rowsTotal; r += 4) {
-        __m128i l = _mm_loadu_si128(reinterpret_cast<const __m128i *>(lb + r));
-        __m128i h = _mm_loadu_si128(reinterpret_cast<const __m128i *>(rb + r));
-        _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + r), _mm_or_si128(l, _mm_slli_epi32(h, 16)));
-    }
-    for (; r < rowsTotal; ++r) dst[r] = (uint32_t)lb[r] | ((uint32_t)rb[r] << 16);
-}
 
 // one-off variant for work outside a device's pipeline
 template <class F>
@@ -359,13 +340,10 @@ int bin_of(int wmax, int M) {
     if (wmax + 32 <= kBin[4].ring) return 4;
     return -1;
 }
-// the bulk kernels take over the warp-per-pair bins for pairs of class 1 / 2
-inline int bin_of_cls(int bin, int cls) { return (cls >= 1 && bin >= 0 && bin <= 1) ? BULK_BIN0 + 2 * (cls - 1) + bin : bin; }
 int lanes_of(int wmax, int M) {          // wavefront width of the pair's bin (0: no kernel takes it)
     const int b = bin_of(wmax, M);
     return b < 0 ? 0 : 32 * kBin[b].G;
 }
-inline int lg_of(int lanes) { return 31 - __builtin_clz((unsigned)lanes); }
 
 size_t fill_smem(int bin) {
     // rings (RING*16-aligned, hence the slack) + 32 B of mailbox per lane + the queue slot
@@ -379,11 +357,11 @@ size_t fill_smem(int bin) {
 namespace yb {
 template <int RING, int G, int P, bool Y16, bool GATED = true>
 __global__ void __launch_bounds__(G * P * 32)
-yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, const int *__restrict__ binRange,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                  const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
                  const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int gapOpen, int gapExt) {
-    fill_body<RING, G, P, Y16, GATED>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
+    fill_body<RING, G, P, Y16, GATED>(metas, order, binRange, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
 }
 // bulk form (fill_body2): one warp per pair, pairs of kernel class 1 / 2
 #ifndef YB_F2_MINCTAS
@@ -391,17 +369,17 @@ yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ ord
 #endif
 template <int RING, bool KEYED>
 __global__ void __launch_bounds__(F2_WARPS * 32, (RING <= 128 ? YB_F2_MINCTAS : 1))
-yb_fill2_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+yb_fill2_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, const int *__restrict__ binRange,
                 int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                 const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
                 const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int nGO, int gapExt) {
-    fill_body2<RING, KEYED>(metas, order, nPairs, queue, rowPool, colPool, tbPool, tbBase, outs, nGO, gapExt);
+    fill_body2<RING, KEYED>(metas, order, binRange, queue, rowPool, colPool, tbPool, tbBase, outs, nGO, gapExt);
 }
 }  // namespace yb
 
 namespace {
 
-typedef void (*FillFn)(const PairMeta *, const int *, int, int *, const RowRec *, const ColRec *,
+typedef void (*FillFn)(const PairMeta *, const int *, const int *, int *, const RowRec *, const ColRec *,
                        unsigned char *, const unsigned long long *, PairOut *, int, int);
 // ungated: the variant without existence multipliers (bulk bins only), for waves of small enough pairs (Slot::ungated)
 FillFn fill_fn(int bin, bool y16, bool ungated = false) {
@@ -438,7 +416,7 @@ int device_init(Device &d) {
     for (auto &s : d.slots) {
         CUDA_TRY(d, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         for (auto &e : s.ev) CUDA_TRY(d, cudaEventCreate(&e));
-        for (int b = 1; b < NBINS; ++b) {
+        for (int b = 0; b < NBINS; ++b) {
             CUDA_TRY(d, cudaStreamCreateWithFlags(&s.binStream[b], cudaStreamNonBlocking));
             CUDA_TRY(d, cudaEventCreateWithFlags(&s.binDone[b], cudaEventDisableTiming));
         }
@@ -512,378 +490,287 @@ int make_schedule(int M, const int *LB, const int *RB, int B, int *sched) {
     return 8;
 }
 
-// Everything the host needs to know about one job; msg (optional) gets the reference's wording.
-void analyse_one(const yb_ctx *ctx, const yb_job &j, JobInfo &ji, int *sched, char *msg, int msglen) {
-    ji = JobInfo();
-    if (j.K < 1 || j.L < 1 || j.M < 1 || j.N < 1 || !j.A || !j.B || !j.LB || !j.RB) {
-        ji.status = YB_ERR_ARG;
-        if (msg) snprintf(msg, msglen, "bad dimensions K=%d M=%d L=%d N=%d", j.K, j.M, j.L, j.N);
-        return;
-    }
-    // vectorised scan (band_scan.cpp): validation + cells + widest row + schedule in one pass; on a violation
-    // the scalar loop below words the message as the reference does
-    int nSteps = 0, lanes = 0;
-    int64_t cells = yb_band_scan(j.M, j.N, j.LB, j.RB, &ji.wmax, sched, &nSteps, lanes_of, &lanes, &ji.connected);
-    if (cells < 0) {
-        ji.connected = 0;
-        cells = check_band(j.M, j.N, j.LB, j.RB, msg, msglen, &ji.wmax);
-        if (cells < 0) { ji.status = YB_ERR_BAND; return; }
-        lanes = lanes_of(ji.wmax, j.M);                        // (unreachable unless the two scans disagree)
-        if (lanes > 0) nSteps = make_schedule(j.M, j.LB, j.RB, lanes, sched);
-    }
-    ji.cells = cells;
-    if (j.K > ctx->maxDepth || j.L > 255) {
-        ji.status = YB_ERR_LIMIT;
-        if (msg) snprintf(msg, msglen, "profile depth K=%d L=%d exceeds the kernel limit (%d/255 rows)", j.K, j.L, ctx->maxDepth);
-        return;
-    }
-    if (lanes <= 0) {
-        ji.status = YB_ERR_LIMIT;
-        if (msg) snprintf(msg, msglen, "band row of %d cells exceeds the kernel limit (%d)", ji.wmax, kBin[NBINS - 1].ring - 32);
-        return;
-    }
-    ji.bin = bin_of(ji.wmax, j.M);
-    ji.nSteps = nSteps;
-    // Kernel class.  Without existence multipliers (classes 1, 2) a candidate from a node that does not exist (exactly
-    // MININT = -2^30) is charged a gap-open the reference skips.  That cannot change any real value, flag or script as long
-    // as real scores stay within +-2^28 and unreal ones within [-2^31, -2^29): both follow from
-    // (M+N)*K*L*(gap_open+gap_extend+max|S|) < 2^28 and a connected band.  The KEYED class carries
-    // 4*value + priority, hence 2^26; both need every pre-multiplied weight of the bulk row record to fit 16 bits.
-    if (ctx->maxCls >= 1 && ji.bin <= 1 && ji.connected) {
-        const long double work = (long double)((int64_t)j.M + j.N) * j.K * j.L * (ctx->sc.gap_open + ctx->sc.gap_ext + ctx->maxAbsS);
-        const long long w16 = std::max<long long>((long long)j.K * (ctx->sc.gap_open + ctx->sc.gap_ext), 2ll * j.K * ctx->maxAbsS);
-        if (ctx->maxCls >= 2 && 4 * w16 <= 32767 && work < (long double)(1 << 26)) ji.cls = 2;
-        else if (w16 <= 32767 && work < (long double)(1 << 28)) ji.cls = 1;
-        ji.bin = bin_of_cls(ji.bin, ji.cls);
-    }
-}
-
 inline bool dims_ok(const yb_job &j) { return j.K >= 1 && j.L >= 1 && j.M >= 1 && j.N >= 1 && j.A && j.B && j.LB && j.RB; }
-inline int band_fmt(const yb_job &j) { return j.N < 65536 ? 0 : 1; }
-inline size_t sched_ints(const yb_job &j) { return (size_t)((j.M + 31) >> 5); }   // upper bound (B >= 32)
+inline size_t sched_ints(const yb_job &j) { return (size_t)((j.M + 31) >> 5) + 1; }   // upper bound (B >= 32)
 
-// bytes a job takes in the input blob: known from its dimensions alone (wave planning needs no band read)
+// input bytes of a job: known from its dimensions alone (wave planning needs no band read)
 inline size_t blob_bytes(const yb_job &j) {
-    return align_up((size_t)j.K * j.M, 64) + align_up((size_t)j.L * j.N, 64) +
-           align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 64) + align_up(sched_ints(j) * 4, 64);
+    return (size_t)j.K * j.M + (size_t)j.L * j.N + (size_t)(j.M + 1) * 8;
 }
-// Analyse + pack jobs [first, first+count) into the slot's pinned buffer, one pass over the caller's data:
-// everything but the traceback size of a pair follows from its dimensions, so blob / record / script offsets
-// are prefix sums taken up front and each helper validates the band (mz_yama.c:58-71), writes the schedule
-// and copies A, B and the band while they are hot in its cache.  Traceback offsets are assigned afterwards.
-// `maxTb` caps the wave's traceback bytes: the wave is cut short (count shrinks, at least one job stays).
-int slot_pack(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t &count, size_t maxTb,
-              bool earlyH2D = false) {
+
+inline bool in_block(const std::vector<HostBlock> &blocks, const unsigned char *lo, const unsigned char *hi) {
+    for (const HostBlock &b : blocks)
+        if (lo >= b.base && hi <= b.base + b.bytes) return true;
+    return false;
+}
+
+// Lay out jobs [first, first+count) from their DIMENSIONS, queue the host->device copies of their four input streams
+// (A, B, LB, RB: straight from the caller's buffers when those lie in yb_host_alloc memory, through the slot's pinned
+// staging buffer otherwise -- a memcpy either way, no band row is read on the host) and K0 behind them.  Nothing here waits
+// for the device.
+int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t count, size_t tbCapacity, bool allBins = false) {
     const double t0 = now_ms();
     s.tPack0 = t0;
-    // ---- dimension-only layout (serial, a few ns per job) ------------------------------------------------------
-    struct Off { size_t blob, row, col; uint32_t script; };
-    s.off.resize((size_t)count);
-    size_t blob = 0, rows = 0, cols = 0, words = 0;
-    int maxK = 0;
-    int64_t maxWork = 0;                     // max over pairs of (M+N)*K*L: bounds every real score and every drift
+    s.first = first;
+    s.off.resize((size_t)count + 1);
+    // ---- dimension-only layout + the address range of each stream (serial, a few ns per job) -------------------------------
+    struct Stream { const unsigned char *lo = nullptr, *hi = nullptr; size_t payload = 0; bool direct = false; size_t devOff = 0, bytes = 0; };
+    Stream st[4];
+    size_t rows = 0, cols = 0, words = 0, sched = 0;
+    int maxK = 0, maxN = 0, minK = 0x7fffffff, nLongMax = 0;
     for (int64_t i = 0; i < count; ++i) {
         const yb_job &j = jobs[first + i];
-        s.off[(size_t)i] = Slot::Off{blob, rows, cols, (uint32_t)words};
+        Slot::Off &o = s.off[(size_t)i];
+        o.a = st[0].payload; o.b = st[1].payload; o.lb = st[2].payload; o.rb = st[3].payload;
+        o.row = rows; o.col = cols; o.sched = sched; o.script = (uint32_t)words;
         if (!dims_ok(j)) continue;
-        maxK = std::max(maxK, j.K);
-        maxWork = std::max(maxWork, ((int64_t)j.M + j.N) * j.K * j.L);
-        blob += blob_bytes(j); rows += (size_t)j.M + 1; cols += (size_t)j.N + 1;
+        maxK = std::max(maxK, j.K); minK = std::min(minK, j.K); maxN = std::max(maxN, j.N);
+        if (j.M + j.N >= ctx->tbLong) ++nLongMax;
+        const unsigned char *ptr[4] = {j.A, j.B, reinterpret_cast<const unsigned char *>(j.LB), reinterpret_cast<const unsigned char *>(j.RB)};
+        const size_t len[4] = {(size_t)j.K * j.M, (size_t)j.L * j.N, (size_t)(j.M + 1) * 4, (size_t)(j.M + 1) * 4};
+        for (int k = 0; k < 4; ++k) {
+            if (!st[k].lo || ptr[k] < st[k].lo) st[k].lo = ptr[k];
+            if (!st[k].hi || ptr[k] + len[k] > st[k].hi) st[k].hi = ptr[k] + len[k];
+            st[k].payload += align_up(len[k], 64);               // (staged layout: sections of whole 64-byte lines)
+        }
+        rows += (size_t)j.M + 1; cols += (size_t)j.N + 1; sched += sched_ints(j);
         words += ((size_t)j.M + j.N + 15) / 16;
     }
-    s.first = first;
+    s.off[(size_t)count] = Slot::Off{st[0].payload, st[1].payload, st[2].payload, st[3].payload, rows, cols, sched, (uint32_t)words};
     s.y16 = (int64_t)std::min(maxK, ctx->maxDepth) * ctx->sc.gap_open <= 32767;
-    // Without existence multipliers a candidate from a node that does not exist (exactly MININT = -2^30) is charged a
-    // gap-open the reference skips.  That cannot change any real value, flag or script as long as real scores stay
-    // within +-2^28 and unreal ones within [-2^31, -2^29): both follow from (M+N)*K*L*(gap_open+gap_extend+max|S|) < 2^28.
-    s.ungated = ctx->ungatedOk && (long double)maxWork * (ctx->sc.gap_open + ctx->sc.gap_ext + ctx->maxAbsS) < (long double)(1 << 28);
+    s.count = count;
+    s.scriptWords = words;
+    // a stream is copied straight from the caller's memory when that is pinned (yb_host_alloc) and dense enough
     s.metaBytes = align_up((size_t)count * sizeof(PairMeta), 256);
-    s.orderOff = s.metaBytes;
-    s.longOff = s.orderOff + align_up((size_t)count * 4, 256);
-    s.tbBaseOff = s.longOff + align_up((size_t)count * 4, 256);
-    const size_t dataOff = s.tbBaseOff + align_up((size_t)count * 8, 256);   // 64-B aligned: every section is
-    CUDA_TRY(d, s.hIn.reserve(dataOff + blob));
-    s.info.resize((size_t)count);
-    s.scriptOff.resize((size_t)count);
+    size_t devOff = s.metaBytes, stagedBytes = 0;
+    size_t stageOff[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) {
+        Stream &x = st[k];
+        if (!x.lo) { x.devOff = devOff; x.bytes = 0; continue; }
+        const unsigned char *lo = reinterpret_cast<const unsigned char *>(reinterpret_cast<uintptr_t>(x.lo) & ~(uintptr_t)63);
+        const size_t span = (size_t)(x.hi - lo);
+        x.direct = ctx->directCopy && span <= x.payload + x.payload / 2 + 65536 && in_block(ctx->hostBlocks, lo, x.hi);
+        if (x.direct) { x.lo = lo; x.bytes = span; }
+        else { x.bytes = x.payload; stageOff[k] = s.metaBytes + stagedBytes; stagedBytes += align_up(x.payload, 256); }
+        x.devOff = devOff;
+        devOff += align_up(x.bytes, 256) + 256;                    // (slack: K1 reads whole words around a row)
+    }
+    const size_t copied = devOff;
+    s.tbBaseOff = devOff; devOff += align_up((size_t)count * 8, 256);
+    s.orderOff = devOff; devOff += align_up((size_t)count * 4, 256);
+    s.longOff = devOff; devOff += align_up((size_t)count * 4, 256);
+    s.bucketOfOff = devOff; devOff += align_up((size_t)count * 4, 256);
+    s.schedOff = devOff; devOff += align_up(sched * 4, 256);
+    s.countersOff = devOff; devOff += align_up((size_t)(2 * NBINS * NB + 16) * 4, 256);
+    s.summaryOff = devOff; devOff += 256;
+    CUDA_TRY(d, s.hIn.reserve(s.metaBytes + stagedBytes + 256));
+    {
+        const void *before = s.dIn.p;
+        CUDA_TRY(d, s.dIn.reserve(devOff));
+        if (s.dIn.p != before) CUDA_TRY(d, cudaMemsetAsync(s.dIn.p, 0, s.dIn.cap, s.stream));   // (slack bytes are read, never used)
+    }
+    CUDA_TRY(d, s.dOut.reserve((size_t)count * sizeof(PairOut) + 64));
+    CUDA_TRY(d, s.hOut.reserve((size_t)count * sizeof(PairOut) + 64));
+    CUDA_TRY(d, s.hPlan.reserve(256));
+    CUDA_TRY(d, s.dQueue.reserve(64));
     unsigned char *h = static_cast<unsigned char *>(s.hIn.p);
     PairMeta *metas = reinterpret_cast<PairMeta *>(h);
-
     const double t1 = now_ms();
     d.t_layout += t1 - t0;
-    // ---- analyse + pack (parallel) -----------------------------------------------------------------------------
-    std::mutex errMu;
-    // The wave is packed in a few contiguous parts; a part's bytes start their way to the device while the next part
-    // is packed (the header -- metas, launch order, traceback offsets -- and the last part follow in slot_launch_fill).
-    // Without this a wave's copy starts only when all of it is packed: 1.3 ms per 64 MB that the device idles at the
-    // start of a batch.
-    s.sentLo = s.sentHi = 0;
-    const int nParts = (earlyH2D && blob >= ((size_t)4 << 20) && count >= 64) ? 4 : 1;
-    if (nParts > 1) {
-        CUDA_TRY(d, s.dIn.reserve(dataOff + blob));
-        CUDA_TRY(d, cudaEventRecord(s.ev[0], s.stream));
-    }
-    int64_t partLo = 0;
-    for (int part = 0; part < nParts; ++part) {
-        int64_t partHi = count;
-        if (part + 1 < nParts) {                                    // cut by bytes
-            const size_t want = blob / (size_t)nParts * (size_t)(part + 1);
-            partHi = std::lower_bound(s.off.begin() + partLo, s.off.end(), want,
-                                      [](const Slot::Off &o, size_t v) { return o.blob < v; }) - s.off.begin();
-            partHi = std::max(partLo, std::min<int64_t>(partHi, count));
-        }
-        const int64_t base = partLo;
-        // dynamic chunks: 32 pairs when pairs are small, fewer when a part holds only a few (large) pairs
-        const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(32, (partHi - partLo) / (4 * (int64_t)d.helpers)));
-        d.pool->run(partHi - partLo, chunk, [&](int64_t lo0, int64_t hi0) {
-            for (int64_t i = base + lo0; i < base + hi0; ++i) {
-                const yb_job &j = jobs[first + i];
-                JobInfo &ji = s.info[(size_t)i];
-                const Slot::Off &of = s.off[(size_t)i];
-                PairMeta pm;
-                memset(&pm, 0, sizeof pm);
-                s.scriptOff[(size_t)i] = of.script;
-                char msg[256];
-                msg[0] = 0;
-                // the schedule goes straight to its place in the blob (after A, B and the band)
-                size_t o = dataOff + of.blob;
-                const bool dimsOk = dims_ok(j);
-                size_t oA = o, oB = 0, oBand = 0, oSched = 0;
-                if (dimsOk) {
-                    oB = oA + align_up((size_t)j.K * j.M, 64);
-                    oBand = oB + align_up((size_t)j.L * j.N, 64);
-                    oSched = oBand + align_up((size_t)(j.M + 1) * (band_fmt(j) ? 8 : 4), 64);
-                }
-                analyse_one(ctx, j, ji, dimsOk ? reinterpret_cast<int *>(h + oSched) : nullptr, msg, sizeof msg);
-                if (ji.status != YB_OK) {
-                    metas[i] = pm;
-                    std::lock_guard<std::mutex> g(errMu);
-                    if (d.err.empty() || first + i < d.errJob) {
-                        char b[400];
-                        if (ji.status == YB_ERR_BAND) snprintf(b, sizeof b, "%s", msg);   // reference wording
-                        else snprintf(b, sizeof b, "job %lld: %s", (long long)(first + i), msg);
-                        d.err = b;
-                        d.errJob = first + i;
-                    }
-                    continue;
-                }
-                pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
-                pm.offA = oA; pm.offB = oB;
-                if (ctx->ntStores) {
-                    copy_nt64(h + oA, j.A, (size_t)j.K * j.M);
-                    copy_nt64(h + oB, j.B, (size_t)j.L * j.N);
-                } else {
-                    memcpy(h + oA, j.A, (size_t)j.K * j.M);
-                    memcpy(h + oB, j.B, (size_t)j.L * j.N);
-                }
-                pm.offBand = oBand;
-                pm.bandFmt = band_fmt(j);
-                if (pm.bandFmt == 0) {
-                    if (ctx->ntStores) pack_band_nt64(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
-                    else pack_band(reinterpret_cast<uint32_t *>(h + oBand), j.LB, j.RB, j.M + 1);
-                } else {
-                    memcpy(h + oBand, j.LB, (size_t)(j.M + 1) * 4);
-                    memcpy(h + oBand + (size_t)(j.M + 1) * 4, j.RB, (size_t)(j.M + 1) * 4);
-                }
-                pm.offSched = oSched;
-                pm.nSteps = ji.nSteps;
-                pm.lgLanes = lg_of(32 * kBin[ji.bin].G);
-                pm.cls = ji.cls;
-                pm.rowBase = of.row;
-                pm.colBase = of.col;
-                pm.scriptBase = of.script;
-                metas[i] = pm;
-                if (ctx->ntStores) _mm_sfence();
-                {
-                    const int lg = 63 - __builtin_clzll((unsigned long long)std::max<int64_t>(ji.cells, 1));
-                    const int frac = lg >= 2 ? (int)((ji.cells >> (lg - 2)) & 3) : 0;
-                    ji.bucket = ji.bin * NB + (NB - 1 - std::min(NB - 1, lg * 4 + frac));
-                }
-            }
-        });
-        if (part + 1 < nParts && partHi > partLo) {
-            const size_t a = dataOff + s.off[(size_t)partLo].blob;
-            const size_t z = partHi < count ? dataOff + s.off[(size_t)partHi].blob : dataOff + blob;
-            CUDA_TRY(d, cudaMemcpyAsync(static_cast<unsigned char *>(s.dIn.p) + a, h + a, z - a, cudaMemcpyHostToDevice, s.stream));
-            if (s.sentHi == 0) s.sentLo = a;
-            s.sentHi = z;
-        }
-        partLo = partHi;
-    }
 
-    // ---- traceback offsets, wave cut, launch order (serial, O(count)) -----------------------------------------------
-    // launch order: per ring bin, big pairs first (longest-processing-time-first on the warp queue); quarter-octave
-    // buckets of the cell count instead of a comparison sort
+    // ---- pair descriptors (+ staged copies) on the helper threads -------------------------------------------------------
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(256, count / (4 * (int64_t)d.helpers)));
+    d.pool->run(count, chunk, [&](int64_t lo0, int64_t hi0) {
+        for (int64_t i = lo0; i < hi0; ++i) {
+            const yb_job &j = jobs[first + i];
+            const Slot::Off &o = s.off[(size_t)i];
+            PairMeta pm;
+            memset(&pm, 0, sizeof pm);
+            if (dims_ok(j)) {
+                pm.K = j.K; pm.M = j.M; pm.L = j.L; pm.N = j.N;
+                const unsigned char *ptr[4] = {j.A, j.B, reinterpret_cast<const unsigned char *>(j.LB), reinterpret_cast<const unsigned char *>(j.RB)};
+                const size_t len[4] = {(size_t)j.K * j.M, (size_t)j.L * j.N, (size_t)(j.M + 1) * 4, (size_t)(j.M + 1) * 4};
+                const size_t so[4] = {o.a, o.b, o.lb, o.rb};
+                unsigned long long dev[4];
+                for (int k = 0; k < 4; ++k) {
+                    if (st[k].direct) dev[k] = st[k].devOff + (size_t)(ptr[k] - st[k].lo);
+                    else {
+                        dev[k] = st[k].devOff + so[k];
+                        copy_nt64(h + stageOff[k] + so[k], ptr[k], len[k]);
+                    }
+                }
+                pm.offA = dev[0]; pm.offB = dev[1]; pm.offBand = dev[2]; pm.offBand2 = dev[3];
+                pm.offSched = s.schedOff + o.sched * 4;
+                pm.rowBase = o.row; pm.colBase = o.col; pm.scriptBase = o.script;
+                pm.lgLanes = 5;
+            }
+            metas[i] = pm;
+        }
+        _mm_sfence();
+    });
     const double t2 = now_ms();
     d.t_par += t2 - t1;
-    s.bucketCount.assign((size_t)NBINS * NB, 0);
-    size_t tb = 0;
-    int64_t kept = count;
-    unsigned long long *tbBase = reinterpret_cast<unsigned long long *>(h + s.tbBaseOff);
-    for (int64_t i = 0; i < count; ++i) {
-        const JobInfo &ji = s.info[(size_t)i];
-        if (ji.status != YB_OK) continue;
-        const size_t need = (size_t)ji.nSteps * 32 * kBin[ji.bin].G;       // one byte per lane and step
-        if (i > 0 && tb + need > maxTb) { kept = i; break; }
-        tbBase[i] = tb;
-        tb += need;
-        s.bucketCount[(size_t)ji.bucket]++;
-        if (!ji.connected) s.ungated = false;
+
+    // ---- copies + K0 ------------------------------------------------------------------------------------------------------
+    unsigned char *dIn = static_cast<unsigned char *>(s.dIn.p);
+    cudaStream_t q = s.stream;
+    CUDA_TRY(d, cudaEventRecord(s.ev[0], q));
+    CUDA_TRY(d, cudaMemcpyAsync(dIn, h, (size_t)count * sizeof(PairMeta), cudaMemcpyHostToDevice, q));
+    s.h2dBytes = (size_t)count * sizeof(PairMeta);
+    for (int k = 0; k < 4; ++k) {
+        if (!st[k].bytes) continue;
+        const void *src = st[k].direct ? static_cast<const void *>(st[k].lo) : static_cast<const void *>(h + stageOff[k]);
+        CUDA_TRY(d, cudaMemcpyAsync(dIn + st[k].devOff, src, st[k].bytes, cudaMemcpyHostToDevice, q));
+        s.h2dBytes += st[k].bytes;
+        if (!st[k].direct) d.staged_bytes += (int64_t)st[k].bytes;
     }
-    count = kept;
-    s.count = count;
-    if (count < (int64_t)s.off.size()) {           // wave cut short: sizes of the kept prefix
-        const Slot::Off &of = s.off[(size_t)count];
-        blob = of.blob; rows = of.row; cols = of.col; words = of.script;
-    }
-    s.blobBytes = dataOff + blob;
-    s.scriptWords = words;
-    {
-        int *order = reinterpret_cast<int *>(h + s.orderOff);
-        int acc = 0;
-        for (int b = 0; b < NBINS; ++b) {
-            s.binStart[b] = acc;
-            for (int q = 0; q < NB; ++q) { int c = s.bucketCount[(size_t)b * NB + q]; s.bucketCount[(size_t)b * NB + q] = acc; acc += c; }
-        }
-        s.binStart[NBINS] = acc;
-        s.nValid = acc;
-        int *longList = reinterpret_cast<int *>(h + s.longOff);
-        s.nLong = 0;
-        s.tbLong = ctx->tbLong;
-        for (int64_t i = 0; i < count; ++i) {
-            const JobInfo &ji = s.info[(size_t)i];
-            if (ji.status != YB_OK) continue;
-            order[s.bucketCount[(size_t)ji.bucket]++] = (int)i;
-            if (jobs[first + i].M + jobs[first + i].N >= s.tbLong) longList[s.nLong++] = (int)i;
-        }
-    }
-    const double t3 = now_ms();
-    d.t_post += t3 - t2;
-    CUDA_TRY(d, s.dIn.reserve(s.blobBytes));
+    (void)copied;
+    CUDA_TRY(d, cudaEventRecord(s.ev[1], q));
+    // every other buffer of the wave is sized from the dimensions; the traceback pool has a fixed capacity (pairs that do not
+    // fit it any more are deferred by K0 and run again in a later wave)
     CUDA_TRY(d, s.dRow.reserve(rows * sizeof(RowRec) + 64));
     {   // column records sit between two COL_PAD margins (see fill_body2); a fresh buffer is zeroed once so that what idle
         // lanes read there is initialised memory
         const void *before = s.dCol.p;
         CUDA_TRY(d, s.dCol.reserve(cols * sizeof(ColRec) + 2 * COL_PAD + 64));
-        if (s.dCol.p != before) CUDA_TRY(d, cudaMemsetAsync(s.dCol.p, 0, s.dCol.cap, s.stream));
+        if (s.dCol.p != before) CUDA_TRY(d, cudaMemsetAsync(s.dCol.p, 0, s.dCol.cap, q));
     }
-    CUDA_TRY(d, s.dTb.reserve(tb + 256));
+    CUDA_TRY(d, s.dTb.reserve(std::max(tbCapacity, (size_t)1 << 20) + 256));
     CUDA_TRY(d, s.dScript.reserve(words * 4 + 64));
-    CUDA_TRY(d, s.dOut.reserve((size_t)count * sizeof(PairOut) + 64));
-    CUDA_TRY(d, s.dQueue.reserve(64));
     s.scriptDst = ctx->scriptStore + ctx->scriptOff[(size_t)first];   // the wave's scripts, in job order, in the batch store
-    CUDA_TRY(d, s.hOut.reserve((size_t)count * sizeof(PairOut) + 64));
-    d.t_reserve += now_ms() - t3;
+    int *counters = reinterpret_cast<int *>(dIn + s.countersOff);
+    CUDA_TRY(d, cudaMemsetAsync(counters, 0, (size_t)(2 * NBINS * NB + 16) * 4, q));
+    PlanParams pp;
+    for (int b = 0; b < NBINS; ++b) { pp.ring[b] = kBin[b].ring; pp.warps[b] = kBin[b].G; }
+    pp.minRows2 = kBin[2].minRows;
+    pp.maxDepth = ctx->maxDepth; pp.maxCls = ctx->maxCls; pp.maxAbsS = ctx->maxAbsS;
+    pp.gapOpen = ctx->sc.gap_open; pp.gapExt = ctx->sc.gap_ext; pp.tbLong = ctx->tbLong;
+    pp.slackBulk = ctx->slackBulk;
+    s.tbLong = ctx->tbLong;
+    {   // Which kernel bins get a fill launch: those the wave's DIMENSIONS allow (a band row has at most N+1 cells; the KEYED
+        // class needs a shallow first profile) and that recent waves actually used -- an empty launch is not free (0.1 ms
+        // and more each, measured).  A pair whose bin is left out is deferred by K0 and runs again at the end of the batch.
+        const int widest = maxN + 1 + 32;
+        unsigned can = 1u;
+        if (widest > kBin[0].ring) can |= (1u << 1) | (1u << 2);
+        if (widest > kBin[1].ring) can |= 1u << 3;
+        if (widest > kBin[3].ring) can |= 1u << 4;
+        if (d.maxCls >= 1) can |= (1u << BULK_BIN0) | ((can & 2u) ? 1u << (BULK_BIN0 + 1) : 0u);
+        if (d.maxCls >= 2 && minK <= d.keyedMaxK) can |= (1u << (BULK_BIN0 + 2)) | ((can & 2u) ? 1u << (BULK_BIN0 + 3) : 0u);
+        unsigned recent = d.recentBins[0] | d.recentBins[1] | d.recentBins[2] | d.recentBins[3];
+        if (allBins || d.summaries == 0) recent = ~0u;
+        s.launchMask = can & recent;
+        if (d.onlyBins) s.launchMask &= (unsigned)d.onlyBins;                  // (development: YB_ONLY_BINS)
+        if (!s.launchMask) s.launchMask = can & ~0u;
+        pp.launchMask = s.launchMask;
+    }
+    PairOut *outs = static_cast<PairOut *>(s.dOut.p);
+    unsigned long long *tbBase = reinterpret_cast<unsigned long long *>(dIn + s.tbBaseOff);
+    int *bucketOf = reinterpret_cast<int *>(dIn + s.bucketOfOff);
+    int *bucketCount = counters, *bucketFill = counters + NBINS * NB, *longFill = counters + 2 * NBINS * NB;
+    PlanSummary *dsum = reinterpret_cast<PlanSummary *>(dIn + s.summaryOff);
+    if (count > 0) {
+        const int warpsPerCta = PLAN_THREADS / 32;
+        const unsigned blocks = (unsigned)std::min<int64_t>((count + warpsPerCta - 1) / warpsPerCta, (int64_t)d.sms * 8);
+        yb_plan_kernel<<<blocks, PLAN_THREADS, 0, q>>>(reinterpret_cast<PairMeta *>(dIn), (int)count, dIn, outs, tbBase, bucketOf, pp);
+        yb_plan_scan<<<1, 1024, 0, q>>>((int)count, tbBase, bucketOf, bucketCount, bucketFill, outs, reinterpret_cast<PairMeta *>(dIn), dsum, pp.tbLong,
+                                       (unsigned long long)tbCapacity, s.launchMask);
+        yb_plan_scatter<<<(unsigned)((count + 255) / 256), 256, 0, q>>>((int)count, bucketOf, bucketCount, bucketFill, reinterpret_cast<const PairMeta *>(dIn),
+                                                                       reinterpret_cast<int *>(dIn + s.orderOff), reinterpret_cast<int *>(dIn + s.longOff), longFill, pp.tbLong);
+        d.launches += 3;
+    } else {
+        CUDA_TRY(d, cudaMemsetAsync(dsum, 0, sizeof(PlanSummary), q));
+    }
+    CUDA_TRY(d, cudaEventRecord(s.ev[7], q));
+    CUDA_TRY(d, cudaGetLastError());
+    s.maxN = maxN; s.minK = minK; s.nLongMax = nLongMax;
+    d.t_post += now_ms() - t2;
     d.pack_ms += now_ms() - t0;
+    d.h2d_bytes += (int64_t)s.h2dBytes;
+    s.fresh = true;
     s.tPack1 = now_ms();
     return YB_OK;
 }
 
-// Enqueue one wave on its slot's stream.  Nothing here waits for the device.
-// Enqueue H2D, K1 and K2 of one wave on its slot's stream.  Nothing here waits for the device.
-int slot_launch_fill(Device &d, Slot &s, bool h2d) {
+// Enqueue K1, K2, K3 and the result copies of a prepared wave.  The kernels take their pair ranges from K0's summary in
+// device memory, so nothing here waits for the device either: the host never learns the plan before the results arrive.
+int slot_launch(Device &d, Slot &s, bool d2h, int fillSplit = 1) {
     const PairMeta *metas = static_cast<const PairMeta *>(s.dIn.p);
-    const unsigned char *blob = static_cast<const unsigned char *>(s.dIn.p);
+    unsigned char *blob = static_cast<unsigned char *>(s.dIn.p);
     RowRec *rows = static_cast<RowRec *>(s.dRow.p);
     ColRec *cols = reinterpret_cast<ColRec *>(static_cast<unsigned char *>(s.dCol.p) + COL_PAD);
-    unsigned char *tb = static_cast<unsigned char *>(s.dTb.p);
-    PairOut *outs = static_cast<PairOut *>(s.dOut.p);
-    const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
-    int *queue = static_cast<int *>(s.dQueue.p);
-    cudaStream_t st = s.stream;
-    const double tl = now_ms();
-
-    if (h2d && s.sentHi > s.sentLo) {            // part of the blob is already on its way (slot_pack): header + the rest
-        unsigned char *dst = static_cast<unsigned char *>(s.dIn.p);
-        const unsigned char *src = static_cast<const unsigned char *>(s.hIn.p);
-        CUDA_TRY(d, cudaMemcpyAsync(dst, src, std::min(s.sentLo, s.blobBytes), cudaMemcpyHostToDevice, st));
-        if (s.blobBytes > s.sentHi)
-            CUDA_TRY(d, cudaMemcpyAsync(dst + s.sentHi, src + s.sentHi, s.blobBytes - s.sentHi, cudaMemcpyHostToDevice, st));
-    } else {
-        CUDA_TRY(d, cudaEventRecord(s.ev[0], st));
-        if (h2d) CUDA_TRY(d, cudaMemcpyAsync(s.dIn.p, s.hIn.p, s.blobBytes, cudaMemcpyHostToDevice, st));
-    }
-    CUDA_TRY(d, cudaEventRecord(s.ev[1], st));
-    CUDA_TRY(d, cudaMemsetAsync(outs, 0, (size_t)s.count * sizeof(PairOut), st));
-    CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, st));
-    // a script region holds ceil((M+N)/16) words but a path has m_new <= M+N ops: the unwritten tail is copied back too
-    if (s.scriptWords) CUDA_TRY(d, cudaMemsetAsync(s.dScript.p, 0, s.scriptWords * 4, st));
-    if (s.nValid > 0) {
-        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0, d.sc);
-        d.launches++;
-    }
-    CUDA_TRY(d, cudaEventRecord(s.ev[2], st));
-    // The wide-ring bins hold few, long pairs (one warp each): they start first, on their own streams, and the
-    // bulk bin fills the machine around them -- launched back to back they would be a serial tail.
-    for (int b = NBINS - 1; b >= 0; --b) {
-        int n = s.binStart[b + 1] - s.binStart[b];
-        if (n <= 0) continue;
-        const BinCfg &bc = kBin[b];
-        cudaStream_t bs = b == 0 ? st : s.binStream[b];
-        if (b > 0) CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[2], 0));
-        const bool bulk = b >= BULK_BIN0;
-        FillFn fn = bulk ? fill_fn2(b) : fill_fn(b, s.y16, s.ungated);
-        const size_t smem = bulk ? fill2_smem(b) : fill_smem(b);
-        const int blocks = std::min((n + bc.P - 1) / bc.P, d.fillBlocks[b]);
-        fn<<<blocks, bc.G * bc.P * 32, smem, bs>>>(metas, order + s.binStart[b], n, queue + b, rows, cols, tb,
-                                                    reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), outs,
-                                                    bulk ? -d.sc.gap_open * (b >= BULK_BIN0 + 2 ? 4 : 1) : d.sc.gap_open, d.sc.gap_ext);
-        if (b > 0) CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
-        d.launches++;
-    }
-    for (int b = 1; b < NBINS; ++b)
-        if (s.binStart[b + 1] - s.binStart[b] > 0) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[b], 0));
-    CUDA_TRY(d, cudaEventRecord(s.ev[3], st));
-    CUDA_TRY(d, cudaGetLastError());
-    s.filled = true;
-    d.waves++;
-    if (h2d) d.h2d_bytes += (int64_t)s.blobBytes;
-    d.t_launch += now_ms() - tl;
-    return YB_OK;
-}
-
-// Enqueue K3 and the D2H copies of a wave whose fill is already queued.  K3 is bound by the latency of the
-// longest pair's pointer chase, not by throughput, and the fill kernels leave it no registers to co-reside with:
-// launching it once per GROUP of waves, on their own streams at the same time, keeps that latency from being
-// paid once per wave.
-int slot_launch_traceback(Device &d, Slot &s, bool d2h) {
-    const PairMeta *metas = static_cast<const PairMeta *>(s.dIn.p);
-    const unsigned char *blob = static_cast<const unsigned char *>(s.dIn.p);
     unsigned char *tb = static_cast<unsigned char *>(s.dTb.p);
     unsigned *script = static_cast<unsigned *>(s.dScript.p);
     PairOut *outs = static_cast<PairOut *>(s.dOut.p);
     const int *order = reinterpret_cast<const int *>(blob + s.orderOff);
+    const PlanSummary *dsum = reinterpret_cast<const PlanSummary *>(blob + s.summaryOff);
+    const unsigned long long *tbBase = reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff);
+    int *queue = static_cast<int *>(s.dQueue.p);
     cudaStream_t st = s.stream;
     const double tl = now_ms();
-    s.tTbLaunch = tl;
+
+    CUDA_TRY(d, cudaEventRecord(s.ev[2], st));
+    CUDA_TRY(d, cudaMemsetAsync(queue, 0, 64, st));
+    // a script region holds ceil((M+N)/16) words but a path has m_new <= M+N ops: the unwritten tail is copied back too
+    if (s.scriptWords) CUDA_TRY(d, cudaMemsetAsync(s.dScript.p, 0, s.scriptWords * 4, st));
+    if (s.count > 0) {
+        yb_profile_kernel<<<(unsigned)s.count, K1_THREADS, 0, st>>>(metas, blob, rows, cols, s.y16 ? 1 : 0, d.sc);
+        d.launches++;
+    }
+    CUDA_TRY(d, cudaEventRecord(s.ev[3], st));
+    // One fill launch per kernel bin of the wave's launch mask (slot_prepare).
+    // Every bin runs on a stream of its own behind the same event, so that they become runnable together and the hardware
+    // starts them in launch order: the wide bins get their CTAs before the bulk bins' persistent CTAs take the machine.
+    static const int launchOrder[NBINS] = {4, 3, 2, 1, 6, 8, 0, 5, 7};       // wide rings first, the bulk bins last
+    for (int k = 0; k < NBINS && s.count > 0; ++k) {
+        const int b = launchOrder[k];
+        s.binOnSide[b] = false;
+        if (!((s.launchMask >> b) & 1u)) continue;
+        const BinCfg &bc = kBin[b];
+        cudaStream_t bs = s.binStream[b];
+        CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[3], 0));
+        const bool bulk = b >= BULK_BIN0;
+        FillFn fn = bulk ? fill_fn2(b) : fill_fn(b, s.y16, false);
+        const size_t smem = bulk ? fill2_smem(b) : fill_smem(b);
+        const int blocks = (int)std::min<int64_t>((s.count + bc.P - 1) / bc.P, std::max(d.sms, d.fillBlocks[b] / fillSplit));
+        fn<<<blocks, bc.G * bc.P * 32, smem, bs>>>(metas, order, dsum->binStart + b, queue + b, rows, cols, tb, tbBase, outs,
+                                                    bulk ? -d.sc.gap_open * (b >= BULK_BIN0 + 2 ? 4 : 1) : d.sc.gap_open, d.sc.gap_ext);
+        CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
+        s.binOnSide[b] = true;
+        d.launches++;
+    }
+    for (int b = 0; b < NBINS; ++b)
+        if (s.count > 0 && s.binOnSide[b]) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[b], 0));
+    CUDA_TRY(d, cudaEventRecord(s.ev[8], st));
+
+    // K3.  The warp-per-path kernel (issue-bound) runs beside the thread-per-pair kernel (latency-bound), on a side stream.
+    s.tTbLaunch = now_ms();
     CUDA_TRY(d, cudaEventRecord(s.ev[6], st));
-    // the warp-per-path kernel (issue-bound) runs beside the thread-per-pair kernel (latency-bound), on a side stream
-    if (s.nLong > 0) {
+    if (s.nLongMax > 0) {
         cudaStream_t ls = s.binStream[1];
         CUDA_TRY(d, cudaStreamWaitEvent(ls, s.ev[6], 0));
-        yb_traceback_long_kernel<<<(unsigned)((s.nLong + 3) / 4), 128, 0, ls>>>(
-            metas, reinterpret_cast<const int *>(blob + s.longOff), s.nLong, blob, tb,
-            reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs);
+        yb_traceback_long_kernel<<<(unsigned)((s.nLongMax + 3) / 4), 128, 0, ls>>>(
+            metas, reinterpret_cast<const int *>(blob + s.longOff), &dsum->nLong, blob, tb, tbBase, script, outs);
         CUDA_TRY(d, cudaEventRecord(s.binDone[1], ls));
         d.launches++;
     }
-    if (s.nValid > s.nLong) {
-        yb_traceback_kernel<<<(unsigned)((s.nValid + 127) / 128), 128, 0, st>>>(
-            metas, order, s.nValid, blob, tb, reinterpret_cast<const unsigned long long *>(blob + s.tbBaseOff), script, outs,
-            s.tbLong);
+    if (s.count > 0) {
+        yb_traceback_kernel<<<(unsigned)((s.count + 127) / 128), 128, 0, st>>>(metas, order, &dsum->nValid, blob, tb, tbBase, script, outs, s.tbLong);
         d.launches++;
     }
-    if (s.nLong > 0) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[1], 0));
+    if (s.nLongMax > 0) CUDA_TRY(d, cudaStreamWaitEvent(st, s.binDone[1], 0));
     CUDA_TRY(d, cudaEventRecord(s.ev[4], st));
+    CUDA_TRY(d, cudaMemcpyAsync(s.hPlan.p, dsum, sizeof(PlanSummary), cudaMemcpyDeviceToHost, st));
     if (d2h) {
         CUDA_TRY(d, cudaMemcpyAsync(s.hOut.p, s.dOut.p, (size_t)s.count * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
         if (s.scriptWords)
             CUDA_TRY(d, cudaMemcpyAsync(s.scriptDst, s.dScript.p, s.scriptWords * 4, cudaMemcpyDeviceToHost, st));
+        d.d2h_bytes += (int64_t)((size_t)s.count * sizeof(PairOut) + s.scriptWords * 4);
     }
     CUDA_TRY(d, cudaEventRecord(s.ev[5], st));
     CUDA_TRY(d, cudaGetLastError());
-    s.filled = false;
     s.busy = true;
-    if (d2h) d.d2h_bytes += (int64_t)((size_t)s.count * sizeof(PairOut) + s.scriptWords * 4);
+    d.waves++;
     d.t_launch += now_ms() - tl;
     return YB_OK;
 }
@@ -902,21 +789,30 @@ int slot_wait(Device &d, Slot &s) {
     CUDA_TRY(d, cudaStreamSynchronize(s.stream));
     d.t_wait += now_ms() - tw;
     CUDA_TRY(d, cudaGetLastError());
-    float h = 0, a = 0, b = 0, c = 0, e = 0;
-    cudaEventElapsedTime(&h, s.ev[0], s.ev[1]);
-    cudaEventElapsedTime(&a, s.ev[1], s.ev[2]);
-    cudaEventElapsedTime(&b, s.ev[2], s.ev[3]);
+    float h = 0, k0 = 0, a = 0, b = 0, c = 0, e = 0;
+    if (s.fresh) { cudaEventElapsedTime(&h, s.ev[0], s.ev[1]); cudaEventElapsedTime(&k0, s.ev[1], s.ev[7]); s.fresh = false; }
+    cudaEventElapsedTime(&a, s.ev[2], s.ev[3]);
+    cudaEventElapsedTime(&b, s.ev[3], s.ev[8]);
     cudaEventElapsedTime(&c, s.ev[6], s.ev[4]);
     cudaEventElapsedTime(&e, s.ev[4], s.ev[5]);
-    d.h2d_ms += h; d.profile_ms += a; d.fill_ms += b; d.tb_ms += c; d.d2h_ms += e;
-    d.kernel_ms += a + b + c;
+    d.h2d_ms += h; d.plan_ms += k0; d.profile_ms += a; d.fill_ms += b; d.tb_ms += c; d.d2h_ms += e;
+    d.kernel_ms += k0 + a + b + c;
+    s.sum = *static_cast<const PlanSummary *>(s.hPlan.p);           // K0's summary came back with the results
+    {
+        unsigned used = 0;
+        for (int b = 0; b < NBINS; ++b) if (s.sum.binStart[b + 1] > s.sum.binStart[b]) used |= 1u << b;
+        d.recentBins[d.recentAt] = used;
+        d.recentAt = (d.recentAt + 1) & 3;
+        ++d.summaries;
+    }
+    if (s.sum.firstFailed >= 0 && (d.firstFailed < 0 || s.first + s.sum.firstFailed < d.firstFailed)) d.firstFailed = s.first + s.sum.firstFailed;
     if (d.timeline && d.evBase) {           // YB_PROFILE=2: where this wave sat on the device's and the host's clocks
-        float t[7] = {0};
-        const int idx[7] = {0, 1, 2, 3, 6, 4, 5};
-        for (int k = 0; k < 7; ++k) cudaEventElapsedTime(&t[k], d.evBase, s.ev[idx[k]]);
-        fprintf(stderr, "yama_b200[timeline] dev %d wave %3d pairs %6lld | host: pack %.2f-%.2f tb-launch %.2f wait-done %.2f | device: h2d %.2f-%.2f "
-                "K1 -%.2f K2 -%.2f | K3 %.2f-%.2f d2h -%.2f\n", d.id, d.waves, (long long)s.count, s.tPack0 - d.tBase, s.tPack1 - d.tBase,
-                s.tTbLaunch - d.tBase, now_ms() - d.tBase, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+        float t[9] = {0};
+        const int idx[9] = {0, 1, 7, 2, 3, 8, 6, 4, 5};
+        for (int k = 0; k < 9; ++k) cudaEventElapsedTime(&t[k], d.evBase, s.ev[idx[k]]);
+        fprintf(stderr, "yama_b200[timeline] dev %d wave %3d pairs %6lld | host: prepare %.2f-%.2f tb-launch %.2f wait-done %.2f | device: h2d %.2f-%.2f "
+                "K0 -%.2f | K1 %.2f-%.2f K2 -%.2f | K3 %.2f-%.2f d2h -%.2f\n", d.id, d.waves, (long long)s.count, s.tPack0 - d.tBase, s.tPack1 - d.tBase,
+                s.tTbLaunch - d.tBase, now_ms() - d.tBase, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
     }
     s.busy = false;
     return YB_OK;
@@ -932,15 +828,13 @@ void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
         for (int64_t i = lo; i < hi; ++i) {
             const int64_t g = s.first + i;
             yb_result &r = results[g];
-            const JobInfo &ji = s.info[(size_t)i];
-            memset(&r, 0, sizeof r);
-            r.status = ji.status;
-            r.cells = ji.cells;
-            if (ji.status != YB_OK) { ++f; continue; }
-            c += ji.cells;
             const PairOut &o = outs[i];
-            r.status = o.status;
-            if (o.status != YB_OK) ++f;
+            memset(&r, 0, sizeof r);
+            r.status = o.status;                       // K0: YB_ERR_ARG / _BAND / _LIMIT (or deferred); K3: YB_ERR_TRACEBACK
+            r.cells = o.cells;
+            if (o.status == YB_DEFERRED) { r.C = o.C; continue; }          // runs again (device_run), with o.C MiB of traceback
+            if (o.status != YB_OK) { ++f; if (o.status != YB_ERR_TRACEBACK) continue; }
+            else c += o.cells;
             r.m_new = o.m_new; r.C = o.C; r.D = o.D; r.I = o.I;
             // the device's 2-bit codes are the ABI's script format and the D2H copy put them in place
             r.script = ctx->scriptStore + ctx->scriptOff[(size_t)g];
@@ -949,6 +843,9 @@ void slot_unpack(yb_ctx *ctx, Device &d, Slot &s, yb_result *results) {
     });
     d.cells += cells.load();
     d.failed += failed.load();
+    if (s.sum.nDeferred > 0)
+        for (int64_t i = 0; i < s.count; ++i)
+            if (outs[i].status == YB_DEFERRED) d.deferred.push_back(s.first + i);
     d.unpack_ms += now_ms() - t0;
 }
 
@@ -958,6 +855,7 @@ void reset_stats(Device &d) {
     d.launches = d.waves = 0;
     d.err.clear();
     d.errJob = 0;
+    d.plan_ms = 0; d.staged_bytes = 0; d.firstFailed = -1; d.deferred.clear();
     d.t_layout = d.t_par = d.t_post = d.t_reserve = d.t_wait = d.t_launch = 0;
 }
 
@@ -972,6 +870,8 @@ void collect_stats(yb_ctx *ctx, yb_stats *st, double total_ms, int64_t cells, in
         st->h2d_bytes += d.h2d_bytes;
         st->d2h_bytes += d.d2h_bytes;
         st->kernel_launches += d.launches;
+        st->plan_ms = std::max(st->plan_ms, d.plan_ms);
+        st->staged_bytes += d.staged_bytes;
     }
     st->fill_ms = ctx->devs[0].fill_ms;
     st->profile_ms = ctx->devs[0].profile_ms;
@@ -1027,7 +927,8 @@ struct Dispatcher {
         lo = cursor;
         const int round = handed / ndev;
         size_t target = std::min(maxBytes, minBytes << std::min(round, 16));           // ramp up
-        target = std::min(target, std::max(tailBytes, remaining / (size_t)(2 * ndev))); // ramp down
+        // (no ramp down: a small wave's fill is as long as its longest pair, and nothing on the host waits for the last one)
+        if (ndev > 1) target = std::min(target, std::max(tailBytes, remaining / (size_t)ndev));      // ... but devices share the end
         // Large pairs (wide bands, deep profiles: a megabyte each) run one CTA per pair, and the device wants a few
         // hundred of them in flight: such a wave is sized by pairs, up to 8x the byte target (cfg5: +50 % end to end).
         const int64_t wantPairs = std::min<int64_t>(kWavePairsWanted, (int64_t)32 << std::min(round, 3));
@@ -1057,53 +958,67 @@ struct Dispatcher {
     }
 };
 
-// One device's share of a batch: grab waves until none are left.  A wave's fill (H2D, K1, K2) is queued as soon as
-// it is packed; tracebacks and D2H copies are queued for TB_GROUP waves at a time; a slot is unpacked when the
-// ring comes back to it (NSLOTS waves later) or at the end.
+// One device's share of a batch: grab waves until none are left.  Every wave is queued in one go on its slot's stream
+// (copies, K0, K1, K2, K3, result copies); a slot is waited for and unpacked when the ring comes back to it, NSLOTS waves
+// later, or at the end.  Pairs that K0 deferred (their traceback matrix no longer fitted their wave's pool) run again at the
+// end, one per wave, with a pool of their own size.
 int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
     if (cudaSetDevice(d.id) != cudaSuccess) { d.err = "cudaSetDevice failed"; return YB_ERR_CUDA; }
-    int rc = YB_OK, next = 0, nFilled = 0;
-    int filledSlots[NSLOTS];
+    int rc = YB_OK, next = 0;
     if (const char *e = getenv("YB_PROFILE")) d.timeline = atoi(e) >= 2;
     if (d.timeline) {
         if (!d.evBase) cudaEventCreate(&d.evBase);
         d.tBase = now_ms();
         cudaEventRecord(d.evBase, d.slots[0].stream);
     }
-    int64_t lo = 0, hi = 0;                      // jobs grabbed but not yet packed
-    auto flush_group = [&]() -> int {
-        for (int k = 0; k < nFilled; ++k) {
-            int r2 = slot_launch_traceback(d, d.slots[filledSlots[k]], true);
-            if (r2 != YB_OK) return r2;
-        }
-        nFilled = 0;
-        return YB_OK;
-    };
-    for (;;) {
-        if (lo >= hi && !disp.grab(lo, hi)) break;
+    int64_t lo = 0, hi = 0;
+    while (disp.grab(lo, hi)) {
         Slot &s = d.slots[next];
-        if (s.filled && (rc = flush_group()) != YB_OK) break;     // (only if NSLOTS < 2*TB_GROUP)
-        if (s.busy) {                            // the wave launched NSLOTS rounds ago
+        if (s.busy) {                            // the wave that used this slot NSLOTS rounds ago
             if ((rc = slot_wait(d, s)) != YB_OK) break;
             slot_unpack(ctx, d, s, results);
         }
-        int64_t count = hi - lo;
-        if ((rc = slot_pack(ctx, d, s, disp.jobs, lo, count, ctx->waveTbBytes, ctx->earlyH2D)) != YB_OK) break;
-        lo += count;
-        if ((rc = slot_launch_fill(d, s, true)) != YB_OK) break;
-        filledSlots[nFilled++] = next;
+        if ((rc = slot_prepare(ctx, d, s, disp.jobs, lo, hi - lo, ctx->waveTbBytes)) != YB_OK) break;
+        // a wave's fill is as long as its longest pair whatever its size: with half the machine per wave, the fills of
+        // consecutive waves overlap instead (measured on cfg2: 13.8 -> 12.7 ms end to end)
+        if ((rc = slot_launch(d, s, true, d.fillSplit)) != YB_OK) break;
         next = (next + 1) % NSLOTS;
-        if (nFilled == TB_GROUP && (rc = flush_group()) != YB_OK) break;
     }
-    if (rc == YB_OK) rc = flush_group();
     for (int k = 0; k < NSLOTS; ++k) {           // drain, oldest first
         Slot &s = d.slots[(next + k) % NSLOTS];
-        if (s.filled) { cudaStreamSynchronize(s.stream); s.filled = false; }
         if (!s.busy) continue;
         int r2 = slot_wait(d, s);
         if (r2 != YB_OK) { if (rc == YB_OK) rc = r2; continue; }
         if (rc == YB_OK) slot_unpack(ctx, d, s, results);
     }
+    // Deferred pairs (rare): their bin had no fill launch in their wave, or the wave's traceback pool was full.  They run
+    // again as waves of their own -- every bin launched, traceback pool sized for the largest of them -- through a gathered
+    // copy of their jobs; results and scripts land where the first attempt would have put them.
+    for (int attempt = 0; attempt < 3 && rc == YB_OK && !d.deferred.empty(); ++attempt) {
+        std::vector<int64_t> again;
+        again.swap(d.deferred);
+        std::sort(again.begin(), again.end());
+        size_t needMax = 0;
+        for (int64_t g : again) needMax = std::max(needMax, ((size_t)std::max(1, results[g].C) + 1) << 20);
+        const size_t cap = std::max(ctx->waveTbBytes, needMax);
+        size_t k = 0;
+        while (k < again.size() && rc == YB_OK) {
+            // contiguous runs of job indices form a wave (scripts go to the batch store by job index)
+            size_t e = k + 1, tbSum = ((size_t)std::max(1, results[again[k]].C) + 1) << 20;
+            while (e < again.size() && again[e] == again[e - 1] + 1) {
+                const size_t nb = ((size_t)std::max(1, results[again[e]].C) + 1) << 20;
+                if (tbSum + nb > cap || e - k >= 65536) break;
+                tbSum += nb; ++e;
+            }
+            Slot &s = d.slots[0];
+            if ((rc = slot_prepare(ctx, d, s, disp.jobs, again[k], (int64_t)(e - k), cap, true)) != YB_OK) break;
+            if ((rc = slot_launch(d, s, true)) != YB_OK) break;
+            if ((rc = slot_wait(d, s)) != YB_OK) break;
+            slot_unpack(ctx, d, s, results);
+            k = e;
+        }
+    }
+    if (rc == YB_OK && !d.deferred.empty()) { d.err = "a pair's traceback matrix does not fit the device"; rc = YB_ERR_LIMIT; }
     return rc;
 }
 
@@ -1153,6 +1068,20 @@ int prepare_script_store(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
         ctx->scriptStoreCap = want;
     }
     return YB_OK;
+}
+
+// the message of a pair the device flagged, in the reference's wording where it has one
+void describe_failure(yb_ctx *ctx, const yb_job &j, int64_t index, int status) {
+    char msg[256];
+    msg[0] = 0;
+    if (status == YB_ERR_TRACEBACK) { set_err(ctx, "Error generating edit script."); return; }
+    if (!dims_ok(j)) { set_err(ctx, "job %lld: bad dimensions K=%d M=%d L=%d N=%d", (long long)index, j.K, j.M, j.L, j.N); return; }
+    int wmax = 0;
+    if (check_band(j.M, j.N, j.LB, j.RB, msg, sizeof msg, &wmax) < 0) { set_err(ctx, "%s", msg); return; }   // reference wording
+    if (j.K > ctx->maxDepth || j.L > 255)
+        set_err(ctx, "job %lld: profile depth K=%d L=%d exceeds the kernel limit (%d/255 rows)", (long long)index, j.K, j.L, ctx->maxDepth);
+    else
+        set_err(ctx, "job %lld: band row of %d cells exceeds the kernel limit (%d)", (long long)index, wmax, kBin[4].ring - 32);
 }
 
 template <class F>
@@ -1207,17 +1136,20 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_WAVE_MB")) ctx->waveInBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_MIN_MB")) ctx->waveMinBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_TAIL_MB")) ctx->waveTailBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
-    {   // traceback bytes per wave: an eighth of the smallest device's free memory (NSLOTS waves can be in flight)
-        size_t cap = (size_t)24 << 30;
+    {   // traceback pool of a wave (one per slot, NSLOTS slots per device): 4 GB, less on a small or crowded device.  A
+        // wave whose pairs need more has the overflowing pairs deferred by K0 and run again at the end (device_run).
+        size_t cap = (size_t)4 << 30;
         for (auto &d : ctx->devs) {
             size_t fr = 0, tot = 0;
-            if (cudaSetDevice(d.id) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess) cap = std::min(cap, fr / 8);
+            if (cudaSetDevice(d.id) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess) cap = std::min(cap, fr / (3 * NSLOTS));
         }
-        ctx->waveTbBytes = std::max<size_t>(cap, (size_t)256 << 20);
+        ctx->waveTbBytes = std::max<size_t>(cap, (size_t)64 << 20);
     }
     if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
-    if (const char *e = getenv("YB_NT")) ctx->ntStores = atoi(e) != 0;
-    if (const char *e = getenv("YB_EARLY_H2D")) ctx->earlyH2D = atoi(e) != 0;
+    if (const char *e = getenv("YB_DIRECT")) ctx->directCopy = atoi(e) != 0;
+    if (const char *e = getenv("YB_ONLY_BINS")) for (auto &d : ctx->devs) d.onlyBins = (int)strtol(e, nullptr, 0);
+    if (const char *e = getenv("YB_FILL_SPLIT")) for (auto &d : ctx->devs) d.fillSplit = std::max(1, atoi(e));
+    if (const char *e = getenv("YB_SLACK")) ctx->slackBulk = std::max(1, atoi(e));
     if (const char *e = getenv("YB_UNGATED")) ctx->ungatedOk = atoi(e) != 0;
     if (const char *e = getenv("YB_KEYED")) if (atoi(e) == 0) ctx->maxCls = std::min(ctx->maxCls, 1);
     if (const char *e = getenv("YB_FILL2")) if (atoi(e) == 0) ctx->maxCls = 0;
@@ -1237,7 +1169,7 @@ void yb_destroy(yb_ctx *ctx) {
         cudaSetDevice(d.id);
         for (auto &s : d.slots) {
             for (DevBuf *b : {&s.dIn, &s.dRow, &s.dCol, &s.dTb, &s.dScript, &s.dOut, &s.dQueue}) b->release();
-            for (PinBuf *b : {&s.hIn, &s.hOut}) b->release();
+            for (PinBuf *b : {&s.hIn, &s.hOut, &s.hPlan}) b->release();
             for (auto &e : s.ev) if (e) cudaEventDestroy(e);
             for (auto &e : s.binDone) if (e) cudaEventDestroy(e);
             for (auto &b : s.binStream) if (b) cudaStreamDestroy(b);
@@ -1250,7 +1182,27 @@ void yb_destroy(yb_ctx *ctx) {
         }
     }
     if (ctx->scriptStore) cudaFreeHost(ctx->scriptStore);
+    for (auto &b : ctx->hostBlocks) cudaFreeHost(const_cast<unsigned char *>(b.base));
     delete ctx;
+}
+
+void *yb_host_alloc(yb_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    void *p = nullptr;
+    const size_t want = align_up(bytes + 512, 4096);               // (slack: copies are rounded to whole 64-byte lines)
+    if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    ctx->hostBlocks.push_back(HostBlock{static_cast<const unsigned char *>(p), want});
+    return p;
+}
+
+void yb_host_free(yb_ctx *ctx, void *p) {
+    if (!ctx || !p) return;
+    for (size_t k = 0; k < ctx->hostBlocks.size(); ++k)
+        if (ctx->hostBlocks[k].base == p) {
+            ctx->hostBlocks.erase(ctx->hostBlocks.begin() + (long)k);
+            cudaFreeHost(p);
+            return;
+        }
 }
 
 const char *yb_last_error(const yb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
@@ -1297,7 +1249,11 @@ int yb_set_scores(yb_ctx *ctx, const int32_t *ss, const int32_t *gop, int32_t ga
     // 16-bit weights in the kernels: sum-of-pairs weights K*max|S6| and the extension weight K*gap_extend
     ctx->maxDepth = std::min(255, 32767 / std::max(maxabs, std::max(1, (int)gap_extend)));
     ctx->maxAbsS = maxabs;
-    for (auto &d : ctx->devs) d.sc = sc;
+    {   // deepest first profile whose weights still fit 16 bits times 4 (the KEYED class, see yb_plan_kernel)
+        const long long per = std::max<long long>((long long)GO + gap_extend, 2ll * maxabs);
+        const int keyedMaxK = (int)std::min<long long>(255, 32767 / (4 * std::max<long long>(per, 1)));
+        for (auto &d : ctx->devs) { d.sc = sc; d.maxCls = ctx->maxCls; d.keyedMaxK = keyedMaxK; }
+    }
     ctx->scoresSet = true;
     return YB_OK;
 }
@@ -1370,18 +1326,19 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
                     "launch %.2f wait %.2f unpack %.2f | device: h2d %.2f kernels %.2f d2h %.2f\n", d.id, d.waves, now_ms() - t0, d.pack_ms,
                     d.t_layout, d.t_par, d.t_post, d.t_reserve, d.t_launch, d.t_wait, d.unpack_ms, d.h2d_ms, d.kernel_ms, d.d2h_ms);
     if (rc != YB_OK) return rc;
-    // per-pair failures: report the first in job order, in the reference's wording where it has one
-    int64_t failed = 0;
-    for (auto &d : ctx->devs) failed += d.failed;
+    // per-pair failures: report the first in job order, in the reference's wording where it has one (the device only
+    // flags a pair; the words come from the scalar restatement of mz_yama.c:58-71 on that one pair)
+    int64_t failed = 0, firstBad = -1;
+    for (auto &d : ctx->devs) {
+        failed += d.failed;
+        if (d.firstFailed >= 0 && (firstBad < 0 || d.firstFailed < firstBad)) firstBad = d.firstFailed;
+    }
     if (failed == 0) return YB_OK;                  // (the usual case: no scan of the results)
-    for (int64_t i = 0; i < n; ++i)
-        if (results[i].status != YB_OK) {
-            bool have = false;
-            for (auto &d : ctx->devs) if (!d.err.empty()) { ctx->err = d.err; have = true; break; }
-            if (!have || results[i].status == YB_ERR_TRACEBACK) set_err(ctx, "Error generating edit script.");
-            return results[i].status;
-        }
-    return YB_OK;
+    if (firstBad < 0 || results[firstBad].status == YB_OK)
+        for (firstBad = 0; firstBad < n && results[firstBad].status == YB_OK; ++firstBad) {}
+    if (firstBad >= n) return YB_OK;
+    describe_failure(ctx, jobs[firstBad], firstBad, results[firstBad].status);
+    return results[firstBad].status;
 }
 
 int yb_resident_load(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
@@ -1390,38 +1347,37 @@ int yb_resident_load(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
     ctx->resJobs.assign(jobs, jobs + n);
     if (prepare_script_store(ctx, n, jobs) != YB_OK) { set_err(ctx, "cudaHostAlloc failed for the script store"); return YB_ERR_CUDA; }
     for (auto &d : ctx->devs) { reset_stats(d); d.hasResident = false; }
-    // static, cell-balanced split: needs every pair's cell count first
-    std::vector<int64_t> cells((size_t)n, 0);
-    std::atomic<int> bad{0};
-    parallel_for(ctx->nThreads, n, 256, [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            JobInfo ji;
-            analyse_one(ctx, jobs[i], ji, nullptr, nullptr, 0);
-            cells[(size_t)i] = ji.cells;
-            if (ji.status != YB_OK) bad.store(1);
-        }
-    });
-    if (bad.load()) { set_err(ctx, "yb_resident_load: the batch holds invalid pairs (use yb_run_batch for per-pair status)"); return YB_ERR_ARG; }
-    ctx->resCells = 0;
-    for (auto c : cells) ctx->resCells += c;
+    // static split over the devices by a dimension-only cost (rows + columns of a pair; the bands are only read on the device)
+    std::vector<int64_t> cost((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) cost[(size_t)i] = dims_ok(jobs[i]) ? 64ll * ((int64_t)jobs[i].M + 1) : 0;
     const int ndev = (int)ctx->devs.size();
     ctx->resSplit.assign((size_t)ndev + 1, 0);
-    plan_split(n, cells.data(), ndev, ctx->resSplit.data());
-    return for_each_device(ctx, [&](int di) -> int {
+    plan_split(n, cost.data(), ndev, ctx->resSplit.data());
+    int rc = for_each_device(ctx, [&](int di) -> int {
         Device &d = ctx->devs[(size_t)di];
         if (cudaSetDevice(d.id) != cudaSuccess) return (int)YB_ERR_CUDA;
         int64_t lo = ctx->resSplit[(size_t)di], cnt = ctx->resSplit[(size_t)di + 1] - lo;
         if (cnt <= 0) return (int)YB_OK;
         Slot &s = d.slots[0];
-        const int64_t want = cnt;
-        int rc = slot_pack(ctx, d, s, ctx->resJobs.data(), lo, cnt, (size_t)-1);
-        if (rc != YB_OK) return rc;
-        if (cnt != want) { d.err = "resident batch does not fit"; return (int)YB_ERR_LIMIT; }
-        CUDA_TRY(d, cudaMemcpyAsync(s.dIn.p, s.hIn.p, s.blobBytes, cudaMemcpyHostToDevice, s.stream));
+        // (the whole share in one wave: its traceback pool is as large as the device allows)
+        size_t fr = 0, tot = 0;
+        CUDA_TRY(d, cudaMemGetInfo(&fr, &tot));
+        int rc2 = slot_prepare(ctx, d, s, ctx->resJobs.data(), lo, cnt, fr / 2, true);
+        if (rc2 != YB_OK) return rc2;
+        PlanSummary sum;
+        CUDA_TRY(d, cudaMemcpyAsync(&sum, static_cast<unsigned char *>(s.dIn.p) + s.summaryOff, sizeof sum, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(d, cudaStreamSynchronize(s.stream));
+        s.sum = sum;
+        if (sum.nFailed) { d.err = "yb_resident_load: the batch holds invalid pairs (use yb_run_batch for per-pair status)"; return (int)YB_ERR_ARG; }
+        if (sum.nDeferred) { d.err = "resident batch does not fit"; return (int)YB_ERR_LIMIT; }
+        s.launchMask = 0;
+        for (int b = 0; b < NBINS; ++b) if (sum.binStart[b + 1] > sum.binStart[b]) s.launchMask |= 1u << b;
         d.hasResident = true;
         return (int)YB_OK;
     });
+    ctx->resCells = 0;
+    for (auto &d : ctx->devs) if (d.hasResident) ctx->resCells += d.slots[0].sum.cells;
+    return rc;
 }
 
 int yb_resident_step(yb_ctx *ctx, yb_stats *stats) {
@@ -1436,8 +1392,7 @@ int yb_resident_step(yb_ctx *ctx, yb_stats *stats) {
             return (int)YB_ERR_ARG;
         }
         if (cudaSetDevice(d.id) != cudaSuccess) return (int)YB_ERR_CUDA;
-        int r = slot_launch_fill(d, d.slots[0], false);
-        if (r == YB_OK) r = slot_launch_traceback(d, d.slots[0], false);
+        int r = slot_launch(d, d.slots[0], false);
         if (r != YB_OK) return r;
         return slot_wait(d, d.slots[0]);
     });

@@ -46,27 +46,27 @@ struct ScoreConst {
 struct PairMeta {
     int K, M, L, N;
     unsigned long long offA, offB;     // byte offsets into the input blob
-    unsigned long long offBand;        // byte offset into the input blob: the band of rows 0..M, see bandFmt
+    unsigned long long offBand;        // byte offset into the input blob: LB[0..M] as the caller's ints (mz_yama.h:14-16)
+    unsigned long long offBand2;       // ... RB[0..M]
     unsigned long long offSched;       // byte offset into the input blob: wavefront schedule, ceil(M/32) ints
     unsigned long long rowBase;        // index of row 0's RowRec in the RowRec pool (M+1 records)
     unsigned long long colBase;        // index of column 0's ColRec in the ColRec pool (N+1 records)
     unsigned long long scriptBase;     // 32-bit word index of this pair's packed script (ceil((M+N)/16) words)
     // (the byte offset of the pair's traceback matrix depends on the band, not only on the dimensions: it lives in a
     //  separate per-wave array so that the host can fill the metas in parallel, before those offsets are known)
-    int nSteps;                        // wavefront steps of this pair (host computed from the schedule)
-    int bandFmt;                       // 0: M+1 words LB | RB<<16 (N < 65536);  1: M+1 ints LB, then M+1 ints RB
+    int nSteps;                        // wavefront steps of this pair (K0, from the schedule)
+    int pad;
     int lgLanes;                       // log2 of the wavefront width: 32 lanes (one warp) ... 256 lanes (a CTA) per pair
     int cls;                           // kernel class: 0 fill_body (RowRec / ColRec), 1 fill_body2, 2 fill_body2 KEYED (RowRec2 / bulk ColRec)
 };
 
-// LB[r] / RB[r] of a pair, whichever way the host packed them
+// LB[r] / RB[r] of a pair
 struct BandView {
-    const unsigned *w;
-    int fmt, M;
+    const int *lbp, *rbp;
     __device__ __forceinline__ BandView(const unsigned char *blob, const PairMeta &pm)
-        : w(reinterpret_cast<const unsigned *>(blob + pm.offBand)), fmt(pm.bandFmt), M(pm.M) {}
-    __device__ __forceinline__ int lb(int r) const { return fmt ? (int)__ldg(w + r) : (int)(__ldg(w + r) & 0xffffu); }
-    __device__ __forceinline__ int rb(int r) const { return fmt ? (int)__ldg(w + M + 1 + r) : (int)(__ldg(w + r) >> 16); }
+        : lbp(reinterpret_cast<const int *>(blob + pm.offBand)), rbp(reinterpret_cast<const int *>(blob + pm.offBand2)) {}
+    __device__ __forceinline__ int lb(int r) const { return __ldg(lbp + r); }
+    __device__ __forceinline__ int rb(int r) const { return __ldg(rbp + r); }
 };
 
 // Row record, 64 B (4 x 16 B).  av* are byte-count vectors matched against the column words (see
@@ -100,7 +100,7 @@ __device__ __forceinline__ unsigned long long tb_byte(unsigned lane, unsigned t,
 //  w3 = w0 zeroed for c==1            (mz_yama.c:173, no gap-open at the start)
 struct __align__(16) ColRec { unsigned w0, w1, w2, w3; };
 
-struct PairOut { int m_new, C, D, I, status, pad; };
+struct PairOut { int m_new, C, D, I, status, pad; long long cells; };   // cells, status: K0; the rest: K2 / K3
 
 __device__ __forceinline__ int classify(unsigned ch) {
     unsigned u = ch | 0x20u;
@@ -318,11 +318,14 @@ __device__ __forceinline__ int pick3(int x, int y, int z, bool exists, unsigned 
 //       one dp2a with 16-bit weights instead of dp4a/extract + imad.
 template <int RING, int G, int P, bool Y16, bool GATED = true>
 __device__ __forceinline__ void
-fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase, const int *__restrict__ binRange,
           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
           const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
           const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, const int gapOpen, const int gapExt) {
     static_assert(G == 1 || P == 1, "several groups per CTA only for warp-sized groups");
+    // the bin's slice of the launch order: [binRange[0], binRange[1]) as K0 left it in device memory (the host never sees it)
+    const int *order = orderBase + __ldg(binRange);
+    const int nPairs = __ldg(binRange + 1) - __ldg(binRange);
     constexpr int B = 32 * G;                                     // lanes of the wavefront
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [ P rings of RING records | P x B lanes x 2 mailbox records | queue slot ]; rings are RING*16-aligned
@@ -677,11 +680,13 @@ constexpr size_t COL_PAD = 32768;                             // bytes of slack 
 
 template <int RING, bool KEYED>
 __device__ __forceinline__ void
-fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase, const int *__restrict__ binRange,
            int *__restrict__ queue, const RowRec *__restrict__ rowPool,
            const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
            const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, const int nGO, const int gapExt) {
     // nGO: -gap_open * SC, from the host (a kernel parameter is an operand, not an instruction)
+    const int *order = orderBase + __ldg(binRange);                // the bin's slice of the launch order, as K0 left it
+    const int nPairs = __ldg(binRange + 1) - __ldg(binRange);
     constexpr int B = 32, P = F2_WARPS;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int SC = KEYED ? 4 : 1;                         // every weight is multiplied by SC
@@ -711,7 +716,6 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ order, in
         unsigned char *tb = tbPool + __ldg(tbBase + p);
         const int KGE = pm.K * gapExt * SC;
         const int nSteps = pm.nSteps;
-        const int N16 = pm.N * 16;
         // the I node's y and z weights on (ndB, b10): K*ndB opens and K*b10 opens (mz_yama.c:131-137), extension folded in;
         // on the last row only the extension is charged (mz_yama.c:123)
         const unsigned cYI = pack16(pm.K * nGO - KGE, 0), cZI = pack16(-KGE, pm.K * nGO), cLast = pack16(-KGE, 0);
@@ -892,12 +896,12 @@ constexpr int TB_LONG = 2048;       // paths of at least this many moves get a w
                                     // kernel is bound by instruction issue, so only where the pointer chase is critical)
 
 __global__ void __launch_bounds__(128)
-yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, int nPairs,
+yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, const int *__restrict__ nPairsPtr,
                     const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
                     const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
                     PairOut *__restrict__ outs, int tbLong) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nPairs) return;
+    if (idx >= __ldg(nPairsPtr)) return;
     const int p = order[idx];
     const PairMeta pm = metas[p];
     if (pm.M + pm.N >= tbLong) return;                  // walked by yb_traceback_long_kernel, one warp per pair
@@ -962,13 +966,13 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
 // the walk finds them in L2 (measured: 20 000-move paths 5.7 -> 2.2 ms).
 constexpr int TB_FAN = 8;
 __global__ void __launch_bounds__(128)
-yb_traceback_long_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ longList, int nLong,
+yb_traceback_long_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ longList, const int *__restrict__ nLongPtr,
                          const unsigned char *__restrict__ blob, const unsigned char *__restrict__ tbPool,
                          const unsigned long long *__restrict__ tbBase, unsigned *__restrict__ scriptPool,
                          PairOut *__restrict__ outs) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= nLong) return;
+    if (w >= __ldg(nLongPtr)) return;
     const int p = longList[w];
     const PairMeta pm = metas[p];
     const unsigned decode = pm.cls == 2 ? TB_DECODE_KEYED : TB_DECODE_FLAGS;

@@ -17,7 +17,7 @@ ABI_SYMBOLS = (
     "yb_create", "yb_destroy", "yb_last_error", "yb_device_count", "yb_set_scores",
     "yb_run_batch", "yb_resident_load", "yb_resident_step", "yb_resident_fetch",
     "yb_submit", "yb_flush", "yb_fetch", "yb_clear", "yb_assemble", "yb_check_band", "yb_plan_split", "yb_pair_facts", "yb_script_unpack",
-    "yb_score_blocks",
+    "yb_score_blocks", "yb_host_alloc", "yb_host_free",
 )
 
 
@@ -45,7 +45,8 @@ class yb_stats(C.Structure):
                 ("pack_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_int64),
                 ("pairs", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("kernel_launches", C.c_int32), ("n_devices", C.c_int32), ("fill_ms", C.c_double),
-                ("profile_ms", C.c_double), ("traceback_ms", C.c_double)]
+                ("profile_ms", C.c_double), ("traceback_ms", C.c_double), ("plan_ms", C.c_double),
+                ("staged_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -93,6 +94,10 @@ def load_library():
     lib.yb_last_error.restype = C.c_char_p
     lib.yb_device_count.argtypes = [C.c_void_p]
     lib.yb_device_count.restype = C.c_int
+    lib.yb_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
+    lib.yb_host_alloc.restype = C.c_void_p
+    lib.yb_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.yb_host_free.restype = None
     lib.yb_set_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     lib.yb_set_scores.restype = C.c_int
     lib.yb_run_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(yb_stats)]
@@ -209,6 +214,26 @@ class YamaB200:
         rc = self.lib.yb_set_scores(self.h, ss.ctypes.data, gop.ctypes.data, int(gap_extend))
         if rc != 0:
             raise self._err(rc)
+
+    # ---- pinned host memory (yb_host_alloc) -------------------------------------------------
+    def host_array(self, nbytes: int) -> np.ndarray:
+        """A uint8 array over a pinned block of the context: inputs built inside it are copied to the device as they
+        are, without a pass over them on the host.  Lives until close()."""
+        p = self.lib.yb_host_alloc(self.h, max(1, int(nbytes)))
+        if not p:
+            raise YamaError(-1, "yb_host_alloc failed")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(1, int(nbytes)),))
+
+    def pin_pools(self, jobs: np.ndarray, pools) -> np.ndarray:
+        """jobs whose A / B / LB / RB pointers point into the four contiguous arrays `pools` (as tools.synth.SynthBatch
+        lays them out) -> the same jobs over pinned copies of those arrays."""
+        out = jobs.copy()
+        for name, arr in zip(("A", "B", "LB", "RB"), pools):
+            raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+            dst = self.host_array(raw.nbytes)
+            dst[:raw.nbytes] = raw
+            out[name] = jobs[name] - np.uint64(arr.ctypes.data) + np.uint64(dst.ctypes.data)
+        return out
 
     # ---- batch -----------------------------------------------------------------------------
     @staticmethod

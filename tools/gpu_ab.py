@@ -55,6 +55,19 @@ for var in variants:
     nfail = int((rr["status"] != 0).sum())
     csum = int(rr["C"].astype(np.int64).sum()), int(rr["m_new"].astype(np.int64).sum())
     print(f"[{var or 'default'}] parity {'OK' if bad == 0 else 'FAIL %d/%d' % (bad, len(want))} | fill {f[0]:.3f} ms = {sb.cells / f[0] / 1e6:.1f} GCUPS | prof {f[1]:.3f} tb {f[2]:.3f} all {f[3]:.3f} ms = {sb.cells / f[3] / 1e6:.1f} GCUPS | failed {nfail} checksum {csum}", flush=True)
+    # end to end through yb_run_batch: inputs in ordinary memory (one staging copy on the host), then in yb_host_alloc memory
+    resbuf = np.zeros(len(sb.jobs), dtype=res.dtype)
+    for tag, jb in (("staged", sb.jobs), ("pinned", ctx.pin_pools(sb.jobs, (sb.A, sb.B, sb.LB, sb.RB)))):
+        walls = []
+        for it in range(5):
+            t0 = time.perf_counter()
+            r2, st2 = ctx.run_batch(jb, out=resbuf, check=False)
+            walls.append((time.perf_counter() - t0) * 1e3)
+        w = float(np.mean(walls[2:]))
+        same = bool((r2["C"] == rr["C"]).all() and (r2["m_new"] == rr["m_new"]).all() and (r2["status"] == 0).all())
+        dd = st2.as_dict()
+        print(f"   e2e {tag}: {w:.2f} ms = {sb.cells / w / 1e6:.1f} GCUPS | host prepare {dd['pack_ms']:.2f} h2d {dd['h2d_ms']:.2f} plan {dd['plan_ms']:.2f} kernels {dd['kernel_ms']:.2f} d2h {dd['d2h_ms']:.2f} | "
+              f"h2d {dd['h2d_bytes'] / 1e6:.0f} MB staged {dd['staged_bytes'] / 1e6:.0f} MB | same results {same}", flush=True)
     ctx.close()
     for k in keys:
         del os.environ[k]
