@@ -181,6 +181,7 @@ struct Slot {
     size_t h2dBytes = 0, scriptWords = 0;
     int maxN = 0, minK = 0, nLongMax = 0;  // dimension facts that bound which kernels the wave can need
     unsigned launchMask = 0;               // kernel bins whose fill is queued for this wave
+    int gridHint[NBINS] = {};              // pairs to size a bin's grid for (0: unknown, a full grid)
     PlanSummary sum{};                     // what K0 found (read back before the fill is queued)
     int nLong = 0;                         // pairs whose traceback path gets a warp of its own
     int tbLong = TB_LONG;                  // ... those with at least this many moves
@@ -212,6 +213,7 @@ struct Device {
     ScoreConst sc{};                       // the owning context's score tables (kernel arguments)
     int onlyBins = 0;
     unsigned recentBins[4] = {0, 0, 0, 0}; // bins that held pairs in the last waves whose summaries came back (ring)
+    int recentCount[4][NBINS] = {};        // ... and how many
     int recentAt = 0, summaries = 0;
     int fillSplit = 2;                     // a wave's fill takes 1/fillSplit of the machine, so that consecutive waves' fills overlap
     int maxCls = 2, keyedMaxK = 0;         // kernel classes on offer; deepest first profile the KEYED class takes (yb_set_scores)
@@ -663,6 +665,13 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
         if (d.onlyBins) s.launchMask &= (unsigned)d.onlyBins;                  // (development: YB_ONLY_BINS)
         if (!s.launchMask) s.launchMask = can & ~0u;
         pp.launchMask = s.launchMask;
+        // grids: a bin that held few pairs lately gets few CTAs (the kernels are persistent: a short grid only means more
+        // pairs per CTA should the guess be low) -- a full grid of a bin with three pairs keeps the bulk bin off the SMs
+        for (int b = 0; b < NBINS; ++b) {
+            int m = 0;
+            for (int k = 0; k < 4; ++k) m = std::max(m, d.recentCount[k][b]);
+            s.gridHint[b] = (allBins || d.summaries == 0) ? 0 : 2 * m + 8 * kBin[b].P;
+        }
     }
     PairOut *outs = static_cast<PairOut *>(s.dOut.p);
     unsigned long long *tbBase = reinterpret_cast<unsigned long long *>(dIn + s.tbBaseOff);
@@ -732,7 +741,8 @@ int slot_launch(Device &d, Slot &s, bool d2h, int fillSplit = 1) {
         const bool bulk = b >= BULK_BIN0;
         FillFn fn = bulk ? fill_fn2(b) : fill_fn(b, s.y16, false);
         const size_t smem = bulk ? fill2_smem(b) : fill_smem(b);
-        const int blocks = (int)std::min<int64_t>((s.count + bc.P - 1) / bc.P, std::max(d.sms, d.fillBlocks[b] / fillSplit));
+        const int64_t pairsGuess = s.gridHint[b] > 0 ? std::min<int64_t>(s.count, s.gridHint[b]) : s.count;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((pairsGuess + bc.P - 1) / bc.P, std::max(d.sms, d.fillBlocks[b] / fillSplit)));
         fn<<<blocks, bc.G * bc.P * 32, smem, bs>>>(metas, order, dsum->binStart + b, queue + b, rows, cols, tb, tbBase, outs,
                                                     bulk ? -d.sc.gap_open * (b >= BULK_BIN0 + 2 ? 4 : 1) : d.sc.gap_open, d.sc.gap_ext);
         CUDA_TRY(d, cudaEventRecord(s.binDone[b], bs));
@@ -800,7 +810,10 @@ int slot_wait(Device &d, Slot &s) {
     s.sum = *static_cast<const PlanSummary *>(s.hPlan.p);           // K0's summary came back with the results
     {
         unsigned used = 0;
-        for (int b = 0; b < NBINS; ++b) if (s.sum.binStart[b + 1] > s.sum.binStart[b]) used |= 1u << b;
+        for (int b = 0; b < NBINS; ++b) {
+            d.recentCount[d.recentAt][b] = s.sum.binStart[b + 1] - s.sum.binStart[b];
+            if (d.recentCount[d.recentAt][b] > 0) used |= 1u << b;
+        }
         d.recentBins[d.recentAt] = used;
         d.recentAt = (d.recentAt + 1) & 3;
         ++d.summaries;
@@ -1371,7 +1384,10 @@ int yb_resident_load(yb_ctx *ctx, int64_t n, const yb_job *jobs) {
         if (sum.nFailed) { d.err = "yb_resident_load: the batch holds invalid pairs (use yb_run_batch for per-pair status)"; return (int)YB_ERR_ARG; }
         if (sum.nDeferred) { d.err = "resident batch does not fit"; return (int)YB_ERR_LIMIT; }
         s.launchMask = 0;
-        for (int b = 0; b < NBINS; ++b) if (sum.binStart[b + 1] > sum.binStart[b]) s.launchMask |= 1u << b;
+        for (int b = 0; b < NBINS; ++b) {
+            s.gridHint[b] = sum.binStart[b + 1] - sum.binStart[b];
+            if (s.gridHint[b] > 0) s.launchMask |= 1u << b;
+        }
         d.hasResident = true;
         return (int)YB_OK;
     });
