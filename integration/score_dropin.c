@@ -22,19 +22,73 @@ double ref_mafScoreRange(struct mafAli *maf, int start, int size);    /* the ref
 /* yama_dropin.cpp */
 int yb_dropin_score_mode(void);                                       /* 0: host function, 1: skip (speculative pass), 2: GPU */
 double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size);
+double mafScoreRange(struct mafAli *maf, int start, int size);
 
 /* mafWrite (maf.h, maf.c:251-284; maf.c is compiled with -DmafWrite=ref_mafWrite): formatting a block costs an
  * fprintf per row; a speculative pass's output goes nowhere, so it is not produced.  The real pass writes as ever. */
 void ref_mafWrite(FILE *f, struct mafAli *maf);
+
+/* ---- deferred output (yama_dropin.cpp, the single-pass driver) -------------------------------------------------------
+ * In the deferred pass yama() answers with a PLACEHOLDER alignment: every column of A and of B once and in order, its
+ * residues replaced by the byte YB_MARK.  mafBuild (mz_preyama.c:38-81) turns it into a block whose rows, names, starts and
+ * sizes are already the final ones -- they depend on which residues a row holds, not on where the gaps go -- and the
+ * host hands that block to mafWrite(stdout, .).  Here it is recognised by its marker, copied (duplicate_ali, maf.c:463)
+ * and kept with its position in the output stream; when the batch has been aligned, yb_defer_emit() gives the copy its
+ * real text, scores it (mafScoreRange, mz_scores.c:124) and writes it with the reference's own mafWrite. */
+#define YB_MARK 1
+int yb_dropin_defer_active(void);
+void yb_dropin_defer_block(void *ali_copy);
+
+static int is_placeholder(const struct mafAli *maf) {
+    const struct mafComp *c = maf ? maf->components : NULL;
+    const char *t;
+    if (c == NULL || c->text == NULL) return 0;
+    for (t = c->text; *t == '-'; ++t) {}
+    return *t == YB_MARK;
+}
+
 void mafWrite(FILE *f, struct mafAli *maf) {
     static int keep = -1;
     if (keep < 0) keep = getenv("YB_SPEC_WRITE") != NULL;        /* measurement knob: format in speculative passes too */
     if (!keep && yb_dropin_score_mode() == 1) return;
+    if (yb_dropin_defer_active() && is_placeholder(maf)) {
+        if (f != stdout) fatal("yama_b200: a merged block is written to a file other than stdout");
+        yb_dropin_defer_block(duplicate_ali(maf));
+        return;
+    }
     ref_mafWrite(f, maf);
+}
+
+/* Give a captured block its alignment (al: m_new columns of W bytes, as yama() returns them: column-major) and write it.
+ * Rows of the alignment that hold no residue were dropped by mafBuild (mz_preyama.c:67-70): the block's components are
+ * the remaining rows, in order.  Returns 0, or -1 if the rows do not match the block. */
+int yb_defer_emit(FILE *f, void *ali_copy, const unsigned char *al, int m_new, int W) {
+    struct mafAli *a = (struct mafAli *)ali_copy;
+    struct mafComp *c = a->components;
+    int r, j;
+    for (r = 0; r < W; ++r) {
+        int any = 0;
+        for (j = 0; j < m_new && !any; ++j) any = al[(size_t)j * W + r] != '-';
+        if (!any) continue;
+        if (c == NULL) return -1;
+        free(c->text);
+        c->text = (char *)malloc((size_t)m_new + 1);
+        if (c->text == NULL) fatal("yama_b200: out of memory");
+        for (j = 0; j < m_new; ++j) c->text[j] = (char)al[(size_t)j * W + r];
+        c->text[m_new] = 0;
+        c = c->next;
+    }
+    if (c != NULL) return -1;
+    a->textSize = m_new;
+    a->score = mafScoreRange(a, 0, m_new);                           /* mz_preyama.c:79 */
+    ref_mafWrite(f, a);
+    mafAliFree(&a);
+    return 0;
 }
 
 double mafScoreRange(struct mafAli *maf, int start, int size) {
     const int mode = yb_dropin_score_mode();
+    if (yb_dropin_defer_active() && is_placeholder(maf)) return 0.0;     /* scored when it has its real text (yb_defer_emit) */
     if (mode == 0) return ref_mafScoreRange(maf, start, size);
     /* the reference's checks, in its order and wording (mz_scores.c:130-134) */
     if (start < 0 || size <= 0 || start + size > maf->textSize)

@@ -40,6 +40,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <malloc.h>
 #include <stdio_ext.h>
 #include <sys/socket.h>
@@ -66,12 +67,18 @@ void yb_host_exit(int code) __attribute__((noreturn));
 FILE *yb_host_fopen(const char *path, const char *mode);
 // block scoring, called by score_dropin.c (the `mafScoreRange` symbol)
 int yb_dropin_score_mode(void);
+// deferred output (score_dropin.c holds the part that walks the reference's structs)
+int yb_dropin_defer_active(void);
+void yb_dropin_defer_block(void *ali_copy);
+int yb_defer_emit(FILE *f, void *ali_copy, const unsigned char *al, int m_new, int W);
+// the tool that was linked in: multiz.c defines multiz(), multic.c does not
+int multiz(void *, void *, FILE *, FILE *, int) __attribute__((weak));
 double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size);
 }
 
 namespace {
 
-enum Mode { DIRECT, RECORD, REPLAY };
+enum Mode { DIRECT, RECORD, REPLAY, DEFER };
 
 struct Key {
     uint64_t a, b;
@@ -112,8 +119,9 @@ struct Globals {
     int pipe_w = -1;
     std::vector<uint8_t> wbuf;
     std::unordered_map<Key, int, KeyHash> shipped;
-    uchar **lastDummy = nullptr;
-    int lastDummyRows = 0, lastDummyCols = 0;
+    uchar **lastDummy = nullptr;           // the placeholder answered last: a later call whose B is this very table, with these
+    int lastDummyRows = 0, lastDummyCols = 0;   // dimensions AND this content, is the chained call of v=0 (an address alone
+    uint32_t lastDummySum = 0;                  // proves nothing: the host frees the table and malloc hands it out again)
     uint64_t nTainted = 0, nShipped = 0, nHits = 0, collisions = 0;
     // parent side
     std::vector<uint8_t> arena;
@@ -133,6 +141,28 @@ struct Globals {
     bool debug = false;
     std::unordered_map<Key, int, KeyHash> failedKeys;   // debug: batch status of jobs that did not align
 } G;
+
+// ---- deferred output (YB_DROPIN=defer, the default): ONE pass of the host for v=1 --------------------------------------
+// The host's own loop (multiz.c:60-177 / multic.c:124-196 with mz_preyama.c) runs once, in this process.  yama() keeps a
+// copy of every job and answers with a placeholder alignment (see score_dropin.c); what the host prints to stdout goes to
+// a memory file, and a merged block is not printed but remembered with its position in that stream.  When main() is done
+// all jobs are aligned in one batch and the stream is written out with the merged blocks, now real, at their places: the
+// bytes and their order are the reference's, the host ran once, and nothing was forked.
+// v=0 (mz_preyama.c:265-335: a second yama() on the first one's output) takes one speculative pass for the first stage
+// (a forked child, as in batch mode), then this pass for the second.
+struct DeferJob { int32_t K, M, L, N; size_t offA, offB, offLB, offRB; Key key; };
+struct DeferBlock { int64_t job; long pos; void *ali; };
+struct Defer {
+    bool active = false, done = false;
+    bool chained = false;                // v=0: calls come in pairs, the second consumes the first one's answer
+    uint64_t callInPair = 0;
+    std::vector<uint8_t> arena;
+    std::vector<DeferJob> jobs;
+    std::vector<DeferBlock> blocks;
+    int64_t lastJob = -1;
+    int savedStdout = -1, memFd = -1;
+    double emit_ms = 0;
+} D;
 
 // ---- streamed replay (YB_DROPIN=stream) ------------------------------------------------------------------------
 // The real pass starts at once in the parent and runs BESIDE the speculative child instead of after it: a reader
@@ -225,6 +255,8 @@ void crc_init() {
         for (int t = 1; t < 8; ++t) g_crcTab[t][i] = (g_crcTab[t - 1][i] >> 8) ^ g_crcTab[0][g_crcTab[t - 1][i] & 0xffu];
 }
 uint32_t crc32c(uint32_t crc, const void *p, size_t n) {
+    static const bool once = (crc_init(), true);
+    (void)once;
     const uint8_t *s = static_cast<const uint8_t *>(p);
     crc = ~crc;
     while (n >= 8) {                                   // slicing-by-8
@@ -239,8 +271,6 @@ uint32_t crc32c(uint32_t crc, const void *p, size_t n) {
     return ~crc;
 }
 Proof proof_of(int K, int M, int L, int N, const uint8_t *A, const uint8_t *B, const int *LB, const int *RB) {
-    static const bool once = (crc_init(), true);
-    (void)once;
     Proof p;
     p.K = K; p.M = M; p.L = L; p.N = N;
     const uint32_t text = crc32c(crc32c(0x59414d41u, A, (size_t)K * M), B, (size_t)L * N);
@@ -473,6 +503,12 @@ int backend_batch(int64_t n, const yb_job *jobs, yb_result *res, yb_stats *st, c
     return yb_run_batch(G.ctx, n, jobs, res, st);
 }
 
+bool is_last_dummy(uchar **B, int L, int N) {
+    if (!G.lastDummy || B != G.lastDummy || L != G.lastDummyRows || N != G.lastDummyCols) return false;
+    for (int i = 2; i <= N; ++i) if (B[i] != B[i - 1] + L) return false;           // (ours are contiguous)
+    return crc32c(0x44554d59u, B[1], (size_t)L * N) == G.lastDummySum;
+}
+
 // allocate the reference's output shape: caller frees AL[1] and AL+1 (mz_yama.h:17-18)
 uchar **alloc_al(int m_new, int W) {
     uchar **al = static_cast<uchar **>(malloc(sizeof(uchar *) * (size_t)(m_new > 0 ? m_new : 1)));
@@ -569,8 +605,126 @@ void emit_dummy(const yb_job &job, uchar ***OAL, int *OM) {
     G.lastDummy = al;
     G.lastDummyRows = W;
     G.lastDummyCols = m_new;
+    G.lastDummySum = crc32c(0x44554d59u, al[1], (size_t)W * m_new);
     *OAL = al;
     *OM = m_new;
+}
+
+// the deferred pass's placeholder: like emit_dummy, residues replaced by the marker byte of score_dropin.c
+constexpr uchar DEFER_MARK = 1;
+void emit_placeholder(const yb_job &job, uchar ***OAL, int *OM) {
+    const int m_new = job.M > job.N ? job.M : job.N, W = job.K + job.L;
+    uchar **al = alloc_al(m_new, W);
+    for (int i = 1; i <= m_new; ++i) {
+        uchar *c = al[i];
+        for (int k = 0; k < job.K; ++k) c[k] = (i <= job.M && job.A[(size_t)(i - 1) * job.K + k] != '-') ? DEFER_MARK : (uchar)'-';
+        for (int l = 0; l < job.L; ++l) c[job.K + l] = (i <= job.N && job.B[(size_t)(i - 1) * job.L + l] != '-') ? DEFER_MARK : (uchar)'-';
+    }
+    G.lastDummy = al;
+    G.lastDummyRows = W;
+    G.lastDummyCols = m_new;
+    G.lastDummySum = crc32c(0x44554d59u, al[1], (size_t)W * m_new);
+    *OAL = al;
+    *OM = m_new;
+}
+
+void defer_record(const Key &key, const yb_job &j) {
+    DeferJob q;
+    q.K = j.K; q.M = j.M; q.L = j.L; q.N = j.N; q.key = key;
+    auto put = [&](const void *src, size_t bytes) {
+        const size_t off = (D.arena.size() + 15) & ~(size_t)15;
+        D.arena.resize(off + bytes);
+        memcpy(D.arena.data() + off, src, bytes);
+        return off;
+    };
+    q.offA = put(j.A, (size_t)j.K * j.M);
+    q.offB = put(j.B, (size_t)j.L * j.N);
+    q.offLB = put(j.LB, (size_t)(j.M + 1) * 4);
+    q.offRB = put(j.RB, (size_t)(j.M + 1) * 4);
+    D.jobs.push_back(q);
+    D.lastJob = (int64_t)D.jobs.size() - 1;
+}
+
+// stdout of the host goes to a memory file while the deferred pass runs
+void defer_begin() {
+    fflush(stdout);
+    D.savedStdout = dup(1);
+    D.memFd = memfd_create("yama_b200_stdout", 0);
+    if (D.savedStdout < 0 || D.memFd < 0 || dup2(D.memFd, 1) < 0) fatalf("yama_b200: cannot capture stdout (%s)", strerror(errno));
+    D.active = true;
+}
+
+// Align everything the pass recorded and write the captured stream with the merged blocks in place.
+void defer_finish() {
+    if (!D.active || D.done) return;
+    D.done = true;
+    const double t0 = now_ms();
+    fflush(stdout);                                           // (the host may have fclose()d stdout itself: multiz.c:288-291
+                                                              //  does when out1/out2 are not given; our descriptor stays)
+    struct stat sb;
+    const off_t total = fstat(D.memFd, &sb) == 0 ? sb.st_size : 0;
+    std::vector<char> text((size_t)(total > 0 ? total : 0));
+    if (total > 0 && pread(D.memFd, text.data(), (size_t)total, 0) != (ssize_t)total) fatalf("yama_b200: cannot read the captured stdout");
+    dup2(D.savedStdout, 1);                                   // fd 1 is the caller's again
+    FILE *out = fdopen(D.savedStdout, "w");                   // ... and so is this stream (stdout itself may be closed)
+    if (!out) fatalf("yama_b200: cannot reopen stdout");
+    __fsetlocking(out, FSETLOCKING_BYCALLER);
+    close(D.memFd);
+    G.mode = REPLAY;                                          // (block scoring below uses the real function)
+    D.active = false;
+    // ---- one batch ------------------------------------------------------------------------------------------------------
+    const size_t n = D.jobs.size();
+    std::vector<yb_job> jobs(n);
+    for (size_t i = 0; i < n; ++i) {
+        const DeferJob &q = D.jobs[i];
+        jobs[i].K = q.K; jobs[i].M = q.M; jobs[i].L = q.L; jobs[i].N = q.N;
+        jobs[i].A = D.arena.data() + q.offA; jobs[i].B = D.arena.data() + q.offB;
+        jobs[i].LB = reinterpret_cast<const int32_t *>(D.arena.data() + q.offLB);
+        jobs[i].RB = reinterpret_cast<const int32_t *>(D.arena.data() + q.offRB);
+    }
+    std::vector<yb_result> res(n);
+    if (n > 0) {
+        yb_stats st;
+        const double tb = now_ms();
+        const int rc = backend_batch((int64_t)n, jobs.data(), res.data(), &st, D.arena.data(), D.arena.size());
+        G.gpu_ms += now_ms() - tb;
+        G.kernel_ms += st.kernel_ms; G.cells += st.cells; G.jobs += (int64_t)n; ++G.batches;
+        if (rc != YB_OK) {
+            // the reference would have died inside the failing yama() call, after writing everything before it
+            size_t bad = 0;
+            while (bad < n && res[bad].status == YB_OK) ++bad;
+            long upto = (long)text.size();
+            for (const DeferBlock &b : D.blocks) if (b.job >= (int64_t)bad) { upto = b.pos; break; }
+            std::vector<uchar> al;
+            long at = 0;
+            for (const DeferBlock &b : D.blocks) {
+                if (b.job >= (int64_t)bad) break;
+                fwrite(text.data() + at, 1, (size_t)(b.pos - at), out);
+                at = b.pos;
+                al.resize((size_t)res[b.job].m_new * (size_t)(jobs[b.job].K + jobs[b.job].L) + 1);
+                if (yb_assemble(&jobs[b.job], &res[b.job], al.data()) == YB_OK)
+                    yb_defer_emit(out, b.ali, al.data(), res[b.job].m_new, jobs[b.job].K + jobs[b.job].L);
+            }
+            fwrite(text.data() + at, 1, (size_t)(upto - at), out);
+            fflush(out);
+            fail_from_status(bad < n ? res[bad].status : rc);
+        }
+    }
+    // ---- the stream, with the merged blocks where the host printed their placeholders ---------------------------------------
+    std::vector<uchar> al;
+    long at = 0;
+    for (const DeferBlock &b : D.blocks) {
+        fwrite(text.data() + at, 1, (size_t)(b.pos - at), out);
+        at = b.pos;
+        const yb_job &j = jobs[(size_t)b.job];
+        const yb_result &r = res[(size_t)b.job];
+        al.resize((size_t)r.m_new * (size_t)(j.K + j.L) + 1);
+        if (yb_assemble(&j, &r, al.data()) != YB_OK || yb_defer_emit(out, b.ali, al.data(), r.m_new, j.K + j.L) != 0)
+            fatalf("new_align: edit script does not consume both alignments (M=%d, N=%d, M_new=%d)", j.M, j.N, r.m_new);
+    }
+    fwrite(text.data() + at, 1, text.size() - (size_t)at, out);
+    fflush(out);
+    D.emit_ms = now_ms() - t0;
 }
 
 // ---- parent side --------------------------------------------------------------------------------
@@ -699,6 +853,8 @@ void align_pending() {
     G.arena.clear();
 }
 
+[[noreturn]] void run_record_child(int argc, char **argv, int pipe_w);
+
 int run_batched(int argc, char **argv) {
     const int maxPasses = 4;
     for (int pass = 1; pass <= maxPasses; ++pass) {
@@ -734,6 +890,39 @@ int run_batched(int argc, char **argv) {
     const double tf = now_ms();
     const int rc = ref_tool_main(argc, argv);
     G.final_ms = now_ms() - tf;
+    return rc;
+}
+
+// YB_DROPIN=defer: one pass with deferred output (see Defer above); v=0 runs one speculative pass for the first stage first
+int run_deferred(int argc, char **argv, bool chained) {
+    if (chained) {
+        int fds[2];
+        if (pipe(fds) != 0) return run_batched(argc, argv);
+        const double tc = now_ms();
+        fflush(nullptr);
+        pid_t pid = fork();
+        if (pid < 0) { close(fds[0]); close(fds[1]); return run_batched(argc, argv); }
+        if (pid == 0) { close(fds[0]); run_record_child(argc, argv, fds[1]); }
+        close(fds[1]);
+        if (R.enabled) remote_begin(); else warm_ctx();
+        WireEnd end{};
+        drain_child(fds[0], end);
+        close(fds[0]);
+        int status = 0;
+        while (waitpid(pid, &status, 0) < 0 && errno == EINTR) {}
+        ++G.passes;
+        G.child_ms += now_ms() - tc;
+        align_pending();
+    } else {
+        if (R.enabled) remote_begin(); else warm_ctx();
+    }
+    D.chained = chained;
+    G.mode = DEFER;
+    defer_begin();
+    const double tf = now_ms();
+    const int rc = ref_tool_main(argc, argv);
+    G.final_ms = now_ms() - tf;
+    defer_finish();
     return rc;
 }
 
@@ -868,6 +1057,7 @@ void print_stats();
 // buffer (yb_destroy + the runtime's atexit handlers) costs a few hundred milliseconds that no caller needs; the
 // driver reclaims the context with the process.  The reference registers no atexit handlers of its own.
 [[noreturn]] void finish_process(int code) {
+    defer_finish();                                // (the host called exit() inside the deferred pass: write what it had)
     if (S.reader.joinable()) {                     // (the host called exit() inside the streamed real pass)
         if (S.reader.get_id() == std::this_thread::get_id()) S.reader.detach();   // a fatal error on the reader itself
         else if (code == 0) S.reader.join();
@@ -884,9 +1074,9 @@ void print_stats() {
     if (!G.stats) return;
     fprintf(stderr,
             "yama_b200: passes=%d batches=%lld jobs=%lld failed=%lld cells=%lld calls=%llu misses=%llu direct=%llu "
-            "gpu_ms=%.2f kernel_ms=%.2f create_ms=%.0f speculative_ms=%.0f final_ms=%.0f wall_ms=%.0f hit_ms=%.0f score_calls=%llu score_ms=%.1f stream_waits=%llu devices=%d\n",
+            "gpu_ms=%.2f kernel_ms=%.2f create_ms=%.0f speculative_ms=%.0f final_ms=%.0f emit_ms=%.0f wall_ms=%.0f hit_ms=%.0f score_calls=%llu score_ms=%.1f stream_waits=%llu devices=%d\n",
             G.passes, (long long)G.batches, (long long)G.jobs, (long long)G.failed, (long long)G.cells, (unsigned long long)G.calls,
-            (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.create_ms, G.child_ms, G.final_ms,
+            (unsigned long long)G.misses, (unsigned long long)G.direct, G.gpu_ms, G.kernel_ms, G.create_ms, G.child_ms, G.final_ms, D.emit_ms,
             now_ms() - G.t_start, G.hit_ms, (unsigned long long)G.scoreCalls, G.score_ms, (unsigned long long)S.waits, R.enabled ? R.devices : (G.ctx ? yb_device_count(G.ctx) : 0));
 }
 
@@ -922,6 +1112,14 @@ void yb_host_exit(int code) {
 
 // mafScoreRange (score_dropin.c): skipped in a speculative pass, the host's own function by default, the device
 // with YB_SCORE=gpu
+int yb_dropin_defer_active(void) { return D.active ? 1 : 0; }
+
+// score_dropin.c hands over its copy of a placeholder block the host just "wrote" to stdout
+void yb_dropin_defer_block(void *ali_copy) {
+    if (D.lastJob < 0) fatalf("yama_b200: a placeholder block without a job");
+    D.blocks.push_back(DeferBlock{D.lastJob, (long)ftello(stdout), ali_copy});
+}
+
 int yb_dropin_score_mode(void) {
     if (G.mode == RECORD) return 1;
     if (G.scoreGpu < 0) {
@@ -968,7 +1166,9 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
     job.LB = LB; job.RB = RB;
 
     // v=0 stage 2 of a pair whose stage 1 we answered with a placeholder: its inputs are meaningless
-    if (G.mode == RECORD && G.lastDummy && B == G.lastDummy && L == G.lastDummyRows && N == G.lastDummyCols) {
+    if (G.mode == DEFER && is_last_dummy(B, L, N))
+        fatalf("yama_b200: a second-stage yama() call (v=0) reached the deferred pass with a placeholder as its input");
+    if (G.mode == RECORD && is_last_dummy(B, L, N)) {
         job.A = contiguous(A, K, M, tmpA);
         job.B = contiguous(B, L, N, tmpB);
         ++G.nTainted;
@@ -1002,6 +1202,7 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
                 const Entry e = it->second;
                 if (lk.owns_lock()) lk.unlock();
                 ++G.nHits;
+                if (G.mode == DEFER && D.chained) ++D.callInPair;
                 emit(job, e.m_new, e.script, OAL, OM);
                 if (G.stats && G.mode == REPLAY) G.hit_ms += now_ms() - tHit0;
                 return;
@@ -1019,6 +1220,14 @@ void yama(uchar **A, int K, int M, uchar **B, int L, int N, int *LB, int *RB, uc
     if (G.mode == RECORD) {
         if (!collided && G.shipped.emplace(key, 1).second) { ship(key, proof, job); ++G.nShipped; }
         emit_dummy(job, OAL, OM);
+        return;
+    }
+    if (G.mode == DEFER) {
+        // v=0: the first call of a pair must have been answered by the speculative pass (a table hit, above); if it was
+        // not, it is aligned now, alone -- its answer is the second call's input
+        if (D.chained && (D.callInPair++ & 1) == 0) { ++G.misses; run_direct(job, OAL, OM); return; }
+        defer_record(key, job);
+        emit_placeholder(job, OAL, OM);
         return;
     }
     ++G.misses;                 // REPLAY miss: speculation did not cover this call; still exact
@@ -1063,14 +1272,27 @@ int main(int argc, char **argv) {
         struct stat sb;
         if (stat(argv[i], &sb) == 0 && !S_ISREG(sb.st_mode)) rereadable = false;
     }
-    if (!rereadable && G.stats) fprintf(stderr, "yama_b200: an input is not a regular file: one pair per launch (YB_DROPIN=direct)\n");
     int rc;
-    if ((m && strcmp(m, "direct") == 0) || !rereadable) {
+    // v (multiz.c:247, multic.c: the third positional argument): 0 chains two yama() calls per overlap
+    int v = -1;
+    for (int i = 1, pos = 0; i < argc; ++i) {
+        if (argv[i][0] && argv[i][1] == '=') continue;
+        if (++pos == 3) { v = atoi(argv[i]); break; }
+    }
+    // multic decides whether to print a merged block by its WIDTH (multic.c:100), which a placeholder does not have:
+    // with a minimum width (M=) it keeps the two-pass mode
+    bool widthMatters = false;
+    if (!multiz) for (int i = 1; i < argc; ++i) if (argv[i][0] == 'M' && argv[i][1] == '=' && atoi(argv[i] + 2) > 1) widthMatters = true;
+    if ((m && strcmp(m, "direct") == 0) || (!rereadable && v != 1)) {
+        G.mode = DIRECT;
+        rc = ref_tool_main(argc, argv);
+    } else if ((!m || strcmp(m, "defer") == 0) && (v == 0 || v == 1) && !widthMatters && (rereadable || v == 1)) {
+        rc = run_deferred(argc, argv, v == 0);  // one pass of the host (v=1; inputs may be streams), two for v=0
+    } else if (!rereadable) {
         G.mode = DIRECT;
         rc = ref_tool_main(argc, argv);
     } else if ((m && strcmp(m, "stream") == 0) || (R.enabled && !(m && strcmp(m, "batch") == 0))) {
-        rc = run_streamed(argc, argv);          // (the default behind the resident server: nothing to start up, so the
-                                                //  real pass can run beside the speculative one from the first call)
+        rc = run_streamed(argc, argv);          // the real pass beside the speculative one (behind the resident server)
     } else {
         rc = run_batched(argc, argv);
     }

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(SHIM_MULTIZ),
                                 reason="integration/_ref/bin/multiz_shim not built (needs /root/reference at build time)")
 
 
-@pytest.mark.parametrize("mode", ["batch", "direct", "stream"])
+@pytest.mark.parametrize("mode", ["defer", "batch", "direct", "stream"])
 def test_golden_maf_cases(tmp_path, mode):
     check_golden_cases(SHIM_MULTIZ, tmp_path, env={"YB_DROPIN": mode})
 
@@ -82,10 +82,13 @@ def test_no_server_and_no_spawn_fails_loudly(tmp_path):
 
 @pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin/multiz not built")
 def test_fresh_data_against_reference_binary(tmp_path):
-    rep = check_against_live_reference(SHIM_MULTIZ, tmp_path, ref_len=60_000, n_species=4, seed=5,
+    rep = check_against_live_reference(SHIM_MULTIZ, tmp_path / "defer", ref_len=60_000, n_species=4, seed=5,
                                        env={"YB_DROPIN_STATS": "1"})
-    # v=1 needs one speculative pass, v=0 two (stage 2 consumes stage 1's output, mz_preyama.c:335)
+    # deferred output: the host runs once for v=1, twice for v=0 (stage 2 consumes stage 1's output, mz_preyama.c:335)
     check_speculation(rep)
+    rep = check_against_live_reference(SHIM_MULTIZ, tmp_path / "batch", ref_len=60_000, n_species=4, seed=5,
+                                       env={"YB_DROPIN_STATS": "1", "YB_DROPIN": "batch"})
+    check_speculation(rep, "batch")
 
 
 @pytest.mark.skipif(not os.path.exists(REF_MULTIZ), reason="oracle/_ref/bin not built")
@@ -133,7 +136,7 @@ def test_speculative_passes_never_touch_the_output_files(tmp_path, v):
     assert rc == 0
     want1, want2 = (open(os.path.join(da, f), "rb").read() for f in ("o1", "o2"))
     assert len(want1) > 200_000
-    for mode in ("stream", "batch", "direct"):
+    for mode in ("defer", "stream", "batch", "direct"):
         db = str(tmp_path / mode)
         shutil.copytree(da, db)
         os.remove(os.path.join(db, "o1")); os.remove(os.path.join(db, "o2"))

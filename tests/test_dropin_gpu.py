@@ -15,7 +15,7 @@ def _need(path):
     assert os.path.exists(path), f"{path} missing: run __graft_entry__.build() where /root/reference exists"
 
 
-@pytest.mark.parametrize("mode", ["batch", "direct", "stream"])
+@pytest.mark.parametrize("mode", ["defer", "batch", "direct", "stream"])
 def test_golden_maf_cases_gpu(tmp_path, mode):
     _need(GPU_MULTIZ)
     check_golden_cases(GPU_MULTIZ, tmp_path, env={"YB_DROPIN": mode})
