@@ -36,8 +36,13 @@ void ref_mafWrite(FILE *f, struct mafAli *maf);
  * and kept with its position in the output stream; when the batch has been aligned, yb_defer_emit() gives the copy its
  * real text, scores it (mafScoreRange, mz_scores.c:124) and writes it with the reference's own mafWrite. */
 #define YB_MARK 1
+/* What mafScoreRange answers in the deferred pass for a real block: scores are only ever stored in mafAli::score and
+ * printed (maf.c:257-258), and every computed score is the score of the whole block as it is later written
+ * (multi_util.c:509, :611; mz_preyama.c:79) -- so the O(rows^2 * columns) loop is not run inside the host's pass; a block
+ * that reaches mafWrite with this value is scored when the pass is over, all such blocks at once. */
+#define YB_SCORE_LATER (-9.0e15)
 int yb_dropin_defer_active(void);
-void yb_dropin_defer_block(void *ali_copy);
+void yb_dropin_defer_block(FILE *f, void *ali_copy, int placeholder);
 
 static int is_placeholder(const struct mafAli *maf) {
     const struct mafComp *c = maf ? maf->components : NULL;
@@ -51,18 +56,17 @@ void mafWrite(FILE *f, struct mafAli *maf) {
     static int keep = -1;
     if (keep < 0) keep = getenv("YB_SPEC_WRITE") != NULL;        /* measurement knob: format in speculative passes too */
     if (!keep && yb_dropin_score_mode() == 1) return;
-    if (yb_dropin_defer_active() && is_placeholder(maf)) {
-        if (f != stdout) fatal("yama_b200: a merged block is written to a file other than stdout");
-        yb_dropin_defer_block(duplicate_ali(maf));
+    if (yb_dropin_defer_active()) {                               /* every block is written when the pass is over */
+        yb_dropin_defer_block(f, duplicate_ali(maf), is_placeholder(maf));
         return;
     }
     ref_mafWrite(f, maf);
 }
 
-/* Give a captured block its alignment (al: m_new columns of W bytes, as yama() returns them: column-major) and write it.
+/* Give a captured placeholder block its alignment (al: m_new columns of W bytes, as yama() returns them: column-major).
  * Rows of the alignment that hold no residue were dropped by mafBuild (mz_preyama.c:67-70): the block's components are
  * the remaining rows, in order.  Returns 0, or -1 if the rows do not match the block. */
-int yb_defer_emit(FILE *f, void *ali_copy, const unsigned char *al, int m_new, int W) {
+int yb_defer_fill(void *ali_copy, const unsigned char *al, int m_new, int W) {
     struct mafAli *a = (struct mafAli *)ali_copy;
     struct mafComp *c = a->components;
     int r, j;
@@ -80,15 +84,39 @@ int yb_defer_emit(FILE *f, void *ali_copy, const unsigned char *al, int m_new, i
     }
     if (c != NULL) return -1;
     a->textSize = m_new;
-    a->score = mafScoreRange(a, 0, m_new);                           /* mz_preyama.c:79 */
+    a->score = YB_SCORE_LATER;                                        /* mz_preyama.c:79 */
+    return 0;
+}
+
+int yb_defer_wants_score(void *ali_copy) { return ((struct mafAli *)ali_copy)->score == YB_SCORE_LATER; }
+int yb_defer_text_size(void *ali_copy) { return ((struct mafAli *)ali_copy)->textSize; }
+int yb_defer_rows(void *ali_copy, const unsigned char **rows, int cap) {
+    int n = 0;
+    struct mafComp *c;
+    for (c = ((struct mafAli *)ali_copy)->components; c != NULL; c = c->next, ++n)
+        if (n < cap) rows[n] = (const unsigned char *)c->text;
+    return n;
+}
+double yb_defer_host_score(void *ali_copy) {
+    struct mafAli *a = (struct mafAli *)ali_copy;
+    return ref_mafScoreRange(a, 0, a->textSize);
+}
+void yb_defer_write(FILE *f, void *ali_copy, int have_score, double score) {
+    struct mafAli *a = (struct mafAli *)ali_copy;
+    if (have_score) a->score = score;
     ref_mafWrite(f, a);
     mafAliFree(&a);
-    return 0;
 }
 
 double mafScoreRange(struct mafAli *maf, int start, int size) {
     const int mode = yb_dropin_score_mode();
-    if (yb_dropin_defer_active() && is_placeholder(maf)) return 0.0;     /* scored when it has its real text (yb_defer_emit) */
+    if (yb_dropin_defer_active()) {
+        if (is_placeholder(maf)) return 0.0;                     /* scored when it has its real text */
+        if (start < 0 || size <= 0 || start + size > maf->textSize)
+            fatalf("mafScoreRange: start = %d, size = %d, textSize = %d\n", start, size, maf->textSize);
+        if (ss == NULL) fatal("mafScoreRange: scores not initialized");
+        return YB_SCORE_LATER;
+    }
     if (mode == 0) return ref_mafScoreRange(maf, start, size);
     /* the reference's checks, in its order and wording (mz_scores.c:130-134) */
     if (start < 0 || size <= 0 || start + size > maf->textSize)

@@ -69,8 +69,14 @@ FILE *yb_host_fopen(const char *path, const char *mode);
 int yb_dropin_score_mode(void);
 // deferred output (score_dropin.c holds the part that walks the reference's structs)
 int yb_dropin_defer_active(void);
-void yb_dropin_defer_block(void *ali_copy);
-int yb_defer_emit(FILE *f, void *ali_copy, const unsigned char *al, int m_new, int W);
+void yb_dropin_defer_block(FILE *f, void *ali_copy, int placeholder);
+int yb_defer_fill(void *ali_copy, const unsigned char *al, int m_new, int W);
+int yb_defer_wants_score(void *ali_copy);
+int yb_defer_text_size(void *ali_copy);
+int yb_defer_rows(void *ali_copy, const unsigned char **rows, int cap);
+double yb_defer_host_score(void *ali_copy);
+void yb_defer_write(FILE *f, void *ali_copy, int have_score, double score);
+int yb_host_fclose(FILE *f);
 // the tool that was linked in: multiz.c defines multiz(), multic.c does not
 int multiz(void *, void *, FILE *, FILE *, int) __attribute__((weak));
 double yb_dropin_score(int nrows, const unsigned char *const *rows, int text_size, int start, int size);
@@ -151,15 +157,17 @@ struct Globals {
 // v=0 (mz_preyama.c:265-335: a second yama() on the first one's output) takes one speculative pass for the first stage
 // (a forked child, as in batch mode), then this pass for the second.
 struct DeferJob { int32_t K, M, L, N; size_t offA, offB, offLB, offRB; Key key; };
-struct DeferBlock { int64_t job; long pos; void *ali; };
+struct DeferBlock { FILE *f; int64_t job; long pos; void *ali; double score; bool haveScore; };   // job < 0: not a placeholder
 struct Defer {
     bool active = false, done = false;
     bool chained = false;                // v=0: calls come in pairs, the second consumes the first one's answer
     uint64_t callInPair = 0;
     std::vector<uint8_t> arena;
     std::vector<DeferJob> jobs;
-    std::vector<DeferBlock> blocks;
+    std::vector<DeferBlock> blocks;          // every block the host "wrote", in its order
+    std::vector<FILE *> closed;              // streams the host closed meanwhile: closed for real when their blocks are out
     int64_t lastJob = -1;
+    long stdoutClosedAt = -1;                // where the captured stream ends for the caller: the host closed stdout there
     int savedStdout = -1, memFd = -1;
     double emit_ms = 0;
 } D;
@@ -654,23 +662,67 @@ void defer_begin() {
     D.active = true;
 }
 
-// Align everything the pass recorded and write the captured stream with the merged blocks in place.
+// Scores of the blocks that still need one (mafScoreRange over the whole block): one yb_score_blocks() batch when this
+// process owns a context, the host's own function on a few threads otherwise (behind the resident server).
+void defer_score(std::vector<DeferBlock> &blocks, size_t upto) {
+    std::vector<size_t> want;
+    for (size_t k = 0; k < upto; ++k) if (yb_defer_wants_score(blocks[k].ali)) want.push_back(k);
+    if (want.empty()) return;
+    const double t0 = now_ms();
+    bool done = false;
+    if (!R.enabled && G.ctx) {
+        size_t nrows = 0;
+        for (size_t k : want) nrows += (size_t)yb_defer_rows(blocks[k].ali, nullptr, 0);
+        std::vector<const unsigned char *> rows(nrows + 1);
+        std::vector<yb_block> yb(want.size());
+        std::vector<double> sc(want.size());
+        size_t at = 0;
+        for (size_t q = 0; q < want.size(); ++q) {
+            void *a = blocks[want[q]].ali;
+            const int n = yb_defer_rows(a, rows.data() + at, (int)(nrows - at));
+            yb[q].nrows = n; yb[q].text_size = yb_defer_text_size(a); yb[q].start = 0; yb[q].size = yb[q].text_size;
+            yb[q].rows = rows.data() + at;
+            at += (size_t)n;
+        }
+        if (yb_score_blocks(G.ctx, (int64_t)yb.size(), yb.data(), sc.data(), nullptr) == YB_OK) {
+            for (size_t q = 0; q < want.size(); ++q) { blocks[want[q]].score = sc[q]; blocks[want[q]].haveScore = true; }
+            done = true;
+        }
+    }
+    if (!done) {
+        unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                for (size_t q = t; q < want.size(); q += nt) {
+                    blocks[want[q]].score = yb_defer_host_score(blocks[want[q]].ali);
+                    blocks[want[q]].haveScore = true;
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    G.scoreCalls += want.size();
+    G.score_ms += now_ms() - t0;
+}
+
+// Align everything the pass recorded, score what needs a score, and write every block the host handed to mafWrite -- to
+// stdout between the bytes the host printed there itself, to out1 / out2 in the host's order.
 void defer_finish() {
     if (!D.active || D.done) return;
     D.done = true;
+    if (G.debug) fprintf(stderr, "yama_b200[debug]: deferred pass over: %zu jobs, %zu blocks, %zu streams closed by the host\n", D.jobs.size(), D.blocks.size(), D.closed.size());
     const double t0 = now_ms();
-    fflush(stdout);                                           // (the host may have fclose()d stdout itself: multiz.c:288-291
-                                                              //  does when out1/out2 are not given; our descriptor stays)
+    fflush(stdout);
     struct stat sb;
     const off_t total = fstat(D.memFd, &sb) == 0 ? sb.st_size : 0;
     std::vector<char> text((size_t)(total > 0 ? total : 0));
     if (total > 0 && pread(D.memFd, text.data(), (size_t)total, 0) != (ssize_t)total) fatalf("yama_b200: cannot read the captured stdout");
     dup2(D.savedStdout, 1);                                   // fd 1 is the caller's again
-    FILE *out = fdopen(D.savedStdout, "w");                   // ... and so is this stream (stdout itself may be closed)
+    FILE *out = fdopen(D.savedStdout, "w");                   // ... and so is this stream (the host may have closed `stdout`)
     if (!out) fatalf("yama_b200: cannot reopen stdout");
     __fsetlocking(out, FSETLOCKING_BYCALLER);
     close(D.memFd);
-    G.mode = REPLAY;                                          // (block scoring below uses the real function)
+    G.mode = REPLAY;
     D.active = false;
     // ---- one batch ------------------------------------------------------------------------------------------------------
     const size_t n = D.jobs.size();
@@ -683,48 +735,54 @@ void defer_finish() {
         jobs[i].RB = reinterpret_cast<const int32_t *>(D.arena.data() + q.offRB);
     }
     std::vector<yb_result> res(n);
+    int rc = YB_OK;
+    size_t bad = n;                                           // first job that did not align
     if (n > 0) {
         yb_stats st;
         const double tb = now_ms();
-        const int rc = backend_batch((int64_t)n, jobs.data(), res.data(), &st, D.arena.data(), D.arena.size());
+        rc = backend_batch((int64_t)n, jobs.data(), res.data(), &st, D.arena.data(), D.arena.size());
         G.gpu_ms += now_ms() - tb;
         G.kernel_ms += st.kernel_ms; G.cells += st.cells; G.jobs += (int64_t)n; ++G.batches;
-        if (rc != YB_OK) {
-            // the reference would have died inside the failing yama() call, after writing everything before it
-            size_t bad = 0;
-            while (bad < n && res[bad].status == YB_OK) ++bad;
-            long upto = (long)text.size();
-            for (const DeferBlock &b : D.blocks) if (b.job >= (int64_t)bad) { upto = b.pos; break; }
-            std::vector<uchar> al;
-            long at = 0;
-            for (const DeferBlock &b : D.blocks) {
-                if (b.job >= (int64_t)bad) break;
-                fwrite(text.data() + at, 1, (size_t)(b.pos - at), out);
-                at = b.pos;
-                al.resize((size_t)res[b.job].m_new * (size_t)(jobs[b.job].K + jobs[b.job].L) + 1);
-                if (yb_assemble(&jobs[b.job], &res[b.job], al.data()) == YB_OK)
-                    yb_defer_emit(out, b.ali, al.data(), res[b.job].m_new, jobs[b.job].K + jobs[b.job].L);
-            }
-            fwrite(text.data() + at, 1, (size_t)(upto - at), out);
-            fflush(out);
-            fail_from_status(bad < n ? res[bad].status : rc);
-        }
+        if (rc == YB_ERR_CUDA || rc == YB_ERR_SCORES || rc == YB_ERR_ARG) fatalf("yama_b200: %s", backend_error());
+        if (rc != YB_OK) { bad = 0; while (bad < n && res[bad].status == YB_OK) ++bad; }
     }
-    // ---- the stream, with the merged blocks where the host printed their placeholders ---------------------------------------
+    // the reference would have died inside the failing yama() call, after writing everything before it
+    size_t upto = D.blocks.size();
+    if (rc != YB_OK)
+        for (size_t k = 0; k < D.blocks.size(); ++k) if (D.blocks[k].job >= (int64_t)bad) { upto = k; break; }
+    // ---- the merged blocks get their text; then every block that needs a score gets one ---------------------------------------
     std::vector<uchar> al;
-    long at = 0;
-    for (const DeferBlock &b : D.blocks) {
-        fwrite(text.data() + at, 1, (size_t)(b.pos - at), out);
-        at = b.pos;
+    for (size_t k = 0; k < upto; ++k) {
+        DeferBlock &b = D.blocks[k];
+        if (b.job < 0) continue;
         const yb_job &j = jobs[(size_t)b.job];
         const yb_result &r = res[(size_t)b.job];
         al.resize((size_t)r.m_new * (size_t)(j.K + j.L) + 1);
-        if (yb_assemble(&j, &r, al.data()) != YB_OK || yb_defer_emit(out, b.ali, al.data(), r.m_new, j.K + j.L) != 0)
+        if (yb_assemble(&j, &r, al.data()) != YB_OK || yb_defer_fill(b.ali, al.data(), r.m_new, j.K + j.L) != 0)
             fatalf("new_align: edit script does not consume both alignments (M=%d, N=%d, M_new=%d)", j.M, j.N, r.m_new);
     }
-    fwrite(text.data() + at, 1, text.size() - (size_t)at, out);
+    if (G.debug) fprintf(stderr, "yama_b200[debug]: batch rc=%d, filled; scoring\n", rc);
+    defer_score(D.blocks, upto);
+    if (G.debug) fprintf(stderr, "yama_b200[debug]: scored; writing\n");
+    // ---- out: stdout's blocks go between the bytes the host printed itself, the others to their files in order --------------
+    long at = 0;
+    const long end = D.stdoutClosedAt >= 0 ? std::min((long)text.size(), D.stdoutClosedAt) : (long)text.size();
+    for (size_t k = 0; k < upto; ++k) {
+        DeferBlock &b = D.blocks[k];
+        FILE *f = b.f;
+        if (f == stdout) {
+            const long pos = std::min(b.pos, end);
+            if (pos > at) { fwrite(text.data() + at, 1, (size_t)(pos - at), out); at = pos; }
+            f = out;
+        }
+        yb_defer_write(f, b.ali, b.haveScore ? 1 : 0, b.score);
+    }
+    const long last = upto < D.blocks.size() ? std::min(end, std::max(at, D.blocks[upto].f == stdout ? D.blocks[upto].pos : at)) : end;
+    if (last > at) fwrite(text.data() + at, 1, (size_t)(last - at), out);
     fflush(out);
+    for (FILE *f : D.closed) if (f != stdout) fclose(f);
     D.emit_ms = now_ms() - t0;
+    if (rc != YB_OK) fail_from_status(bad < n ? res[bad].status : rc);
 }
 
 // ---- parent side --------------------------------------------------------------------------------
@@ -1114,10 +1172,27 @@ void yb_host_exit(int code) {
 // with YB_SCORE=gpu
 int yb_dropin_defer_active(void) { return D.active ? 1 : 0; }
 
-// score_dropin.c hands over its copy of a placeholder block the host just "wrote" to stdout
-void yb_dropin_defer_block(void *ali_copy) {
-    if (D.lastJob < 0) fatalf("yama_b200: a placeholder block without a job");
-    D.blocks.push_back(DeferBlock{D.lastJob, (long)ftello(stdout), ali_copy});
+// score_dropin.c hands over its copy of a block the host just "wrote" (deferred pass)
+void yb_dropin_defer_block(FILE *f, void *ali_copy, int placeholder) {
+    if (placeholder && D.lastJob < 0) fatalf("yama_b200: a placeholder block without a job");
+    if (placeholder && f != stdout) fatalf("yama_b200: a merged block is written to a file other than stdout");
+    D.blocks.push_back(DeferBlock{f, placeholder ? D.lastJob : (int64_t)-1, f == stdout ? (long)ftello(stdout) : 0L, ali_copy, 0.0, false});
+}
+
+// fclose() of the reference objects (-Dfclose=yb_host_fclose): in the deferred pass the host's output streams are kept
+// open until their blocks have been written (multiz.c:288-291 closes out1 / out2 -- and stdout, when they are not given)
+int yb_host_fclose(FILE *f) {
+    if (D.active && f) {
+        // (the reference loses what it prints to stdout after closing it -- the "##eof maf" line of multiz.c:292 when
+        //  out1 / out2 are not given: so do we)
+        if (f == stdout) { if (D.stdoutClosedAt < 0) D.stdoutClosedAt = (long)ftello(stdout); return 0; }
+        for (const DeferBlock &b : D.blocks)
+            if (b.f == f) {
+                if (std::find(D.closed.begin(), D.closed.end(), f) == D.closed.end()) D.closed.push_back(f);
+                return 0;
+            }
+    }
+    return fclose(f);
 }
 
 int yb_dropin_score_mode(void) {
