@@ -38,7 +38,8 @@ struct PlanSummary {
     int binStart[PLAN_NBINS + 1];          // ranges of the launch order per kernel bin
     int nValid, nLong, nFailed, firstFailed;             // firstFailed: lowest failing pair index of the wave (or -1)
     int nDeferred, pad;                    // pairs whose traceback matrix did not fit the wave's pool any more
-    unsigned long long tbBytes;            // traceback pool bytes of the wave
+    unsigned long long tbBytes;            // traceback pool bytes of the wave (the pairs that were placed)
+    unsigned long long tbNeed;             // ... and of all its valid pairs, placed or deferred
     long long cells;                       // DP cells of the valid pairs
 };
 
@@ -206,6 +207,7 @@ yb_plan_scan(int nPairs, unsigned long long *__restrict__ tbBytes, int *__restri
     if (t == 0) {                                   // (1024 partial sums: a serial scan by one thread is a microsecond)
         unsigned long long acc = 0;
         for (int k = 0; k < T; ++k) { const unsigned long long v = part[k]; part[k] = acc; acc += v; }
+        summary->tbNeed = acc;
     }
     __syncthreads();
     unsigned long long acc = part[t], used = 0;

@@ -178,7 +178,7 @@ struct Slot {
     // layout of dIn: [descriptors | stream A | stream B | stream LB | stream RB] copied from the host, then
     // [traceback offsets | launch order | long-path list | bucket of each pair | schedules | counters | summary] written by K0
     size_t metaBytes = 0, tbBaseOff = 0, orderOff = 0, longOff = 0, bucketOfOff = 0, schedOff = 0, countersOff = 0, summaryOff = 0;
-    size_t h2dBytes = 0, scriptWords = 0;
+    size_t h2dBytes = 0, scriptWords = 0, tbEst = 0;
     int maxN = 0, minK = 0, nLongMax = 0;  // dimension facts that bound which kernels the wave can need
     unsigned launchMask = 0;               // kernel bins whose fill is queued for this wave
     int gridHint[NBINS] = {};              // pairs to size a bin's grid for (0: unknown, a full grid)
@@ -212,6 +212,7 @@ struct Device {
     int timeline = 0;
     ScoreConst sc{};                       // the owning context's score tables (kernel arguments)
     int onlyBins = 0;
+    double tbRatio = 1.0;                  // traceback bytes recent waves needed / the one-warp-per-pair estimate from their dimensions
     unsigned recentBins[4] = {0, 0, 0, 0}; // bins that held pairs in the last waves whose summaries came back (ring)
     int recentCount[4][NBINS] = {};        // ... and how many
     int recentAt = 0, summaries = 0;
@@ -520,6 +521,7 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
     Stream st[4];
     size_t rows = 0, cols = 0, words = 0, sched = 0;
     int maxK = 0, maxN = 0, minK = 0x7fffffff, nLongMax = 0;
+    size_t tbEst = 0;
     for (int64_t i = 0; i < count; ++i) {
         const yb_job &j = jobs[first + i];
         Slot::Off &o = s.off[(size_t)i];
@@ -527,6 +529,7 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
         o.row = rows; o.col = cols; o.sched = sched; o.script = (uint32_t)words;
         if (!dims_ok(j)) continue;
         maxK = std::max(maxK, j.K); minK = std::min(minK, j.K); maxN = std::max(maxN, j.N);
+        tbEst += 32ull * ((size_t)j.M + j.N + 3 * (((size_t)j.M + 31) >> 5) + 40);        // one warp, a diagonal band
         if (j.M + j.N >= ctx->tbLong) ++nLongMax;
         const unsigned char *ptr[4] = {j.A, j.B, reinterpret_cast<const unsigned char *>(j.LB), reinterpret_cast<const unsigned char *>(j.RB)};
         const size_t len[4] = {(size_t)j.K * j.M, (size_t)j.L * j.N, (size_t)(j.M + 1) * 4, (size_t)(j.M + 1) * 4};
@@ -637,6 +640,13 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
         CUDA_TRY(d, s.dCol.reserve(cols * sizeof(ColRec) + 2 * COL_PAD + 64));
         if (s.dCol.p != before) CUDA_TRY(d, cudaMemsetAsync(s.dCol.p, 0, s.dCol.cap, q));
     }
+    // The traceback pool of the wave: what its pairs would need with one warp each on diagonal bands (known from the
+    // dimensions), times what recent waves needed relative to that estimate (wide bands run 4 or 8 warps per pair), with a
+    // margin; never more than tbCapacity.  Pairs that do not fit are deferred by K0 and run again at the end -- a fixed
+    // large pool per slot would cost every short-lived process seconds of allocation and teardown.
+    s.tbEst = tbEst;
+    if (!allBins || tbCapacity == 0) tbCapacity = std::min<size_t>(std::max<size_t>(tbCapacity, (size_t)16 << 20),
+                                                                    (size_t)((double)tbEst * d.tbRatio * 1.25) + ((size_t)16 << 20));
     CUDA_TRY(d, s.dTb.reserve(std::max(tbCapacity, (size_t)1 << 20) + 256));
     CUDA_TRY(d, s.dScript.reserve(words * 4 + 64));
     s.scriptDst = ctx->scriptStore + ctx->scriptOff[(size_t)first];   // the wave's scripts, in job order, in the batch store
@@ -815,6 +825,10 @@ int slot_wait(Device &d, Slot &s) {
             if (d.recentCount[d.recentAt][b] > 0) used |= 1u << b;
         }
         d.recentBins[d.recentAt] = used;
+        if (s.tbEst > 0 && s.sum.tbNeed > 0) {
+            const double r = (double)s.sum.tbNeed / (double)s.tbEst;
+            d.tbRatio = std::max(1.0, d.summaries == 0 ? r : std::max(r, 0.5 * d.tbRatio + 0.5 * r));
+        }
         d.recentAt = (d.recentAt + 1) & 3;
         ++d.summaries;
     }
@@ -1024,7 +1038,7 @@ int device_run(yb_ctx *ctx, Device &d, Dispatcher &disp, yb_result *results) {
                 tbSum += nb; ++e;
             }
             Slot &s = d.slots[0];
-            if ((rc = slot_prepare(ctx, d, s, disp.jobs, again[k], (int64_t)(e - k), cap, true)) != YB_OK) break;
+            if ((rc = slot_prepare(ctx, d, s, disp.jobs, again[k], (int64_t)(e - k), std::min(cap, tbSum + ((size_t)16 << 20)), true)) != YB_OK) break;
             if ((rc = slot_launch(d, s, true)) != YB_OK) break;
             if ((rc = slot_wait(d, s)) != YB_OK) break;
             slot_unpack(ctx, d, s, results);
@@ -1322,7 +1336,10 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     Dispatcher disp;
     disp.jobs = jobs; disp.n = n;
     disp.prefix = ctx->blobPrefix.data();
-    disp.maxBytes = ctx->waveInBytes; disp.maxPairs = ctx->wavePairs;
+    // a wave costs a fixed chain of kernel launches and the latency of its longest pair whatever its size: large batches run
+    // in larger waves (about ten per device), bounded by the device memory a wave's traceback and record pools take
+    disp.maxBytes = std::max(ctx->waveInBytes, std::min<size_t>((size_t)512 << 20, ctx->batchBlobBytes / (10 * ctx->devs.size())));
+    disp.maxPairs = ctx->wavePairs;
     disp.minBytes = std::min(ctx->waveInBytes, ctx->waveMinBytes);
     disp.tailBytes = std::min(ctx->waveInBytes, ctx->waveTailBytes);
     disp.ndev = (int)ctx->devs.size();
