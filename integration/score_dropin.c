@@ -27,6 +27,7 @@ double mafScoreRange(struct mafAli *maf, int start, int size);
 /* mafWrite (maf.h, maf.c:251-284; maf.c is compiled with -DmafWrite=ref_mafWrite): formatting a block costs an
  * fprintf per row; a speculative pass's output goes nowhere, so it is not produced.  The real pass writes as ever. */
 void ref_mafWrite(FILE *f, struct mafAli *maf);
+void yb_maf_write(FILE *f, struct mafAli *maf);                       /* maf_dropin.c: the same bytes, one fwrite per block */
 
 /* ---- deferred output (yama_dropin.cpp, the single-pass driver) -------------------------------------------------------
  * In the deferred pass yama() answers with a PLACEHOLDER alignment: every column of A and of B once and in order, its
@@ -60,7 +61,7 @@ void mafWrite(FILE *f, struct mafAli *maf) {
         yb_dropin_defer_block(f, duplicate_ali(maf), is_placeholder(maf));
         return;
     }
-    ref_mafWrite(f, maf);
+    yb_maf_write(f, maf);
 }
 
 /* Give a captured placeholder block its alignment (al: m_new columns of W bytes, as yama() returns them: column-major).
@@ -104,7 +105,7 @@ double yb_defer_host_score(void *ali_copy) {
 void yb_defer_write(FILE *f, void *ali_copy, int have_score, double score) {
     struct mafAli *a = (struct mafAli *)ali_copy;
     if (have_score) a->score = score;
-    ref_mafWrite(f, a);
+    yb_maf_write(f, a);
     mafAliFree(&a);
 }
 
