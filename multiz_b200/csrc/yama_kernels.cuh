@@ -873,6 +873,17 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
                 Cl = vC; Dl = vD; Il = vI;
                 Cd = Cu; Dd = Du; Id = Iu;
                 c16 += 16;
+                // The ring is the one shared-memory hand-off left (lane 31 writes a band row, lane 0 reads it a block of rows
+                // later; the row slots and the stash word are private to a lane).  Its write and its read are always in
+                // different steps, and the steps of a warp are separated by the three full-mask shuffles above, which no lane
+                // passes before all have arrived: the LDS of a later step is issued after the STS of an earlier one, and shared
+                // memory serves one warp's accesses in issue order.  (A __syncwarp() here is elided by ptxas -- the warp is
+                // converged -- but its compiler barrier keeps the next step's column load from being hoisted: not shipped.)
+                // The `make sanitize` build separates the steps with a named 32-thread barrier, which is never elided and
+                // which compute-sanitizer's racecheck can see: same protocol, tool-checked (profiles/r2_sanitizer.md).
+#ifdef YB_FORCE_WARPSYNC
+                asm volatile("bar.sync %0, 32;" ::"r"(grp + 1) : "memory");
+#endif
             }
             cp += 128;
             tbp += 2 * B;
