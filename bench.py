@@ -28,6 +28,10 @@ import time
 
 import numpy as np
 
+# the library's streams need more hardware work queues than CUDA's default of 8 (yb_create, multiz_b200/csrc/yama_b200.cu);
+# torch creates the CUDA context in this process, so the variable is set before torch is imported
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

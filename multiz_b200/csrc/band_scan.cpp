@@ -77,7 +77,30 @@ extern "C" int64_t YB_BAND_SCAN_NAME(int M, int N, const int32_t *__restrict__ L
     return cells;
 }
 
+// Delta-coded band of one pair for the host->device copy: byte r = X[r] - X[r-1] when that lies in 0..254 (bands are
+// non-decreasing and move a few columns per row), 255 marks a row whose step the caller lists separately; byte 0 is 0.
+// Written so that the compiler vectorises it (32-bit subtract, compare, narrowing store).  Returns the number of marked rows.
+#define YB_CAT2(a, b) a##b
+#define YB_CAT(a, b) YB_CAT2(a, b)
+#define YB_BAND_PACK_NAME YB_CAT(YB_BAND_SCAN_NAME, _pack)
+extern "C" int YB_BAND_PACK_NAME(int M, const int32_t *__restrict__ X, uint8_t *__restrict__ out) {
+    int marked = 0;
+    out[0] = 0;
+    for (int r = 1; r <= M; ++r) {
+        const uint32_t d = (uint32_t)X[r] - (uint32_t)X[r - 1];
+        const bool ok = d < 255u;
+        out[r] = ok ? (uint8_t)d : (uint8_t)255;
+        marked += !ok;
+    }
+    return marked;
+}
+
 #ifdef YB_BAND_SCAN_DISPATCH
+extern "C" int yb_band_scan_avx2_pack(int, const int32_t *, uint8_t *);
+extern "C" int yb_band_pack(int M, const int32_t *X, uint8_t *out) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("YB_NO_AVX2");
+    return avx2 ? yb_band_scan_avx2_pack(M, X, out) : YB_BAND_PACK_NAME(M, X, out);
+}
 extern "C" int64_t yb_band_scan_avx2(int, int, const int32_t *, const int32_t *, int32_t *, int32_t *, int32_t *,
                                      int (*)(int, int), int32_t *, int32_t *);
 extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,

@@ -53,6 +53,70 @@ __device__ __forceinline__ int plan_bin_of(const PlanParams &pp, int wmax, int M
 
 constexpr int PLAN_THREADS = 256;
 
+// ---- delta-coded bands ---------------------------------------------------------------------------------------------------
+// The band is most of what a shallow pair sends over PCIe: 8 bytes per row (two ints, mz_yama.h:14-16) next to K + ~1
+// bytes of sequence.  When the host has threads to spare it ships a pair's band as one byte per row and array -- the step
+// X[r] - X[r-1], which is 0..254 for any band pre_yama builds except across a long indel -- and this kernel restores the
+// caller's int arrays in device memory before anything reads them (K0 validates the restored rows, so an invalid band is
+// still reported in the reference's words).  Steps outside 0..254 travel as exceptions: byte 255 plus an (index, step) entry.
+struct BandPackHdr { int LB0, RB0, nExc, excStart; };      // then dl[align4(M+1)], dr[align4(M+1)] (pad bytes are 0)
+struct BandExc { int idx, delta; };                        // idx: row r of LB, or M+1+r of RB
+constexpr unsigned long long BAND_RAW = ~0ull;
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+yb_band_expand(const PairMeta *__restrict__ metas, int nPairs, unsigned char *blob, const unsigned long long *__restrict__ packOff,
+               const BandExc *__restrict__ exc) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (int p = warp; p < nPairs; p += nWarps) {
+        const PairMeta pm = metas[p];
+        const unsigned long long po = __ldg(packOff + p);
+        if (pm.M < 1 || po == BAND_RAW) continue;
+        const int M = pm.M;
+        const BandPackHdr hdr = *reinterpret_cast<const BandPackHdr *>(blob + po);
+        const int words = (M + 4) >> 2;                                 // align4(M+1) / 4
+        const BandExc *ex = exc + hdr.excStart;
+        for (int which = 0; which < 2; ++which) {
+            const unsigned *src = reinterpret_cast<const unsigned *>(blob + po + sizeof(BandPackHdr)) + which * words;
+            int *out = reinterpret_cast<int *>(blob + (which ? pm.offBand2 : pm.offBand));
+            unsigned carry = (unsigned)(which ? hdr.RB0 : hdr.LB0);
+            const int idx0 = which * (M + 1);
+            for (int r0 = 0; r0 <= M; r0 += 128) {
+                const int r = r0 + 4 * lane;
+                const unsigned w = r <= M ? __ldg(src + (r >> 2)) : 0u;
+                unsigned v0 = w & 0xffu, v1 = v0 + ((w >> 8) & 0xffu), v2 = v1 + ((w >> 16) & 0xffu), v3 = v2 + (w >> 24);
+                unsigned inc = v3;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned o = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                const unsigned before = carry + inc - v3;
+                v0 += before; v1 += before; v2 += before; v3 += before;
+                for (int e = 0; e < hdr.nExc; ++e) {                    // (rare: a band step outside 0..254)
+                    const BandExc x = ex[e];
+                    const int at = x.idx - idx0;
+                    if (at < 0 || at > M) continue;
+                    const unsigned adj = (unsigned)x.delta - 255u;
+                    if (r >= at) v0 += adj;
+                    if (r + 1 >= at) v1 += adj;
+                    if (r + 2 >= at) v2 += adj;
+                    if (r + 3 >= at) v3 += adj;
+                }
+                if (r + 3 <= M) *reinterpret_cast<int4 *>(out + r) = make_int4((int)v0, (int)v1, (int)v2, (int)v3);
+                else {
+                    if (r <= M) out[r] = (int)v0;
+                    if (r + 1 <= M) out[r + 1] = (int)v1;
+                    if (r + 2 <= M) out[r + 2] = (int)v2;
+                }
+                carry += __shfl_sync(FULL, inc, 31);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(PLAN_THREADS)
 yb_plan_kernel(PairMeta *metas, int nPairs, unsigned char *blob, PairOut *__restrict__ outs,
                unsigned long long *__restrict__ tbBytes, int *__restrict__ bucketOf,

@@ -37,6 +37,7 @@
 
 using namespace yb;
 
+extern "C" int yb_band_pack(int M, const int32_t *X, uint8_t *out);      // band_scan.cpp: one byte per row, 255 = listed separately
 extern "C" int64_t yb_band_scan(int M, int N, const int32_t *LB, const int32_t *RB, int32_t *wmax, int32_t *sched,
                                 int32_t *nSteps, int (*lanesOf)(int, int), int32_t *lanes, int32_t *connected);   // band_scan.cpp
 
@@ -173,7 +174,7 @@ struct Slot {
     double tPack0 = 0, tPack1 = 0, tTbLaunch = 0;   // host times (ms) of the wave: prepare start/end, traceback launch
     // the wave it holds
     int64_t first = 0, count = 0;
-    struct Off { size_t a, b, lb, rb, row, col, sched; uint32_t script; };
+    struct Off { size_t a, b, lb, rb, row, col, sched; uint32_t script; size_t pk; };   // pk: the pair's delta-coded band section
     std::vector<Off> off;                  // per pair, dimension-only offsets (streams, pools)
     // layout of dIn: [descriptors | stream A | stream B | stream LB | stream RB] copied from the host, then
     // [traceback offsets | launch order | long-path list | bucket of each pair | schedules | counters | summary] written by K0
@@ -248,7 +249,7 @@ struct yb_ctx {
     int maxDepth = 255;
     int maxAbsS = 1;                        // max |S6|
     bool ungatedOk = true;                  // YB_UNGATED=0 keeps the existence multipliers in every fill kernel
-    int slackBulk = 3;                      // YB_SLACK: schedule slack of the shuffle kernels (development)
+    int slackBulk = 3 + F2_SW - 1;          // schedule slack of the shuffle kernels (see YB_F2_SW in yama_kernels.cuh); YB_SLACK (development)
     int maxCls = 2;                         // highest kernel class handed out: YB_FILL2=0 -> 0 (fill_body only), YB_KEYED=0 -> 1
     int nThreads = 1;
     size_t waveInBytes = (size_t)64 << 20;  // input bytes per wave (steady state)
@@ -259,6 +260,7 @@ struct yb_ctx {
     int64_t wavePairs = 1 << 20;
     int tbLong = TB_LONG;                   // paths of at least this many moves: warp-per-path traceback (YB_TB_LONG)
     bool directCopy = true;                 // inputs inside yb_host_alloc memory are copied from where they are (YB_DIRECT=0: always staged)
+    int bandPack = -1;                      // delta-coded bands over PCIe: -1 when the device has >= 8 host threads, YB_BAND_PACK=0/1
     std::vector<HostBlock> hostBlocks;      // yb_host_alloc
     // results of the last batch
     uint8_t *scriptStore = nullptr;         // pinned (portable): the D2H copies of the waves land here directly
@@ -416,11 +418,17 @@ int device_init(Device &d) {
     cudaDeviceProp prop;
     CUDA_TRY(d, cudaGetDeviceProperties(&prop, d.id));
     d.sms = prop.multiProcessorCount;
+    // A wave's copies, K0, K1, K3 run on its main stream, the fill kernels on the bin streams.  The fill kernels are persistent
+    // and fill the machine; the short kernels of the NEXT waves must get the CTA slots that free up first, or every wave's
+    // K0 / K1 / K3 waits behind a whole fill: the main streams get the higher priority (YB_PRIO=0: all equal).
+    int prioLo = 0, prioHi = 0;
+    CUDA_TRY(d, cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi));
+    if (const char *e = getenv("YB_PRIO")) if (atoi(e) == 0) prioHi = prioLo;
     for (auto &s : d.slots) {
-        CUDA_TRY(d, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUDA_TRY(d, cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prioHi));
         for (auto &e : s.ev) CUDA_TRY(d, cudaEventCreate(&e));
         for (int b = 0; b < NBINS; ++b) {
-            CUDA_TRY(d, cudaStreamCreateWithFlags(&s.binStream[b], cudaStreamNonBlocking));
+            CUDA_TRY(d, cudaStreamCreateWithPriority(&s.binStream[b], cudaStreamNonBlocking, prioLo));
             CUDA_TRY(d, cudaEventCreateWithFlags(&s.binDone[b], cudaEventDisableTiming));
         }
     }
@@ -511,37 +519,78 @@ inline bool in_block(const std::vector<HostBlock> &blocks, const unsigned char *
 // (A, B, LB, RB: straight from the caller's buffers when those lie in yb_host_alloc memory, through the slot's pinned
 // staging buffer otherwise -- a memcpy either way, no band row is read on the host) and K0 behind them.  Nothing here waits
 // for the device.
-int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t count, size_t tbCapacity, bool allBins = false) {
+int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t first, int64_t count, size_t tbCapacity, bool allBins = false,
+                 bool rawBands = false) {
     const double t0 = now_ms();
+    // delta-coded bands (yb_band_expand): worth it when the host has threads to spare -- it reads every band row once so
+    // that PCIe carries a quarter of it; with few threads per device the copy of the raw rows is the faster way
+    const bool pack = !rawBands && count > 0 && (ctx->bandPack > 0 || (ctx->bandPack < 0 && d.helpers >= 8));
     s.tPack0 = t0;
     s.first = first;
     s.off.resize((size_t)count + 1);
-    // ---- dimension-only layout + the address range of each stream (serial, a few ns per job) -------------------------------
+    // ---- dimension-only layout + the address range of each stream: per chunk of jobs on the helper threads (offsets
+    // relative to the chunk), then one serial pass over the chunks ------------------------------------------------------------
     struct Stream { const unsigned char *lo = nullptr, *hi = nullptr; size_t payload = 0; bool direct = false; size_t devOff = 0, bytes = 0; };
     Stream st[4];
-    size_t rows = 0, cols = 0, words = 0, sched = 0;
+    size_t rows = 0, cols = 0, words = 0, sched = 0, pkBytes = 0;
     int maxK = 0, maxN = 0, minK = 0x7fffffff, nLongMax = 0;
     size_t tbEst = 0;
-    for (int64_t i = 0; i < count; ++i) {
-        const yb_job &j = jobs[first + i];
-        Slot::Off &o = s.off[(size_t)i];
-        o.a = st[0].payload; o.b = st[1].payload; o.lb = st[2].payload; o.rb = st[3].payload;
-        o.row = rows; o.col = cols; o.sched = sched; o.script = (uint32_t)words;
-        if (!dims_ok(j)) continue;
-        maxK = std::max(maxK, j.K); minK = std::min(minK, j.K); maxN = std::max(maxN, j.N);
-        tbEst += 32ull * ((size_t)j.M + j.N + 3 * (((size_t)j.M + 31) >> 5) + 40);        // one warp, a diagonal band
-        if (j.M + j.N >= ctx->tbLong) ++nLongMax;
-        const unsigned char *ptr[4] = {j.A, j.B, reinterpret_cast<const unsigned char *>(j.LB), reinterpret_cast<const unsigned char *>(j.RB)};
-        const size_t len[4] = {(size_t)j.K * j.M, (size_t)j.L * j.N, (size_t)(j.M + 1) * 4, (size_t)(j.M + 1) * 4};
-        for (int k = 0; k < 4; ++k) {
-            if (!st[k].lo || ptr[k] < st[k].lo) st[k].lo = ptr[k];
-            if (!st[k].hi || ptr[k] + len[k] > st[k].hi) st[k].hi = ptr[k] + len[k];
-            st[k].payload += align_up(len[k], 64);               // (staged layout: sections of whole 64-byte lines)
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(256, count / (4 * (int64_t)d.helpers)));
+    const int64_t nChunks = (count + chunk - 1) / chunk;
+    struct Part {
+        Slot::Off tot{};
+        const unsigned char *lo[4] = {nullptr, nullptr, nullptr, nullptr}, *hi[4] = {nullptr, nullptr, nullptr, nullptr};
+        int maxK = 0, maxN = 0, minK = 0x7fffffff, nLong = 0;
+        size_t tbEst = 0;
+    };
+    std::vector<Part> part((size_t)nChunks);
+    const int tbLongMoves = ctx->tbLong;
+    d.pool->run(count, chunk, [&](int64_t lo0, int64_t hi0) {
+        for (int64_t c = lo0 / chunk; c * chunk < hi0; ++c) {                 // (a run without helpers gets [0, count) at once)
+            Part P;
+            Slot::Off r{};
+            for (int64_t i = c * chunk, e = std::min<int64_t>(count, (c + 1) * chunk); i < e; ++i) {
+                const yb_job &j = jobs[first + i];
+                s.off[(size_t)i] = r;
+                if (!dims_ok(j)) continue;
+                r.pk += align_up(sizeof(BandPackHdr) + 2 * align_up((size_t)j.M + 1, 4), 16);
+                P.maxK = std::max(P.maxK, j.K); P.minK = std::min(P.minK, j.K); P.maxN = std::max(P.maxN, j.N);
+                P.tbEst += 32ull * ((size_t)j.M + j.N + 3 * (((size_t)j.M + 31) >> 5) + 40);      // one warp, a diagonal band
+                if (j.M + j.N >= tbLongMoves) ++P.nLong;
+                const unsigned char *ptr[4] = {j.A, j.B, reinterpret_cast<const unsigned char *>(j.LB), reinterpret_cast<const unsigned char *>(j.RB)};
+                const size_t len[4] = {(size_t)j.K * j.M, (size_t)j.L * j.N, (size_t)(j.M + 1) * 4, (size_t)(j.M + 1) * 4};
+                for (int k = 0; k < 4; ++k) {
+                    if (!P.lo[k] || ptr[k] < P.lo[k]) P.lo[k] = ptr[k];
+                    if (!P.hi[k] || ptr[k] + len[k] > P.hi[k]) P.hi[k] = ptr[k] + len[k];
+                }
+                r.a += align_up(len[0], 64); r.b += align_up(len[1], 64);       // (staged layout: sections of whole 64-byte lines)
+                r.lb += align_up(len[2], 64); r.rb += align_up(len[3], 64);
+                r.row += (size_t)j.M + 1; r.col += (size_t)j.N + 1; r.sched += sched_ints(j);
+                r.script += (uint32_t)(((size_t)j.M + j.N + 15) / 16);
+            }
+            P.tot = r;
+            part[(size_t)c] = P;
         }
-        rows += (size_t)j.M + 1; cols += (size_t)j.N + 1; sched += sched_ints(j);
-        words += ((size_t)j.M + j.N + 15) / 16;
+    });
+    {
+        Slot::Off run{};
+        for (int64_t c = 0; c < nChunks; ++c) {
+            Part &P = part[(size_t)c];
+            const Slot::Off t = P.tot;
+            P.tot = run;                                                      // now: the chunk's base offsets
+            run.a += t.a; run.b += t.b; run.lb += t.lb; run.rb += t.rb; run.row += t.row; run.col += t.col; run.sched += t.sched;
+            run.script += t.script; run.pk += t.pk;
+            for (int k = 0; k < 4; ++k) {
+                if (P.lo[k] && (!st[k].lo || P.lo[k] < st[k].lo)) st[k].lo = P.lo[k];
+                if (P.hi[k] && (!st[k].hi || P.hi[k] > st[k].hi)) st[k].hi = P.hi[k];
+            }
+            maxK = std::max(maxK, P.maxK); minK = std::min(minK, P.minK); maxN = std::max(maxN, P.maxN);
+            nLongMax += P.nLong; tbEst += P.tbEst;
+        }
+        st[0].payload = run.a; st[1].payload = run.b; st[2].payload = run.lb; st[3].payload = run.rb;
+        rows = run.row; cols = run.col; sched = run.sched; words = run.script; pkBytes = run.pk;
     }
-    s.off[(size_t)count] = Slot::Off{st[0].payload, st[1].payload, st[2].payload, st[3].payload, rows, cols, sched, (uint32_t)words};
+    s.off[(size_t)count] = Slot::Off{st[0].payload, st[1].payload, st[2].payload, st[3].payload, rows, cols, sched, (uint32_t)words, pkBytes};
     s.y16 = (int64_t)std::min(maxK, ctx->maxDepth) * ctx->sc.gap_open <= 32767;
     s.count = count;
     s.scriptWords = words;
@@ -554,12 +603,24 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
         if (!x.lo) { x.devOff = devOff; x.bytes = 0; continue; }
         const unsigned char *lo = reinterpret_cast<const unsigned char *>(reinterpret_cast<uintptr_t>(x.lo) & ~(uintptr_t)63);
         const size_t span = (size_t)(x.hi - lo);
+        if (pack && k >= 2) {                                      // restored on the device, in the staged layout
+            x.direct = false; x.bytes = 0; x.devOff = devOff;
+            devOff += align_up(x.payload, 256) + 256;
+            continue;
+        }
         x.direct = ctx->directCopy && span <= x.payload + x.payload / 2 + 65536 && in_block(ctx->hostBlocks, lo, x.hi);
         if (x.direct) { x.lo = lo; x.bytes = span; }
         else { x.bytes = x.payload; stageOff[k] = s.metaBytes + stagedBytes; stagedBytes += align_up(x.payload, 256); }
         x.devOff = devOff;
         devOff += align_up(x.bytes, 256) + 256;                    // (slack: K1 reads whole words around a row)
     }
+    // delta-coded bands: [section offset per pair | sections | exception list], contiguous on the host and on the device
+    const size_t excCap = pack ? (size_t)count + 4096 : 0;
+    const size_t pkArr = align_up((size_t)count * 8, 256), pkSec = align_up(pkBytes, 256);
+    const size_t pkHost = s.metaBytes + stagedBytes, pkDev = devOff;
+    if (pack) { stagedBytes += pkArr + pkSec + align_up(excCap * sizeof(BandExc), 256); devOff += pkArr + pkSec + align_up(excCap * sizeof(BandExc), 256); }
+    std::atomic<int64_t> excFill{0};
+    std::atomic<bool> excOverflow{false};
     const size_t copied = devOff;
     s.tbBaseOff = devOff; devOff += align_up((size_t)count * 8, 256);
     s.orderOff = devOff; devOff += align_up((size_t)count * 4, 256);
@@ -584,11 +645,15 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
     d.t_layout += t1 - t0;
 
     // ---- pair descriptors (+ staged copies) on the helper threads -------------------------------------------------------
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(256, count / (4 * (int64_t)d.helpers)));
     d.pool->run(count, chunk, [&](int64_t lo0, int64_t hi0) {
         for (int64_t i = lo0; i < hi0; ++i) {
             const yb_job &j = jobs[first + i];
-            const Slot::Off &o = s.off[(size_t)i];
+            Slot::Off o = s.off[(size_t)i];
+            {
+                const Slot::Off &b = part[(size_t)(i / chunk)].tot;
+                o.a += b.a; o.b += b.b; o.lb += b.lb; o.rb += b.rb; o.row += b.row; o.col += b.col; o.sched += b.sched;
+                o.script += b.script; o.pk += b.pk;
+            }
             PairMeta pm;
             memset(&pm, 0, sizeof pm);
             if (dims_ok(j)) {
@@ -601,18 +666,43 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
                     if (st[k].direct) dev[k] = st[k].devOff + (size_t)(ptr[k] - st[k].lo);
                     else {
                         dev[k] = st[k].devOff + so[k];
-                        copy_nt64(h + stageOff[k] + so[k], ptr[k], len[k]);
+                        if (!(pack && k >= 2)) copy_nt64(h + stageOff[k] + so[k], ptr[k], len[k]);
                     }
+                }
+                if (pack) {
+                    unsigned char *sec = h + pkHost + pkArr + o.pk;
+                    const size_t a4 = align_up((size_t)j.M + 1, 4);
+                    BandPackHdr *hd = reinterpret_cast<BandPackHdr *>(sec);
+                    uint8_t *dl = sec + sizeof(BandPackHdr), *dr = dl + a4;
+                    memset(dl + a4 - 4, 0, 4); memset(dr + a4 - 4, 0, 4);          // pad bytes past row M
+                    const int n1 = yb_band_pack(j.M, j.LB, dl), n2 = yb_band_pack(j.M, j.RB, dr);
+                    hd->LB0 = j.LB[0]; hd->RB0 = j.RB[0]; hd->nExc = n1 + n2; hd->excStart = 0;
+                    if (n1 + n2 > 0) {
+                        const int64_t at = excFill.fetch_add(n1 + n2);
+                        if ((size_t)(at + n1 + n2) > excCap) { excOverflow = true; hd->nExc = 0; }
+                        else {
+                            hd->excStart = (int)at;
+                            BandExc *ex = reinterpret_cast<BandExc *>(h + pkHost + pkArr + pkSec) + at;
+                            for (int r = 1; r <= j.M; ++r)
+                                if (dl[r] == 255) *ex++ = BandExc{r, (int)((uint32_t)j.LB[r] - (uint32_t)j.LB[r - 1])};
+                            for (int r = 1; r <= j.M; ++r)
+                                if (dr[r] == 255) *ex++ = BandExc{j.M + 1 + r, (int)((uint32_t)j.RB[r] - (uint32_t)j.RB[r - 1])};
+                        }
+                    }
+                    reinterpret_cast<unsigned long long *>(h + pkHost)[i] = pkDev + pkArr + o.pk;
                 }
                 pm.offA = dev[0]; pm.offB = dev[1]; pm.offBand = dev[2]; pm.offBand2 = dev[3];
                 pm.offSched = s.schedOff + o.sched * 4;
                 pm.rowBase = o.row; pm.colBase = o.col; pm.scriptBase = o.script;
                 pm.lgLanes = 5;
             }
+            else if (pack) reinterpret_cast<unsigned long long *>(h + pkHost)[i] = BAND_RAW;
             metas[i] = pm;
         }
         _mm_sfence();
     });
+    // more band steps outside 0..254 than the exception list holds (no band pre_yama builds does that): the plain way
+    if (excOverflow) return slot_prepare(ctx, d, s, jobs, first, count, tbCapacity, allBins, true);
     const double t2 = now_ms();
     d.t_par += t2 - t1;
 
@@ -628,6 +718,12 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
         CUDA_TRY(d, cudaMemcpyAsync(dIn + st[k].devOff, src, st[k].bytes, cudaMemcpyHostToDevice, q));
         s.h2dBytes += st[k].bytes;
         if (!st[k].direct) d.staged_bytes += (int64_t)st[k].bytes;
+    }
+    if (pack) {
+        const size_t n = pkArr + pkSec + (size_t)excFill.load() * sizeof(BandExc);
+        CUDA_TRY(d, cudaMemcpyAsync(dIn + pkDev, h + pkHost, n, cudaMemcpyHostToDevice, q));
+        s.h2dBytes += n;
+        d.staged_bytes += (int64_t)n;
     }
     (void)copied;
     CUDA_TRY(d, cudaEventRecord(s.ev[1], q));
@@ -691,6 +787,12 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
     if (count > 0) {
         const int warpsPerCta = PLAN_THREADS / 32;
         const unsigned blocks = (unsigned)std::min<int64_t>((count + warpsPerCta - 1) / warpsPerCta, (int64_t)d.sms * 8);
+        if (pack) {
+            yb_band_expand<<<blocks, PLAN_THREADS, 0, q>>>(reinterpret_cast<const PairMeta *>(dIn), (int)count, dIn,
+                                                           reinterpret_cast<const unsigned long long *>(dIn + pkDev),
+                                                           reinterpret_cast<const BandExc *>(dIn + pkDev + pkArr + pkSec));
+            d.launches++;
+        }
         yb_plan_kernel<<<blocks, PLAN_THREADS, 0, q>>>(reinterpret_cast<PairMeta *>(dIn), (int)count, dIn, outs, tbBase, bucketOf, pp);
         yb_plan_scan<<<1, 1024, 0, q>>>((int)count, tbBase, bucketOf, bucketCount, bucketFill, outs, reinterpret_cast<PairMeta *>(dIn), dsum, pp.tbLong,
                                        (unsigned long long)tbCapacity, s.launchMask);
@@ -1141,6 +1243,11 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     *out = nullptr;
     int avail = 0;
     const double tc0 = now_ms();
+    // A wave runs on ten streams (copies + short kernels, one per fill bin) and eight waves are in flight: with the
+    // default of 8 hardware work queues unrelated streams share a queue and wait for each other -- a wave's copy behind
+    // another wave's fill (measured on cfg2: 12.2 -> 11.1 ms per end-to-end call with 32).  Only effective when this call
+    // is what creates the process's CUDA context; a host that initialises CUDA itself sets the variable itself (bench.py).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     if (cudaGetDeviceCount(&avail) != cudaSuccess || avail < 1) return YB_ERR_CUDA;
     const double tc1 = now_ms();
     yb_ctx *ctx = new yb_ctx();
@@ -1174,6 +1281,7 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     }
     if (const char *e = getenv("YB_WAVE_TB_MB")) ctx->waveTbBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_DIRECT")) ctx->directCopy = atoi(e) != 0;
+    if (const char *e = getenv("YB_BAND_PACK")) ctx->bandPack = atoi(e) != 0;
     if (const char *e = getenv("YB_ONLY_BINS")) for (auto &d : ctx->devs) d.onlyBins = (int)strtol(e, nullptr, 0);
     if (const char *e = getenv("YB_FILL_SPLIT")) for (auto &d : ctx->devs) d.fillSplit = std::max(1, atoi(e));
     if (const char *e = getenv("YB_SLACK")) ctx->slackBulk = std::max(1, atoi(e));

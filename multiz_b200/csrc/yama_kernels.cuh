@@ -55,9 +55,9 @@ struct PairMeta {
     // (the byte offset of the pair's traceback matrix depends on the band, not only on the dimensions: it lives in a
     //  separate per-wave array so that the host can fill the metas in parallel, before those offsets are known)
     int nSteps;                        // wavefront steps of this pair (K0, from the schedule)
-    int pad;
+    int skew;                          // extra steps between the last lane of a warp and the first lane of the next (fill_body3; else 0)
     int lgLanes;                       // log2 of the wavefront width: 32 lanes (one warp) ... 256 lanes (a CTA) per pair
-    int cls;                           // kernel class: 0 fill_body (RowRec / ColRec), 1 fill_body2, 2 fill_body2 KEYED (RowRec2 / bulk ColRec)
+    int cls;                           // kernel class: 0 fill_body / fill_body3 (RowRec / ColRec), 1 fill_body2, 2 fill_body2 KEYED (RowRec2 / bulk ColRec)
 };
 
 // LB[r] / RB[r] of a pair
@@ -81,7 +81,8 @@ struct __align__(16) RowRec {
     int RB16, LBp16;                   // q3: 16*RB[r], 16*LB[r-1]
     int off;                           //     wavefront schedule: this row computes column (step - off)
     int RBn;                           //     warp-sized wavefronts: RB[r+1] (RB[r] on the last row), how far the row below
-                                       //     reads us; CTA-sized wavefronts: 16*RB[r-1] + 16, where the row above ends
+                                       //     reads us; CTA-sized wavefronts: 16*RB[r-1] + 16, where the row above ends;
+                                       //     fill_body3 (PairMeta::skew > 0): 16*LB[r-2] (INT_MAX for row 1), and `off` is 16*off
 };
 
 // Traceback matrix layout: the wavefront (B = 32 << (lgLanes-5) lanes: one warp, or the warps of a CTA) advances one
@@ -223,6 +224,11 @@ yb_profile_kernel(const PairMeta *__restrict__ metas, const unsigned char *__res
         rr.off = r >= 1 ? sched[(r - 1) >> pm.lgLanes] + ((r - 1) & ((1 << pm.lgLanes) - 1)) : 0;
         rr.RBn = r < M ? band.rb(r + 1) : band.rb(r);
         if (pm.lgLanes > 5 && r >= 1) rr.RBn = band.rb(r - 1) * 16 + 16;      // (row 0 keeps RB[1]: the ring initialisation)
+        if (pm.skew > 0 && r >= 1) {                                           // fill_body3
+            const int l = (r - 1) & ((1 << pm.lgLanes) - 1);
+            rr.off = 16 * (rr.off + pm.skew * (l >> 5));
+            rr.RBn = r >= 2 ? band.lb(r - 2) * 16 : 0x7fffffff;
+        }
         if (r >= 1) {
             const unsigned char *now = A + (size_t)(r - 1) * K;
             const Census q = census(now, r > 1 ? now - K : nullptr, K);    // mz_yama.c:175,213 (s==0 when row==1)
@@ -674,9 +680,24 @@ __device__ __forceinline__ void profile_bulk(const PairMeta &pm, const unsigned 
 #ifndef YB_F2_WARPS
 #define YB_F2_WARPS 8
 #endif
+// YB_F2_SW: a lane that has finished its row moves to its next row at the next step that is a multiple of YB_F2_SW (1, 2, 4
+// or 8) instead of at once.  The row switch is the one divergent region of the kernel -- some forty instructions executed for
+// a single lane, about every second step of a warp whose 32 rows end one step apart -- and with YB_F2_SW = 4 up to four lanes
+// share one pass through it.  The price: a lane idles up to YB_F2_SW - 1 steps past its row (handing down MININT, as a lane
+// outside its row always does), so the schedule leaves that many more steps between blocks of rows (PlanParams::slackBulk =
+// 3 + YB_F2_SW - 1), one more compare per step (c <= RB[r]), and the final scores are picked up where cell (M,N) is computed
+// -- in one of the last two 8-step groups, which run a copy of the step code with that check -- not at the switch.
+// Measured on cfg2 (profiles/r2_ab_sw.txt): 1 -> 5.69 ms, 2 -> 5.98 ms, 4 -> 5.44 ms per fill.
+#ifndef YB_F2_SW
+#define YB_F2_SW 4
+#endif
+constexpr int F2_SW = YB_F2_SW;
 constexpr int F2_WARPS = YB_F2_WARPS;                         // pairs in flight per CTA
 constexpr size_t COL_PAD = 32768;                             // bytes of slack before and after a wave's column records: lanes outside
                                                               // their row read (and discard) up to about two band rows off either end
+
+struct FalseTag { static constexpr bool value = false; };
+struct TrueTag { static constexpr bool value = true; };
 
 template <int RING, bool KEYED>
 __device__ __forceinline__ void
@@ -789,7 +810,9 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
         int Cd = MIN_C, Dd = MIN_D, Id = MIN_I;               // grid point (r-1, c-1)
         __syncwarp();
 
-        for (int t8 = 0; t8 < nSteps; t8 += 8) {              // (nSteps is a multiple of 8)
+        // one group of eight steps; CHECK: this group may hold cell (M,N) (F2_SW > 1 only)
+        auto group = [&](const int t8, auto checkTag) {
+            constexpr bool CHECK = decltype(checkTag)::value;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 // ---- grid point (r-1, c): the last cell of the lane above, or MININT if it is outside its row --------
@@ -798,15 +821,16 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
                     const uint4 up = lds128(and_xor((unsigned)c16, RMASK, ringAddr));
                     Cu = (int)up.x; Du = (int)up.y; Iu = (int)up.z;
                 }
-                if (c16 > RB16) {
+                if ((F2_SW == 1 || (u % F2_SW) == 0) && c16 > RB16) {
                     // ---- this lane finished its row: move one wavefront width down -----------------------------------
                     // the row below keeps reading us up to its own right bound and must find never-written dp[] entries
                     // there (mz_yama.c:93-94): an idle lane hands down MININT by itself, the ring needs them written
                     if (lane == B - 1) {
                         int RBn;
                         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(RBn) : "r"(stash) : "memory");
+                        // (F2_SW > 1: the columns it idled over since the row ended were written step by step, below)
 #pragma unroll 1
-                        for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
+                        for (int cc = (F2_SW == 1 ? RB16 + 16 : c16) >> 4; cc <= RBn; ++cc)
                             sts128(and_xor((unsigned)cc << 4, RMASK, ringAddr), MIN_C, MIN_D, MIN_I, 0u);
                     }
                     r += B;
@@ -817,15 +841,17 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
                         if (r + B <= M) prefetch_row();               // (after the slot's words were consumed)
                     } else {
                         // a lane that runs out of rows idles; the one that just finished row M leaves the final scores
-                        if (r - B == M) { outs[p].C = unkey<KEYED>(Cl); outs[p].D = unkey<KEYED>(Dl); outs[p].I = unkey<KEYED>(Il); }
+                        if (F2_SW == 1 && r - B == M) { outs[p].C = unkey<KEYED>(Cl); outs[p].D = unkey<KEYED>(Dl); outs[p].I = unkey<KEYED>(Il); }
                         LB16 = 0x7fffffff; RB16 = 0x7fffffff; LBc16 = 0x7fffffff; LBst16 = 0x7fffffff;
                         cp = colBase - 16 * u;                        // (idles over the pair's first columns)
                     }
                 }
-                const bool active = (c16 >= LB16);
+                // F2_SW > 1: a lane may sit past the end of its row for a few steps; it is outside its row there
+                const bool in = F2_SW == 1 || c16 <= RB16;
+                const bool active = (c16 >= LB16) && in;
                 const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(cp + 16 * u));       // column record of column c
                 int vI, vC, vD;
-                const bool hasI = c16 > LB16, hasC = c16 > LBc16;
+                const bool hasI = (c16 > LB16) && in, hasC = (c16 > LBc16) && in;
                 if (!KEYED) acc >>= 8;                       // make room for this cell's byte (bits 24..31)
                 // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
                 {
@@ -867,6 +893,7 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
                 }
                 vI = hasI ? vI : MIN_I;
                 if (c16 >= LBst16) sts128(and_xor((unsigned)c16, RMASK, ringAddr), vC, vD, vI, 0u);
+                if (F2_SW > 1 && CHECK && c16 == RB16 && r == M) {     /* cell (M,N): RB[M] == N */ outs[p].C = unkey<KEYED>(vC); outs[p].D = unkey<KEYED>(vD); outs[p].I = unkey<KEYED>(vI); }
                 // four steps of this lane = one 32-bit word of its 8-step group (see tb_byte)
                 if (u == 3) tbp[0] = acc;
                 if (u == 7) tbp[1] = acc;
@@ -887,8 +914,280 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
             }
             cp += 128;
             tbp += 2 * B;
+        };
+        {                                                      // (nSteps is a multiple of 8; cell (M,N) lies in its last 9 steps)
+            int t8 = 0;
+            if (F2_SW > 1) {
+                for (; t8 < nSteps - 16; t8 += 8) group(t8, FalseTag{});
+                for (; t8 < nSteps; t8 += 8) group(t8, TrueTag{});
+            } else {
+                for (; t8 < nSteps; t8 += 8) group(t8, FalseTag{});
+            }
         }
         __syncwarp();
+    }
+}
+
+// =================================================================================================
+// K2, wide bands (fill_body3): one CTA of G warps per pair, for band rows of hundreds to thousands of cells on long pairs
+// (BASELINE configs[4]: K+L = 100, M = 10^4, R = 300) -- pairs whose scores approach the int32 range, so the arithmetic is
+// fill_body's (byte counts x gap_open, existence multipliers), while the communication is rebuilt around what ncu showed of
+// fill_body<2048,8,1> on cfg5 (profiles/r2_fill_cta_summary.md: 52 % of the issue slots, one bar.sync of 256 threads and one
+// LDS.128 + STS.128 per lane and step):
+//
+//  * inside a warp (C,D,I) of the row above arrive by three shuffles, as in fill_body2; the existence multipliers of a grid
+//    point are not handed down at all: the C node of (r-1,c) exists iff c > LB[r-2], its I node iff c > LB[r-1]
+//    (mz_yama.c:163-165, :202-204), two compares against numbers the row record carries;
+//  * the warps of a CTA are NOT in lock step.  Lane 31 of warp w leaves its (C,D,I) of every step in a small FIFO indexed by
+//    the step; lane 0 of warp w+1 picks up the entry of eight steps earlier -- the schedule puts F3_SKEW = 7 extra steps
+//    between the two lanes (PairMeta::skew; K0, K1 and K3 know) -- so a warp needs its predecessor to have FINISHED the
+//    previous group of eight steps, not to stand at the same step.  Each warp publishes the number of groups it has completed
+//    (one shared-memory word, written by lane 31 after a fence); before a group, lane 0 waits until the warp it reads from is
+//    far enough and the warp that reads it is not more than F3_BP groups behind (the FIFO and the ring are finite).  No CTA
+//    barrier inside a pair; warps drift a few groups apart and hide each other's row switches and column loads;
+//  * the last warp hands a band row to the first through the ring, indexed by the column as ever; the first warp works out
+//    from the schedule how many groups it may run ahead of the last (the distance in steps between a block of rows and the
+//    next is known when lane 0 switches rows);
+//  * a lane's next row record is copied global -> shared (cp.async) while it walks its current row.
+// =================================================================================================
+constexpr int F3_SKEW = 7;          // steps between lane 31 of a warp and lane 0 of the next, beyond the usual one
+constexpr int F3_FIFO = 64;         // entries of an inter-warp FIFO
+constexpr int F3_BP = 5;            // groups a warp may run ahead of the warp that reads it (FIFO: 64 steps = 8 groups, minus the
+                                    // group being written, the group being read and the skew)
+// ring entries a band row of `wmax` cells needs: the row, the distance in columns between the lane that writes the ring and
+// the lane that reads it (B - 1 lanes + the skews), the drift allowed between their warps, and a margin
+__host__ __device__ constexpr int f3_ring_need(int wmax, int G) { return wmax + 32 * G + F3_SKEW * (G - 1) + 8 * (F3_BP + 1) + 16; }
+
+__device__ __forceinline__ int ld_volatile_shared(unsigned addr) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared(unsigned addr, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+template <int RING, int G, bool Y16>
+__device__ __forceinline__ void
+fill_body3(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase, const int *__restrict__ binRange,
+           int *__restrict__ queue, const RowRec *__restrict__ rowPool,
+           const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
+           const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, const int gapOpen, const int gapExt) {
+    const int *order = orderBase + __ldg(binRange);
+    const int nPairs = __ldg(binRange + 1) - __ldg(binRange);
+    // (the pair descriptors sit at the start of the wave's input blob: the band rows are reached through them)
+    const unsigned char *blob = reinterpret_cast<const unsigned char *>(metas);
+    constexpr int B = 32 * G;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned RMASK = (unsigned)(RING * 16 - 16);
+    constexpr unsigned FMASK = (unsigned)(F3_FIFO * 16 - 16);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [ ring: RING records | G FIFOs of F3_FIFO records (FIFO w is written by warp w) | B row slots of 64 B | G progress words | queue slot ]
+    const int w = (int)(threadIdx.x >> 5);
+    const int lane = (int)(threadIdx.x & 31);
+    const int l = (int)threadIdx.x;                               // lane within the pair's wavefront
+    const unsigned ringAddr = smem_u32(smem_raw);
+    const unsigned fifoW = ringAddr + RING * 16 + (unsigned)w * (F3_FIFO * 16);
+    const unsigned fifoR = ringAddr + RING * 16 + (unsigned)((w + G - 1) % G) * (F3_FIFO * 16);
+    const unsigned rowSlot = ringAddr + RING * 16 + G * F3_FIFO * 16 + (unsigned)l * 64u;
+    const unsigned doneAddr = ringAddr + RING * 16 + G * F3_FIFO * 16 + B * 64;
+    const unsigned slotAddr = doneAddr + G * 4;
+    const unsigned donePrev = doneAddr + 4u * (unsigned)((w + G - 1) % G), doneNext = doneAddr + 4u * (unsigned)((w + 1) % G);
+    const int nGO = -gapOpen;
+
+    for (;;) {
+        int slot;
+        if (l == 0) st_volatile_shared(slotAddr, atomicAdd(queue, 1));
+        if (l < G) st_volatile_shared(doneAddr + 4u * l, 0);
+        __syncthreads();
+        slot = ld_volatile_shared(slotAddr);
+        if (slot >= nPairs) break;
+        const int p = order[slot];
+        const PairMeta pm = metas[p];
+        const int M = pm.M;
+        const RowRec *rows = rowPool + pm.rowBase;
+        const ColRec *cols = colPool + pm.colBase;
+        const int *rbArr = reinterpret_cast<const int *>(blob + pm.offBand2);
+        unsigned char *tb = tbPool + __ldg(tbBase + p);
+        const unsigned nKGE_lo = launder((unsigned)(-(pm.K * gapExt)) & 0xffffu);   // dp2a.hi weight of byte 2 (ndB)
+        const int KGE = pm.K * gapExt;
+        const int nSteps = pm.nSteps;
+        const int N16 = pm.N * 16;
+        const int KnGO = pm.K * nGO;                        // I-node y / z charge per residue / per closing gap of B
+
+        // ---- row 0 (mz_yama.c:83-94) into the ring (first warp) --------------------------------------------------------
+        if (w == 0) {
+            const int RB0 = rows[0].RB16 >> 4;
+            const int RB1 = __ldg(rbArr + 1);
+            int carry = 0;
+            for (int base = 0; base <= RB1; base += 32) {
+                int c = base + lane;
+                int nd = 0;
+                if (c >= 1 && c <= RB0) nd = (int)((__ldg(&cols[c].w0) >> 16) & 0xffu);
+                int inc = nd;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int o = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                const unsigned a = ringAddr + (((unsigned)c << 4) & RMASK);
+                if (c <= RB0) {
+                    int I0 = -(carry + inc) * KGE;
+                    if (c == 0) sts128(a, 0, 0, 0, 0u);                    // (0,0): nothing is ever charged
+                    else sts128(a, MININT, MININT, I0, 0u);                // only the I node exists in row 0
+                } else if (c <= RB1) {
+                    sts128(a, MININT, MININT, MININT, 0u);                 // stale dp[] entry, mz_yama.c:93-94
+                }
+                carry += __shfl_sync(FULL, inc, 31);
+            }
+        }
+
+        // ---- per-lane row state ------------------------------------------------------------------------------------------
+        int r = l + 1;
+        unsigned avXC = 0, avYC = 0, avZC = 0, avXI = 0, avXD = 0, avYD = 0, avZD = 0;
+        int gIrow = 0, gIz = 0;
+        unsigned w01 = 0, w23 = 0, w45 = 0;
+        int eD = 0, LB16 = 0x7fffffff, RB16 = 0x7fffffff, LBp16 = 0x7fffffff, LBpp16 = 0x7fffffff, c16 = 0, off16 = 0;
+        // the lane that leaves its values for another warp: every step into the FIFO (warps 0..G-2), its row into the ring (warp G-1)
+        int LBst16 = 0x7fffffff;
+        int needAdj = -(1 << 24);                              // warp 0: groups it must stay behind warp G-1, see the row switch
+        const unsigned char *pf = reinterpret_cast<const unsigned char *>(rows + r + B);     // the record the next switch prefetches
+        auto unpack_row = [&](const uint4 &q0, const uint4 &q1, const uint4 &q2, const uint4 &q3, int t16) {
+            avXC = q0.x; avYC = q0.y; avZC = q0.z; avXI = q0.w;
+            avXD = q1.x; avYD = q1.y; avZD = q1.z; eD = (int)q1.w;
+            w01 = q2.x; w23 = q2.y; w45 = q2.z; LB16 = (int)q2.w;
+            RB16 = (int)q3.x; LBp16 = (int)q3.y; off16 = (int)q3.z; LBpp16 = (int)q3.w;
+            c16 = t16 - off16;
+            gIrow = r < M ? (Y16 ? (KnGO & 0xffff) : KnGO) : 0;     // mz_yama.c:123: no I-node gap-open on the last row
+            gIz = Y16 ? gIrow << 16 : gIrow;                        // the z candidate's weight sits on byte 1 (b10)
+            if (lane == 31) LBst16 = (w < G - 1) ? (int)0x80000000 : LB16;
+        };
+        auto prefetch_row = [&]() {
+            cp_async16(rowSlot, pf); cp_async16(rowSlot + 16, pf + 16);
+            cp_async16(rowSlot + 32, pf + 32); cp_async16(rowSlot + 48, pf + 48);
+            cp_async_commit();
+            pf += B * sizeof(RowRec);
+        };
+        if (lane == 31 && w < G - 1) LBst16 = (int)0x80000000;      // (a FIFO lane stores whether or not it has a row)
+        if (r <= M) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(rows + r);
+            const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+            unpack_row(q0, q1, q2, q3, 0);
+            if (r + B <= M) prefetch_row();
+        }
+        unsigned acc = 0;
+        unsigned *tbp = reinterpret_cast<unsigned *>(tb) + l * 2;      // this lane's two words of an 8-step group (see tb_byte)
+        int Cl = MININT, Dl = MININT, Il = MININT, gCl = 0, gIl = 0;     // grid point (r, c-1)
+        int Cd = MININT, Dd = MININT, Id = MININT, gCd = 0, gId = 0;     // grid point (r-1, c-1)
+        unsigned fr = (unsigned)(-8 * 16) & FMASK, fw = 0;               // FIFO slots (byte offsets) of step t-8 (read) and t (write)
+        __syncthreads();
+
+        for (int t8 = 0; t8 < nSteps; t8 += 8) {
+            const int g = t8 >> 3;
+            // ---- wait: the warp we read from has finished the groups our reads come from; the warp that reads us is near ----
+            if (lane == 0) {
+                const int needPrev = (w == 0) ? g + needAdj : g;
+                while (ld_volatile_shared(donePrev) < needPrev) __nanosleep(20);
+                while (ld_volatile_shared(doneNext) < g - F3_BP) __nanosleep(20);
+                __threadfence_block();
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                // ---- grid point (r-1, c) ------------------------------------------------------------------------------
+                int Cu = __shfl_up_sync(FULL, Cl, 1), Du = __shfl_up_sync(FULL, Dl, 1), Iu = __shfl_up_sync(FULL, Il, 1);
+                if (lane == 0) {
+                    const uint4 up = lds128(w == 0 ? ringAddr + ((unsigned)c16 & RMASK) : fifoR + fr);
+                    Cu = (int)up.x; Du = (int)up.y; Iu = (int)up.z;
+                }
+                if (c16 > RB16) {
+                    // ---- this lane finished its row ------------------------------------------------------------------
+                    if (l == B - 1) {
+                        // the row below reads us up to its own right bound and must find never-written dp[] entries there
+                        const int RBn = r < M ? __ldg(rbArr + r + 1) : (RB16 >> 4);
+#pragma unroll 1
+                        for (int cc = (RB16 >> 4) + 1; cc <= RBn; ++cc)
+                            sts128(ringAddr + (((unsigned)cc << 4) & RMASK), MININT, MININT, MININT, 0u);
+                    }
+                    r += B;
+                    if (r <= M) {
+                        const int offOld = off16;
+                        cp_async_wait_all();
+                        const uint4 q0 = lds128(rowSlot), q1 = lds128(rowSlot + 16), q2 = lds128(rowSlot + 32), q3 = lds128(rowSlot + 48);
+                        unpack_row(q0, q1, q2, q3, (t8 + u) * 16);
+                        if (r + B <= M) prefetch_row();
+                        if (l == 0) {
+                            // The ring entries of the block of rows above were written `gap` steps before we read them
+                            // (the schedule: >= 8).  Entries read in group g come from the last warp's groups up to
+                            // g + floor((7 - gap) / 8): that many it must have completed.
+                            const int gap = ((off16 - offOld) >> 4) - (B - 1) - F3_SKEW * (G - 1);
+                            needAdj = 1 + ((7 - gap) >> 3);
+                            while (ld_volatile_shared(donePrev) < g + needAdj) __nanosleep(20);
+                            __threadfence_block();
+                        }
+                    } else {
+                        if (r - B == M) { outs[p].C = Cl; outs[p].D = Dl; outs[p].I = Il; }
+                        LB16 = 0x7fffffff; RB16 = 0x7fffffff; LBp16 = 0x7fffffff; LBpp16 = 0x7fffffff;
+                        if (l == B - 1) LBst16 = 0x7fffffff;
+                    }
+                }
+                const bool active = (c16 >= LB16);
+                const bool hasI = c16 > LB16, hasC = c16 > LBp16;
+                // existence multipliers of grid point (r-1, c): its C node exists iff c > LB[r-2], its I node iff c > LB[r-1]
+                const int gCu = c16 > LBpp16 ? nGO : 0, gIu = hasC ? nGO : 0;
+                const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(cols) +
+                                                                       (unsigned)__vimin_s32_relu(c16, N16)));
+                int vI, vC, vD;
+                acc >>= 8;                                   // make room for this cell's byte (bits 24..31)
+                // ---- I node (mz_yama.c:114-166) -----------------------------------------------------------
+                {
+                    int x = Cl + dp4a_uu(cw.x, avXI, 0) * gCl;
+                    int y, z;
+                    if (Y16) {
+                        y = dp2a_hi_su((unsigned)gIrow, cw.x, Dl);                    // K*ndB opens (mz_yama.c:131-134)
+                        z = dp2a_lo_su((unsigned)gIl, cw.x, Il);                      // K*b10, if I(r,c-1) exists
+                    } else {
+                        y = Dl + (int)__byte_perm(cw.x, 0, 0x4442) * gIrow;
+                        z = Il + (int)__byte_perm(cw.x, 0, 0x4441) * gIl;
+                    }
+                    vI = pick3<4>(x, y, z, hasI, acc);
+                    vI = dp2a_hi_su(nKGE_lo, cw.x, vI);            // - ndB*K*gap_ext (mz_yama.c:158-161)
+                }
+                vI = hasI ? vI : MININT;
+                // ---- C node (mz_yama.c:169-205) -----------------------------------------------------------
+                {
+                    int x = Cd + dp4a_uu(cw.w, avXC, 0) * gCd;
+                    int y = Y16 ? dp2a_hi_su(avYC, cw.w, Dd) : Dd + dp4a_uu(cw.w, avYC, 0) * nGO;
+                    int z = Id + dp4a_uu(cw.w, avZC, 0) * gId;
+                    vC = pick3<0>(x, y, z, hasC, acc);
+                    vC = dp2a_lo_su(w01, cw.y, vC);
+                    vC = dp2a_hi_su(w23, cw.y, vC);
+                    vC = dp2a_lo_su(w45, cw.z, vC);
+                }
+                vC = hasC ? vC : MININT;
+                // ---- D node (mz_yama.c:208-242) -----------------------------------------------------------
+                {
+                    int x = Cu + dp4a_uu(cw.z, avXD, 0) * gCu;
+                    int y = Y16 ? dp2a_hi_su(avYD, cw.z, Du) : Du + dp4a_uu(cw.z, avYD, 0) * nGO;
+                    int z = Iu + dp4a_uu(cw.z, avZD, 0) * gIu;
+                    vD = pick3<2>(x, y, z, true, acc) - eD;
+                }
+                vD = active ? vD : MININT;
+                if (c16 >= LBst16) sts128(w < G - 1 ? fifoW + fw : ringAddr + ((unsigned)c16 & RMASK), vC, vD, vI, 0u);
+                if (u == 3) tbp[0] = acc;
+                if (u == 7) tbp[1] = acc;
+                Cl = vC; Dl = vD; Il = vI;
+                gCl = hasC ? nGO : 0; gIl = hasI ? gIz : 0; gCd = gCu; gId = gIu;
+                Cd = Cu; Dd = Du; Id = Iu;
+                c16 += 16;
+                fr = (fr + 16u) & FMASK; fw = (fw + 16u) & FMASK;
+            }
+            tbp += 2 * B;
+            // ---- publish: this warp has finished group g ------------------------------------------------------------------
+            __syncwarp();
+            if (lane == 31) { __threadfence_block(); st_volatile_shared(doneAddr + 4u * (unsigned)w, g + 1); }
+        }
+        __syncthreads();
     }
 }
 
@@ -942,7 +1241,7 @@ yb_traceback_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ 
         } else {
             if (((r - 1) >> lg) != blk) { blk = (r - 1) >> lg; offBlk = __ldg(sched + blk); }
             const unsigned lane = (unsigned)(r - 1) & laneMask;
-            const unsigned t = min((unsigned)(c + offBlk) + lane, tmax);              // clamp: stay inside this pair
+            const unsigned t = min((unsigned)(c + offBlk) + lane + (unsigned)pm.skew * (lane >> 5), tmax);   // clamp: stay inside this pair
             const unsigned long long at = tb_byte(lane, t, lg);
             // The bytes were written a whole fill kernel ago: every new 32-B sector is a dependent miss to HBM.  A path
             // is mostly diagonal, so when it enters a sector the one it will need TB_AHEAD sectors later is known:
@@ -1012,7 +1311,7 @@ yb_traceback_long_kernel(const PairMeta *__restrict__ metas, const int *__restri
         } else {
             if (((r - 1) >> lg) != blk) { blk = (r - 1) >> lg; offBlk = __ldg(sched + blk); }
             const unsigned ln = (unsigned)(r - 1) & laneMask;
-            const unsigned t = min((unsigned)(c + offBlk) + ln, tmax);                // clamp: stay inside this pair
+            const unsigned t = min((unsigned)(c + offBlk) + ln + (unsigned)pm.skew * (ln >> 5), tmax);       // clamp: stay inside this pair
             const unsigned long long at = tb_byte(ln, t, lg);
             const long long sec = (long long)(at >> 5);
             if (sec != lastSec) {

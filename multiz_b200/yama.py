@@ -68,6 +68,10 @@ BLOCK_DTYPE = np.dtype([("nrows", "<i4"), ("text_size", "<i4"), ("start", "<i4")
 assert BLOCK_DTYPE.itemsize == C.sizeof(yb_block)
 
 
+# see yb_create: more hardware work queues than the default 8, set before anything in this process initialises CUDA
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def lib_path() -> str:
     return os.environ.get("YAMA_B200_LIB", os.path.join(_HERE, "libyama_b200.so"))
 

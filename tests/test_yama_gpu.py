@@ -342,3 +342,53 @@ def test_cfg3_depth64_r100(yama_ctx, oracle):
             assert (int(r["C"]), int(r["D"]), int(r["I"])) == tuple(int(x) for x in o["cdi"]), (R, i)
             assert np.array_equal(yama_ctx.script_of(r), o["script"]), (R, i)
             assert np.array_equal(yama_ctx.assemble(sb.jobs[i], r), o["al"]), (R, i)
+
+
+def test_delta_coded_bands_match_raw_bands(oracle):
+    """YB_BAND_PACK=1: the host ships a band as one byte per row (the step LB[r]-LB[r-1]) and yb_band_expand restores the
+    caller's int arrays on the device.  Steps of 255 and more travel as exceptions; an invalid band (a negative step, a row
+    that is too narrow) must still be reported per pair in the reference's words; results equal the raw-band run and the
+    oracle.  Rows around the kernel's 128-row chunks and 4-row words."""
+    import os
+    from multiz_b200 import YamaB200
+    rng = np.random.default_rng(2025)
+    probs = []
+    for M in (1, 2, 3, 4, 5, 127, 128, 129, 130, 255, 256, 257, 700):
+        probs.append(random_problem(rng, 2, 1, M, int(rng.integers(1, 90)), band=("smooth", "ragged", "full")[M % 3]))
+    # long jumps: a band that follows a diagonal, leaps 255 / 256 / 1000 columns, and goes on (connected: RB leaps first)
+    for jump in (253, 254, 255, 1000):                   # steps of 254 (a byte), 255, 256, 1001 (exceptions)
+        M, N = 300, 300 + jump
+        diag = np.arange(M + 1)
+        diag = np.where(diag > 150, diag + jump, diag)
+        LB = np.maximum(0, np.where(np.arange(M + 1) > 160, diag - 20, np.minimum(diag, np.arange(M + 1)) - 20)).astype(np.int32)
+        RB = np.minimum(N, np.where(np.arange(M + 1) > 140, np.maximum(diag, np.arange(M + 1) + jump) + 20, diag + 20)).astype(np.int32)
+        LB = np.maximum.accumulate(LB); RB = np.maximum.accumulate(RB)
+        LB[0] = 0; RB[M] = N
+        A, B, _, _ = random_problem(rng, 3, 1, M, N, band="full")
+        probs.append((A, B, LB, RB))
+    good = len(probs)
+    A, B, LB, RB = random_problem(rng, 2, 1, 60, 70, band="smooth")
+    bad1 = (A, B, LB.copy(), RB.copy()); bad1[2][40] = bad1[2][39] + 2; bad1[2][41] = bad1[2][39] + 1   # LB decreases: mz_yama.c:67-68
+    bad2 = (A, B, LB.copy(), RB.copy()); bad2[3][10] = max(0, int(bad2[2][10]) + 2)          # too narrow: mz_yama.c:63-65
+    probs += [bad1, bad2]
+    out = {}
+    for mode in ("0", "1"):
+        os.environ["YB_BAND_PACK"] = mode
+        try:
+            ctx = YamaB200(devices=[0])
+            jobs, keep = ctx.make_jobs(probs)
+            res, st = ctx.run_batch(jobs, check=False)
+            out[mode] = ([tuple(int(r[f]) for f in ("status", "m_new", "C", "D", "I", "cells")) for r in res],
+                         [ctx.script_of(r).tobytes() if r["status"] == 0 else b"" for r in res],
+                         ctx.lib.yb_last_error(ctx.h).decode(), st.h2d_bytes)
+            ctx.close()
+        finally:
+            del os.environ["YB_BAND_PACK"]
+    assert out["0"][:3] == out["1"][:3]
+    assert out["1"][3] < out["0"][3]                     # fewer bytes went over the bus
+    assert [t[0] for t in out["1"][0][good:]] == [-2, -2]
+    for i in range(good):
+        o = oracle.yama(*probs[i], want_tback=False)
+        t = out["1"][0][i]
+        assert t[0] == 0 and t[1] == o["m_new"] and t[2:5] == tuple(int(x) for x in o["cdi"]), i
+        assert out["1"][1][i] == o["script"].tobytes(), i
