@@ -39,6 +39,9 @@ if ROOT not in sys.path:
 from tools.synth import SynthBatch  # noqa: E402
 
 OPS_PER_CELL = 38          # canonical int32 ops per DP cell
+# the fill kernel that takes most of a step, per workload (ncu launch lists under profiles/)
+DOMINANT_KERNEL = {"cfg2": "yb_fill2_kernel<128, KEYED>", "cfg3": "yb_fill2_kernel<128, KEYED / class 1>", "cfg3r100": "yb_fill2_kernel<512>",
+                   "cfg5": "yb_fill_kernel_w<1024, 8, 1> (a CTA per pair, existence multipliers)"}
 INT32_PEAK_FALLBACK_GOPS = 148 * 128 * 1.965   # issue limit: 4 warp-instructions/SM/clk at 1965 MHz
 
 
@@ -102,6 +105,106 @@ def workload_shapes(name: str, seed: int, scale: float):
         Ms = np.full(n, 10000, np.int32)
         return Ks, Ls, Ms, 300, "cfg5: 100-row blocks, M=10000, R=300"
     raise SystemExit(f"unknown workload {name}")
+
+
+def record_real_merge(scale: float, seed: int):
+    """cfg2real: the yama() jobs of the ACTUAL progressive 5-way merge (BASELINE.json configs[1]) -- synthetic MAFs over a
+    10 Mb reference (tools/mafsynth.py), merged step by step by the reference's own multiz host linked against this
+    library (integration/_ref/bin/multiz); every invocation dumps the jobs yama() received (YB_DUMP_JOBS).  Returns one
+    RecordedBatch per merge step.  Needs the GPU (the tool has no CPU path) and the prebuilt integration/_ref binaries."""
+    import shutil
+    import tempfile
+    from tools.mafsynth import make_dataset
+    from tools.synth import RecordedBatch
+    tool = os.path.join(ROOT, "integration", "_ref", "bin", "multiz")
+    if not os.path.exists(tool):
+        raise SystemExit("bench.py: integration/_ref/bin/multiz missing (built by __graft_entry__.build() where /root/reference exists)")
+    tmp = tempfile.mkdtemp(prefix="yb_real_")
+    try:
+        make_dataset(tmp, ref_len=max(100_000, int(10_000_000 * scale)), n_species=4, seed=seed)
+        acc, batches = "ref.sp1.maf", []
+        for i in range(2, 5):
+            dump = os.path.join(tmp, f"jobs{i}.bin")
+            p = subprocess.run([tool, acc, f"ref.sp{i}.maf", "1", f"u1.{i}", f"u2.{i}"], cwd=tmp, stdout=subprocess.PIPE,
+                               stderr=subprocess.PIPE, env=dict(os.environ, YB_DUMP_JOBS=dump))
+            if p.returncode != 0:
+                raise SystemExit(f"bench.py: multiz step {i} failed: {p.stderr.decode()[-300:]}")
+            acc = f"acc{i}.maf"
+            open(os.path.join(tmp, acc), "wb").write(p.stdout)
+            batches.append(RecordedBatch(dump))
+        return batches
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_real_merge(args, ctx, sampler_cls, local):
+    """The cfg2real line: every merge step is its own batch -- kernels with resident inputs, then end to end through
+    yb_run_batch from pinned host buffers -- and the steps run one after the other, as the pipeline runs them."""
+    from multiz_b200 import RESULT_DTYPE
+    batches = record_real_merge(args.scale, 1)
+    per = []
+    launches = 0
+    sampler = sampler_cls(local)
+    t_all0 = time.perf_counter()
+    for k, sb in enumerate(batches):
+        ctx.resident_load(sb.jobs)
+        for _ in range(max(3, args.warmup)):
+            ctx.resident_step()
+        acc = dict(kern=0.0, fill=0.0, prof=0.0, tb=0.0)
+        import torch
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = ctx.resident_step()
+            acc["kern"] += st.kernel_ms; acc["fill"] += st.fill_ms; acc["prof"] += st.profile_ms; acc["tb"] += st.traceback_ms
+            launches += st.kernel_launches
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3 / args.steps
+        res = np.zeros(len(sb.jobs), dtype=RESULT_DTYPE)
+        pinned = ctx.pin_pools(sb.jobs, (sb.A, sb.B, sb.LB, sb.RB))
+        for _ in range(2):
+            ctx.run_batch(pinned, out=res)
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        for _ in range(args.steps):
+            _, st = ctx.run_batch(pinned, out=res)
+            h2d += st.h2d_bytes; d2h += st.d2h_bytes
+        e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+        per.append({"step": f"multiz(acc, ref.sp{k + 2}, v=1)", "pairs": int(sb.n), "cells": int(sb.cells), "K": int(sb.K.max()),
+                    "kernels_ms": wall, "fill_ms": acc["fill"] / args.steps, "profile_ms": acc["prof"] / args.steps,
+                    "traceback_ms": acc["tb"] / args.steps, "kernels_gcups": sb.cells / wall / 1e6,
+                    "e2e_ms": e2e, "e2e_gcups": sb.cells / e2e / 1e6, "h2d_bytes": int(h2d / args.steps), "d2h_bytes": int(d2h / args.steps),
+                    "failed_pairs": int((res["status"] != 0).sum()),
+                    "longest_pair_rows": int(sb.M.max()), "median_pair_rows": int(np.median(sb.M))})
+    clocks = sampler.stop(t_all0, time.perf_counter())
+    cells = sum(p["cells"] for p in per)
+    k_ms = sum(p["kernels_ms"] for p in per); e_ms = sum(p["e2e_ms"] for p in per); f_ms = sum(p["fill_ms"] for p in per)
+    int_peak, int_how = measured_int_peak()
+    peaks, how = measured_peaks()
+    alg = sum(algorithmic_bytes(sb) for sb in batches)
+    return {
+        "metric": "GCUPS", "value": cells / k_ms / 1e6, "unit": "GCUPS", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic MAFs (tools/mafsynth.py), jobs recorded from the real merge",
+        "pairs_per_s": sum(p["pairs"] for p in per) / (k_ms * 1e-3),
+        "config": {"workload": "cfg2real: the yama jobs of the three v=1 merge steps of a progressive 5-way multiz merge over a "
+                               f"{max(100_000, int(10_000_000 * args.scale)) / 1e6:g} Mb reference, recorded from the tool and replayed one merge step at a time",
+                   "pairs_per_gpu": sum(p["pairs"] for p in per), "cells_per_gpu": cells,
+                   "l2": "no flush needed: each merge step writes 0.6 GB of traceback, far above the 126 MB L2",
+                   "parallelism": "1 GPU, the merge steps one after the other"},
+        "merge_steps": per,
+        "kernel_split_ms": {"profile": sum(p["profile_ms"] for p in per), "fill": f_ms, "traceback": sum(p["traceback_ms"] for p in per)},
+        "roofline": {"bound": "int32", "achieved": cells / f_ms / 1e6 * OPS_PER_CELL, "peak": int_peak, "unit": "Gop/s",
+                     "frac": cells / f_ms / 1e6 * OPS_PER_CELL / int_peak, "ops_per_cell": OPS_PER_CELL, "peak_source": int_how,
+                     "kernel": "yb_fill2_kernel<128, KEYED>", "fill_gcups": cells / f_ms / 1e6, "traffic": None,
+                     "hbm": {"achieved": alg / (f_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": alg / (f_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg}},
+        "e2e": {"value": cells / e_ms / 1e6, "unit": "GCUPS", "h2d_bytes_per_step": sum(p["h2d_bytes"] for p in per),
+                "d2h_bytes_per_step": sum(p["d2h_bytes"] for p in per), "ms_per_step": e_ms,
+                "failed_pairs": sum(p["failed_pairs"] for p in per),
+                "inputs": "pinned host memory (yb_host_alloc), int32 bands as yama() receives them; one yb_run_batch per merge step"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
 
 
 def make_batch(name, seed, scale):
@@ -317,6 +420,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    if args.workload == "cfg2real":
+        if world > 1:
+            raise SystemExit("bench.py: cfg2real replays ONE pipeline, step by step: --gpus 1")
+        ctx = YamaB200(devices=[local])
+        emit(run_real_merge(args, ctx, ClockSampler, local))
+        ctx.close()
+        return
     sb, desc = make_batch(args.workload, seed + rank, args.scale)     # weak scaling: same work per GPU
     if world > 1 and "YB_THREADS" not in os.environ:                   # the ranks of one box share its host cores
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
@@ -393,13 +503,13 @@ def main():
             # integer peak; the HBM form is kept beside it as the secondary figure
             "roofline": {"bound": "int32", "achieved": sb.cells / fill_avg_s / 1e9 * OPS_PER_CELL, "peak": int_peak, "unit": "Gop/s",
                          "frac": sb.cells / fill_avg_s / 1e9 * OPS_PER_CELL / int_peak, "ops_per_cell": OPS_PER_CELL,
-                         "peak_source": int_how, "kernel": "yb_fill2_kernel<128, KEYED> (dominant; one launch per kernel bin)",
+                         "peak_source": int_how, "kernel": DOMINANT_KERNEL.get(args.workload, "yb_fill2_kernel<128, KEYED>") + " (dominant; one launch per kernel bin)",
                          "fill_gcups": sb.cells / fill_avg_s / 1e9,
                          "traffic": measured_traffic(args.workload, sb.cells),
                          "hbm": {"achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                                  "algorithmic_bytes_per_launch": alg,
                                  "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback 6650 GB/s"},
-                         "note": "ncu evidence in profiles/r2_fill_summary.md"},
+                         "note": "ncu evidence in profiles/r2_fill_summary.md (cfg2), profiles/r2_fill_cta_summary.md (cfg5)"},
             "e2e": {"value": e2e_val, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d / esteps), "d2h_bytes_per_step": int(d2h / esteps),
                     "pairs_per_s": total_pairs * esteps / (e_ms_max * 1e-3), "steps": esteps, "failed_pairs": bad,
                     "ms_per_step": e_ms_max / esteps, "inputs": "pinned host memory (yb_host_alloc), int32 bands as yama() receives them",

@@ -734,6 +734,26 @@ void defer_finish() {
         jobs[i].LB = reinterpret_cast<const int32_t *>(D.arena.data() + q.offLB);
         jobs[i].RB = reinterpret_cast<const int32_t *>(D.arena.data() + q.offRB);
     }
+    // YB_DUMP_JOBS=<file>: the jobs of this invocation as yama() received them, for the benchmark's replay of a real merge
+    // (bench.py --workload cfg2real): "YBJ1", n, then per job K M L N (int32) and the four byte streams A, B, LB, RB
+    if (const char *path = getenv("YB_DUMP_JOBS")) {
+        if (FILE *df = fopen(path, "wb")) {
+            const uint64_t n64 = n;
+            fwrite("YBJ1", 1, 4, df); fwrite(&n64, 8, 1, df);
+            for (size_t i = 0; i < n; ++i) {
+                const int32_t dims[4] = {jobs[i].K, jobs[i].M, jobs[i].L, jobs[i].N};
+                fwrite(dims, 4, 4, df);
+            }
+            for (int k = 0; k < 4; ++k)
+                for (size_t i = 0; i < n; ++i) {
+                    const yb_job &j = jobs[i];
+                    if (k == 0) fwrite(j.A, 1, (size_t)j.K * j.M, df);
+                    else if (k == 1) fwrite(j.B, 1, (size_t)j.L * j.N, df);
+                    else fwrite(k == 2 ? j.LB : j.RB, 4, (size_t)j.M + 1, df);
+                }
+            fclose(df);
+        }
+    }
     std::vector<yb_result> res(n);
     int rc = YB_OK;
     size_t bad = n;                                           // first job that did not align

@@ -27,6 +27,7 @@ constexpr int PLAN_BULK_BIN0 = 5;
 
 struct PlanParams {
     int ring[PLAN_NBINS], warps[PLAN_NBINS], minRows2;   // bin geometry: ring entries, warps per pair; bin 2 takes pairs of >= minRows2 rows
+    int skew[PLAN_NBINS];                                // fill_body3 bins: extra steps between the warps of a pair (else 0)
     int maxDepth, maxCls, maxAbsS, gapOpen, gapExt;      // limits and score magnitudes that decide the kernel class
     int tbLong;                                          // paths of at least this many moves go to the long-path list
     int slackBulk;                                       // schedule slack of the shuffle kernels (see yb_plan_kernel)
@@ -46,8 +47,8 @@ struct PlanSummary {
 __device__ __forceinline__ int plan_bin_of(const PlanParams &pp, int wmax, int M) {
     if (wmax + 32 <= pp.ring[0]) return 0;
     if (wmax + 32 <= pp.ring[1]) return M >= pp.minRows2 ? 2 : 1;
-    if (wmax + 32 <= pp.ring[3]) return 3;
-    if (wmax + 32 <= pp.ring[4]) return 4;
+    if ((pp.skew[3] ? f3_ring_need(wmax, pp.warps[3]) : wmax + 32) <= pp.ring[3]) return 3;
+    if ((pp.skew[4] ? f3_ring_need(wmax, pp.warps[4]) : wmax + 32) <= pp.ring[4]) return 4;
     return -1;
 }
 
@@ -210,14 +211,17 @@ yb_plan_kernel(PairMeta *metas, int nPairs, unsigned char *blob, PairOut *__rest
                 // shuffle kernels -- it reads the ring at the top of a step, before a row switch in that step, so it must
                 // have switched two steps before its new row's first cell for that cell's diagonal neighbour to be read
                 // at the new row's column (measured: slack 2 saves 1.3 % of the fill and breaks 0.2 % of the pairs).
+                // fill_body3 (skew > 0): the warps of a pair are `skew` extra steps apart, and lane 0 of a block of rows reads
+                // the ring at least 8 steps after the last lane of the block above wrote it (another warp: a finished group)
                 const int B = 32 * pp.warps[bin];
+                const int skew = pp.skew[bin];
                 const int slack = cls ? pp.slackBulk : 3;
                 int *sched = reinterpret_cast<int *>(blob + pm.offSched);
                 const int nblk = (M + B - 1) / B;
                 int off = 0;
                 for (int b = 0; b + 1 < nblk; ++b) {
                     if (lane == 0) sched[b] = off;
-                    int nd = B;
+                    int nd = skew ? f3_min_advance(pp.warps[bin]) : B;
                     const int r0 = B * b + 1, r1 = min(M - B, B * b + B);
                     for (int r = r0 + lane; r <= r1; r += 32) nd = max(nd, __ldg(RB + r + 1) - __ldg(LB + r + B) + slack);
 #pragma unroll
@@ -225,9 +229,10 @@ yb_plan_kernel(PairMeta *metas, int nPairs, unsigned char *blob, PairOut *__rest
                     off += nd;
                 }
                 if (lane == 0) sched[nblk - 1] = off;
-                const int last = off + ((M - 1) % B) + N;              // step of the last cell (RB[M] == N)
+                const int last = off + ((M - 1) % B) + skew * (((M - 1) % B) >> 5) + N;     // step of the last cell (RB[M] == N)
                 const int nSteps = ((last + 2) + 7) & ~7;              // +1 step to publish the final scores, whole 8-step groups
                 pm.nSteps = nSteps;
+                pm.skew = skew;
                 pm.lgLanes = 31 - __clz(B);
                 pm.cls = cls;
                 tbb = (unsigned long long)nSteps * (unsigned)B;        // one byte per lane and step
@@ -239,7 +244,7 @@ yb_plan_kernel(PairMeta *metas, int nPairs, unsigned char *blob, PairOut *__rest
         }
         if (lane == 0) {
             if (o.status == 0) {
-                metas[p].nSteps = pm.nSteps; metas[p].lgLanes = pm.lgLanes; metas[p].cls = pm.cls;
+                metas[p].nSteps = pm.nSteps; metas[p].lgLanes = pm.lgLanes; metas[p].cls = pm.cls; metas[p].skew = pm.skew;
             } else {
                 metas[p].M = 0;                                        // K1..K3 skip the pair
             }

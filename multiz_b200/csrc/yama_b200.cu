@@ -152,9 +152,18 @@ constexpr int NB = 160;                    // launch-order buckets per ring bin
 // pairs run one warp per pair; wide bands on long pairs run one CTA per pair (one ring per pair -> full occupancy).
 // Bins 5..8 are the bulk kernels (fill_body2) for pairs of kernel class 1 (bins 5, 6) and 2 (KEYED; bins 7, 8): same
 // rings as bins 0 and 1.
-struct BinCfg { int ring, G, P, minRows; };
-const BinCfg kBin[NBINS] = {{128, 1, 8, 0}, {512, 1, 8, 0}, {512, 4, 1, 192}, {2048, 8, 1, 0}, {4096, 8, 1, 0},
-                            {128, 1, F2_WARPS, 0}, {512, 1, F2_WARPS, 0}, {128, 1, F2_WARPS, 0}, {512, 1, F2_WARPS, 0}};
+// Bins 3 and 4 take the wide bands, a CTA of 8 warps per pair: band rows of up to 992 cells on a 1 024-entry ring (40 KB of
+// shared memory per CTA: 4 CTAs per SM -- the 2 048-entry ring of round 1 allowed 3), up to 4 064 on a 4 096-entry ring.
+// -DYB_FILL3 (make ../libyama_b200_fill3.so) puts the experimental fill_body3 there instead: 4 decoupled warps per pair, rings
+// that also cover the distance between the lane that writes the ring and the lane that reads it (f3_ring_need).
+struct BinCfg { int ring, G, P, minRows, skew; };
+#ifdef YB_FILL3
+const BinCfg kBin[NBINS] = {{128, 1, 8, 0, 0}, {512, 1, 8, 0, 0}, {512, 4, 1, 192, 0}, {1024, 4, 1, 0, F3_SKEW}, {8192, 4, 1, 0, F3_SKEW},
+#else
+const BinCfg kBin[NBINS] = {{128, 1, 8, 0, 0}, {512, 1, 8, 0, 0}, {512, 4, 1, 192, 0}, {1024, 8, 1, 0, 0}, {4096, 8, 1, 0, 0},
+#endif
+                            {128, 1, F2_WARPS, 0, 0}, {512, 1, F2_WARPS, 0, 0}, {128, 1, F2_WARPS, 0, 0}, {512, 1, F2_WARPS, 0, 0}};
+inline int ring_need(int bin, int wmax) { return kBin[bin].skew ? f3_ring_need(wmax, kBin[bin].G) : wmax + 32; }
 constexpr int BULK_BIN0 = 5;
 constexpr int NSLOTS = 8;                 // waves in flight per device (each on its own stream, queued in one go)
 
@@ -339,11 +348,16 @@ void parallel_for(int threads, int64_t n, int64_t chunk, F &&fn) {
 }
 
 int bin_of(int wmax, int M) {
-    if (wmax + 32 <= kBin[0].ring) return 0;
-    if (wmax + 32 <= kBin[1].ring) return M >= kBin[2].minRows ? 2 : 1;
-    if (wmax + 32 <= kBin[3].ring) return 3;
-    if (wmax + 32 <= kBin[4].ring) return 4;
+    if (ring_need(0, wmax) <= kBin[0].ring) return 0;
+    if (ring_need(1, wmax) <= kBin[1].ring) return M >= kBin[2].minRows ? 2 : 1;
+    if (ring_need(3, wmax) <= kBin[3].ring) return 3;
+    if (ring_need(4, wmax) <= kBin[4].ring) return 4;
     return -1;
+}
+int max_band_row() {                      // widest band row any kernel bin takes
+    int w = kBin[4].ring;
+    while (ring_need(4, w) > kBin[4].ring) --w;
+    return w;
 }
 int lanes_of(int wmax, int M) {          // wavefront width of the pair's bin (0: no kernel takes it)
     const int b = bin_of(wmax, M);
@@ -351,8 +365,10 @@ int lanes_of(int wmax, int M) {          // wavefront width of the pair's bin (0
 }
 
 size_t fill_smem(int bin) {
-    // rings (RING*16-aligned, hence the slack) + 32 B of mailbox per lane + the queue slot
     const BinCfg &c = kBin[bin];
+    // fill_body3: ring + one FIFO per warp + a 64-B row slot per lane + progress words + the queue slot
+    if (c.skew) return (size_t)c.ring * 16 + (size_t)c.G * F3_FIFO * 16 + (size_t)c.G * 32 * 64 + (size_t)c.G * 4 + 32;
+    // rings (RING*16-aligned, hence the slack) + 32 B of mailbox per lane + the queue slot
     return (size_t)c.P * ((size_t)c.ring * 16 + (size_t)c.G * 1024) + (size_t)c.ring * 16 + 16;
 }
 
@@ -360,13 +376,25 @@ size_t fill_smem(int bin) {
 
 // ---- kernels with a runtime warps-per-CTA: thin wrappers around the template ---------------------
 namespace yb {
+#ifndef YB_F1_MINCTAS
+#define YB_F1_MINCTAS 5
+#endif
 template <int RING, int G, int P, bool Y16, bool GATED = true>
-__global__ void __launch_bounds__(G * P * 32)
+__global__ void __launch_bounds__(G * P * 32, (RING == 1024 && G == 8) ? YB_F1_MINCTAS : 1)
 yb_fill_kernel_w(const PairMeta *__restrict__ metas, const int *__restrict__ order, const int *__restrict__ binRange,
                  int *__restrict__ queue, const RowRec *__restrict__ rowPool,
                  const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
                  const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int gapOpen, int gapExt) {
     fill_body<RING, G, P, Y16, GATED>(metas, order, binRange, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
+}
+// wide bands (fill_body3): a CTA of G decoupled warps per pair
+template <int RING, int G, bool Y16>
+__global__ void __launch_bounds__(G * 32, (RING <= 1024 ? 7 : 1))
+yb_fill3_kernel(const PairMeta *__restrict__ metas, const int *__restrict__ order, const int *__restrict__ binRange,
+                int *__restrict__ queue, const RowRec *__restrict__ rowPool,
+                const ColRec *__restrict__ colPool, unsigned char *__restrict__ tbPool,
+                const unsigned long long *__restrict__ tbBase, PairOut *__restrict__ outs, int gapOpen, int gapExt) {
+    fill_body3<RING, G, Y16>(metas, order, binRange, queue, rowPool, colPool, tbPool, tbBase, outs, gapOpen, gapExt);
 }
 // bulk form (fill_body2): one warp per pair, pairs of kernel class 1 / 2
 #ifndef YB_F2_MINCTAS
@@ -394,8 +422,13 @@ FillFn fill_fn(int bin, bool y16, bool ungated = false) {
         case 0: return y16 ? yb_fill_kernel_w<128, 1, 8, true> : yb_fill_kernel_w<128, 1, 8, false>;
         case 1: return y16 ? yb_fill_kernel_w<512, 1, 8, true> : yb_fill_kernel_w<512, 1, 8, false>;
         case 2: return y16 ? yb_fill_kernel_w<512, 4, 1, true> : yb_fill_kernel_w<512, 4, 1, false>;
-        case 3: return y16 ? yb_fill_kernel_w<2048, 8, 1, true> : yb_fill_kernel_w<2048, 8, 1, false>;
+#ifdef YB_FILL3
+        case 3: return y16 ? yb_fill3_kernel<1024, 4, true> : yb_fill3_kernel<1024, 4, false>;
+        default: return y16 ? yb_fill3_kernel<8192, 4, true> : yb_fill3_kernel<8192, 4, false>;
+#else
+        case 3: return y16 ? yb_fill_kernel_w<1024, 8, 1, true> : yb_fill_kernel_w<1024, 8, 1, false>;
         default: return y16 ? yb_fill_kernel_w<4096, 8, 1, true> : yb_fill_kernel_w<4096, 8, 1, false>;
+#endif
     }
 }
 
@@ -749,7 +782,7 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
     int *counters = reinterpret_cast<int *>(dIn + s.countersOff);
     CUDA_TRY(d, cudaMemsetAsync(counters, 0, (size_t)(2 * NBINS * NB + 16) * 4, q));
     PlanParams pp;
-    for (int b = 0; b < NBINS; ++b) { pp.ring[b] = kBin[b].ring; pp.warps[b] = kBin[b].G; }
+    for (int b = 0; b < NBINS; ++b) { pp.ring[b] = kBin[b].ring; pp.warps[b] = kBin[b].G; pp.skew[b] = kBin[b].skew; }
     pp.minRows2 = kBin[2].minRows;
     pp.maxDepth = ctx->maxDepth; pp.maxCls = ctx->maxCls; pp.maxAbsS = ctx->maxAbsS;
     pp.gapOpen = ctx->sc.gap_open; pp.gapExt = ctx->sc.gap_ext; pp.tbLong = ctx->tbLong;
@@ -762,7 +795,7 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
         unsigned can = 1u;
         if (widest > kBin[0].ring) can |= (1u << 1) | (1u << 2);
         if (widest > kBin[1].ring) can |= 1u << 3;
-        if (widest > kBin[3].ring) can |= 1u << 4;
+        if (ring_need(3, maxN + 1) > kBin[3].ring) can |= 1u << 4;
         if (d.maxCls >= 1) can |= (1u << BULK_BIN0) | ((can & 2u) ? 1u << (BULK_BIN0 + 1) : 0u);
         if (d.maxCls >= 2 && minK <= d.keyedMaxK) can |= (1u << (BULK_BIN0 + 2)) | ((can & 2u) ? 1u << (BULK_BIN0 + 3) : 0u);
         unsigned recent = d.recentBins[0] | d.recentBins[1] | d.recentBins[2] | d.recentBins[3];
@@ -1210,7 +1243,7 @@ void describe_failure(yb_ctx *ctx, const yb_job &j, int64_t index, int status) {
     if (j.K > ctx->maxDepth || j.L > 255)
         set_err(ctx, "job %lld: profile depth K=%d L=%d exceeds the kernel limit (%d/255 rows)", (long long)index, j.K, j.L, ctx->maxDepth);
     else
-        set_err(ctx, "job %lld: band row of %d cells exceeds the kernel limit (%d)", (long long)index, wmax, kBin[4].ring - 32);
+        set_err(ctx, "job %lld: band row of %d cells exceeds the kernel limit (%d)", (long long)index, wmax, max_band_row());
 }
 
 template <class F>

@@ -951,12 +951,17 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
 //  * a lane's next row record is copied global -> shared (cp.async) while it walks its current row.
 // =================================================================================================
 constexpr int F3_SKEW = 7;          // steps between lane 31 of a warp and lane 0 of the next, beyond the usual one
-constexpr int F3_FIFO = 64;         // entries of an inter-warp FIFO
-constexpr int F3_BP = 5;            // groups a warp may run ahead of the warp that reads it (FIFO: 64 steps = 8 groups, minus the
-                                    // group being written, the group being read and the skew)
+constexpr int F3_FIFO = 128;        // entries of an inter-warp FIFO: 16 groups of eight steps
+constexpr int F3_BP = F3_FIFO / 8 - 3;   // groups a warp may run ahead of the warp that reads it (the FIFO's groups minus the group
+                                    // being written, the group being read and the skew)
+#ifndef YB_F3_SLEEP
+#define YB_F3_SLEEP 64
+#endif
 // ring entries a band row of `wmax` cells needs: the row, the distance in columns between the lane that writes the ring and
 // the lane that reads it (B - 1 lanes + the skews), the drift allowed between their warps, and a margin
 __host__ __device__ constexpr int f3_ring_need(int wmax, int G) { return wmax + 32 * G + F3_SKEW * (G - 1) + 8 * (F3_BP + 1) + 16; }
+// steps a block of rows starts after the block above, at least: lane 0 reads the ring a finished group (8 steps) after it was written
+__host__ __device__ constexpr int f3_min_advance(int G) { return 32 * G + F3_SKEW * (G - 1) + 7; }
 
 __device__ __forceinline__ int ld_volatile_shared(unsigned addr) {
     int v;
@@ -1087,8 +1092,8 @@ fill_body3(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
             // ---- wait: the warp we read from has finished the groups our reads come from; the warp that reads us is near ----
             if (lane == 0) {
                 const int needPrev = (w == 0) ? g + needAdj : g;
-                while (ld_volatile_shared(donePrev) < needPrev) __nanosleep(20);
-                while (ld_volatile_shared(doneNext) < g - F3_BP) __nanosleep(20);
+                while (ld_volatile_shared(donePrev) < needPrev) __nanosleep(YB_F3_SLEEP);
+                while (ld_volatile_shared(doneNext) < g - F3_BP) __nanosleep(YB_F3_SLEEP);
                 __threadfence_block();
             }
             __syncwarp();
@@ -1122,7 +1127,7 @@ fill_body3(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
                             // g + floor((7 - gap) / 8): that many it must have completed.
                             const int gap = ((off16 - offOld) >> 4) - (B - 1) - F3_SKEW * (G - 1);
                             needAdj = 1 + ((7 - gap) >> 3);
-                            while (ld_volatile_shared(donePrev) < g + needAdj) __nanosleep(20);
+                            while (ld_volatile_shared(donePrev) < g + needAdj) __nanosleep(YB_F3_SLEEP);
                             __threadfence_block();
                         }
                     } else {

@@ -118,3 +118,40 @@ def test_tba_eight_species_tree(tmp_path):
     finally:
         stop_server(srv)
     assert got2 == want
+
+
+def test_kernel_limits_stop_the_tool_like_a_failing_yama(tmp_path):
+    """Limits the reference does not have: more than 255 rows in a profile, a band row wider than the
+    widest ring.  There is no CPU path to fall back to, so the tool must stop the way the reference stops when yama()
+    fails -- a message on stderr, a non-zero exit code, everything BEFORE the failing pair written, nothing of it or
+    after it -- instead of writing a wrong or partial merge silently."""
+    import random
+    _need(GPU_MULTIZ); _need(REF_MULTIZ)
+    rng = random.Random(3)
+    n1, n2 = 400, 300
+    seq = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    ref = seq(n1 + 50 + n2)
+    def block(start, n, rows):
+        t = ref[start:start + n]
+        lines = ["a score=0.0", "s ref.chr1 %d %d + %d %s" % (start, n, len(ref), t)]
+        for k in range(rows):
+            lines.append("s sp%d.chr1 %d %d + %d %s" % (k, 10, n, 5000, t))
+        return "\n".join(lines) + "\n\n"
+    head = "##maf version=1 scoring=multiz\n"
+    f1 = head + block(0, n1, 1) + block(n1 + 50, n2, 299)          # second block: K = 300 rows
+    f2 = head + "a score=0.0\ns ref.chr1 0 %d + %d %s\ns other.chr1 0 %d + %d %s\n\n" % (len(ref), len(ref), ref, len(ref), len(ref), ref)
+    outs = {}
+    for name, tool in (("ref", REF_MULTIZ), ("gpu", GPU_MULTIZ)):
+        d = tmp_path / name
+        d.mkdir()
+        (d / "a.maf").write_text(f1); (d / "b.maf").write_text(f2)
+        outs[name] = run_tool(tool, ["a.maf", "b.maf", "1", "o1", "o2"], str(d))
+    rc_r, out_r, _ = outs["ref"]
+    rc_g, out_g, err_g = outs["gpu"]
+    assert rc_r == 0                                              # the reference has no such limit
+    assert rc_g != 0 and b"exceeds the kernel limit" in err_g, err_g[-300:]
+    import re
+    blocks_r = re.findall(rb"^a .*?\n\n", out_r, flags=re.S | re.M)
+    blocks_g = re.findall(rb"^a .*?\n\n", out_g, flags=re.S | re.M)
+    assert len(blocks_r) >= 2 and blocks_g == blocks_r[:len(blocks_g)] and len(blocks_g) >= 1      # a true prefix
+    assert not any(b.count(b"\ns ") > 10 for b in blocks_g)      # nothing of the 300-row merge

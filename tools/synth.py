@@ -186,3 +186,42 @@ def random_problem(rng, K, L, M, N, band="smooth", alphabet="mixed", dash=0.15):
         B[i, :] = A[i, rng.integers(0, K, size=L)]
     LB, RB = random_band(rng, M, N, band)
     return A, B, LB, RB
+
+
+class RecordedBatch:
+    """The yama() jobs of one real multiz invocation, as the drop-in dumped them (YB_DUMP_JOBS, integration/yama_dropin.cpp):
+    same attributes as SynthBatch (jobs, A, B, LB, RB, n, cells, K, M, L, N, problem())."""
+
+    def __init__(self, path):
+        raw = np.fromfile(path, dtype=np.uint8)
+        assert raw[:4].tobytes() == b"YBJ1", path
+        n = int(raw[4:12].view(np.uint64)[0])
+        dims = raw[12:12 + 16 * n].view(np.int32).reshape(n, 4)
+        self.n = n
+        self.K, self.M, self.L, self.N = (np.ascontiguousarray(dims[:, k]) for k in range(4))
+        K, M, L, N = (x.astype(np.int64) for x in (self.K, self.M, self.L, self.N))
+        szA, szB, szBand = K * M, L * N, M + 1
+        at = 12 + 16 * n
+        self.A = raw[at:at + int(szA.sum())].copy(); at += int(szA.sum())
+        self.B = raw[at:at + int(szB.sum())].copy(); at += int(szB.sum())
+        nb = int(szBand.sum())
+        self.LB = raw[at:at + 4 * nb].copy().view(np.int32); at += 4 * nb
+        self.RB = raw[at:at + 4 * nb].copy().view(np.int32); at += 4 * nb
+        assert at == len(raw), (at, len(raw))
+        self.offA = np.concatenate([[0], np.cumsum(szA)[:-1]]).astype(np.int64)
+        self.offB = np.concatenate([[0], np.cumsum(szB)[:-1]]).astype(np.int64)
+        self.offBand = np.concatenate([[0], np.cumsum(szBand)[:-1]]).astype(np.int64)
+        self.cells = int((self.RB.astype(np.int64) - self.LB + 1).sum())
+        jobs = np.zeros(n, dtype=JOB_DTYPE)
+        jobs["K"], jobs["M"], jobs["L"], jobs["N"] = self.K, self.M, self.L, self.N
+        jobs["A"] = np.uint64(self.A.ctypes.data) + self.offA.astype(np.uint64)
+        jobs["B"] = np.uint64(self.B.ctypes.data) + self.offB.astype(np.uint64)
+        jobs["LB"] = np.uint64(self.LB.ctypes.data) + (self.offBand * 4).astype(np.uint64)
+        jobs["RB"] = np.uint64(self.RB.ctypes.data) + (self.offBand * 4).astype(np.uint64)
+        self.jobs = jobs
+
+    problem = SynthBatch.problem
+    cells_per_pair = SynthBatch.cells_per_pair
+
+    def close(self):
+        pass
