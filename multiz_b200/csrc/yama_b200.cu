@@ -377,7 +377,7 @@ size_t fill_smem(int bin) {
 // ---- kernels with a runtime warps-per-CTA: thin wrappers around the template ---------------------
 namespace yb {
 #ifndef YB_F1_MINCTAS
-#define YB_F1_MINCTAS 5
+#define YB_F1_MINCTAS 4
 #endif
 template <int RING, int G, int P, bool Y16, bool GATED = true>
 __global__ void __launch_bounds__(G * P * 32, (RING == 1024 && G == 8) ? YB_F1_MINCTAS : 1)
