@@ -450,6 +450,11 @@ fill_body(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase,
             for (int u = 0; u < 4; ++u) {
                 // ---- grid point (r-1, c): read before anybody may overwrite it ------------------------
                 const uint4 up = lds128(and_xor((unsigned)(G > 1 ? min(c16, rdMax16) : c16), rdMask, rdBase));
+#ifdef YB_FORCE_WARPSYNC
+                // sanitize build: the stores of this step (a finished row fills slots whose previous content its reader took just
+                // above) come after every lane's read in program order; a barrier says so to the tool
+                if (G == 1) group_sync();
+#endif
                 if (c16 > RB16) {
                     // ---- this lane finished its row -----------------------------------------------------
                     // (a) the row below keeps reading us up to its own right bound: stale dp[] entries (mz_yama.c:93-94).
@@ -821,6 +826,9 @@ fill_body2(const PairMeta *__restrict__ metas, const int *__restrict__ orderBase
                     const uint4 up = lds128(and_xor((unsigned)c16, RMASK, ringAddr));
                     Cu = (int)up.x; Du = (int)up.y; Iu = (int)up.z;
                 }
+#ifdef YB_FORCE_WARPSYNC
+                asm volatile("bar.sync %0, 32;" ::"r"(grp + 1) : "memory");     // (sanitize build: this step's ring stores follow the read)
+#endif
                 if ((F2_SW == 1 || (u % F2_SW) == 0) && c16 > RB16) {
                     // ---- this lane finished its row: move one wavefront width down -----------------------------------
                     // the row below keeps reading us up to its own right bound and must find never-written dp[] entries
