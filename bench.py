@@ -207,6 +207,30 @@ def run_real_merge(args, ctx, sampler_cls, local):
     }
 
 
+def bind_to_gpu_numa_node(local: int, threads: int):
+    """One rank per GPU: keep the rank -- its pinned input buffers are placed where the allocating thread runs, and the
+    library's helper threads inherit the mask -- on the NUMA node its GPU hangs off, so that host->device copies do not cross
+    the socket interconnect.  Only if that node offers at least `threads` of the CPUs this process may use.  Returns the node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if len(allowed) < max(1, threads):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def make_batch(name, seed, scale):
     Ks, Ls, Ms, R, desc = workload_shapes(name, seed, scale)
     perm = np.random.default_rng(seed + 1).permutation(len(Ks))   # reference order mixes sizes
@@ -428,9 +452,12 @@ def main():
         ctx.close()
         return
     sb, desc = make_batch(args.workload, seed + rank, args.scale)     # weak scaling: same work per GPU
+    numa_node = None
     if world > 1 and "YB_THREADS" not in os.environ:                   # the ranks of one box share its host cores
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
         os.environ["YB_THREADS"] = str(max(2, (os.cpu_count() or 1) // max(1, local_world)))
+    if world > 1 and os.environ.get("YB_NUMA", "1") != "0":
+        numa_node = bind_to_gpu_numa_node(local, int(os.environ.get("YB_THREADS", "1")))
     ctx = YamaB200(devices=[local])
     ctx.resident_load(sb.jobs)
 
@@ -496,7 +523,8 @@ def main():
             "pairs_per_s": total_pairs * args.steps / (wall_ms_max * 1e-3),
             "config": {"workload": desc, "pairs_per_gpu": int(sb.n), "cells_per_gpu": int(sb.cells),
                        "l2": "no flush needed: each step writes %.1f GB of traceback + row/column records, far above the 126 MB L2" % (sb.cells / 1e9),
-                       "parallelism": f"{world} GPU(s), independent pair shards, no collective"},
+                       "parallelism": f"{world} GPU(s), independent pair shards, no collective",
+                       "numa_node_of_rank0": numa_node},
             "device_event_ms_per_step": kern_ms_max / args.steps,
             "kernel_split_ms": {"profile": prof_ms / args.steps, "fill": fill_ms / args.steps, "traceback": tb_ms / args.steps},
             # the fill kernel is bound by integer instruction issue, not by HBM: the roofline is the measured

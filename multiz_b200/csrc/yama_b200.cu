@@ -17,6 +17,9 @@
 #include "score_kernels.cuh"
 
 #include <emmintrin.h>
+#include <pthread.h>
+#include <sched.h>
+#include <cctype>
 
 #include <algorithm>
 #include <array>
@@ -77,8 +80,12 @@ struct PinBuf {
 // the helpers plus the calling thread, and returns when all of [0,n) is done.
 class Pool {
   public:
-    explicit Pool(int helpers) {
+    // cpus: the CPUs of the device's NUMA node (may be empty): the helpers stay next to the device's PCIe root, so that the pinned
+    // staging they fill and the copies out of it do not cross the socket interconnect
+    explicit Pool(int helpers, const cpu_set_t *cpus = nullptr) {
         for (int t = 0; t < helpers; ++t) th_.emplace_back([this] { loop(); });
+        if (cpus && CPU_COUNT(cpus) > 0)
+            for (auto &t : th_) pthread_setaffinity_np(t.native_handle(), sizeof(cpu_set_t), cpus);
     }
     ~Pool() {
         { std::lock_guard<std::mutex> g(mu_); stop_ = true; ++gen_; genFast_.store(gen_, std::memory_order_release); }
@@ -230,6 +237,8 @@ struct Device {
     int maxCls = 2, keyedMaxK = 0;         // kernel classes on offer; deepest first profile the KEYED class takes (yb_set_scores)
     int fillBlocks[NBINS] = {};
     int helpers = 1;
+    cpu_set_t cpus;                        // CPUs of the device's NUMA node that this process may use (empty: unknown / YB_NUMA=0)
+    int numaNode = -1;
     std::unique_ptr<Pool> pool;
     // accumulated stats of the current call
     double kernel_ms = 0, fill_ms = 0, profile_ms = 0, tb_ms = 0, h2d_ms = 0, d2h_ms = 0, pack_ms = 0, unpack_ms = 0;
@@ -444,6 +453,41 @@ size_t fill2_smem(int bin) {
     // rings (RING*16-aligned, hence the slack) + a 64-B row slot per lane + a stash word per warp
     const size_t ring = (size_t)kBin[bin].ring * 16;
     return F2_WARPS * (ring + 32 * 64 + 16) + ring + 16;
+}
+
+// The CPUs of the NUMA node the device hangs off (sysfs), intersected with what the process may use.  YB_NUMA=0 turns it off.
+void device_cpus(Device &d) {
+    CPU_ZERO(&d.cpus);
+    d.numaNode = -1;
+    if (const char *e = getenv("YB_NUMA")) if (atoi(e) == 0) return;
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, d.id) != cudaSuccess) return;
+    for (char *c = bdf; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return;
+    cpu_set_t mine, want;
+    CPU_ZERO(&want);
+    int a, b;
+    char sep;
+    while (fscanf(f, "%d", &a) == 1) {                     // "0-15,32-47"
+        b = a;
+        if (fscanf(f, "%c", &sep) == 1 && sep == '-') { if (fscanf(f, "%d", &b) != 1) b = a; if (fscanf(f, "%c", &sep) != 1) sep = 0; }
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET(c, &want);
+        if (sep != ',') break;
+    }
+    fclose(f);
+    if (sched_getaffinity(0, sizeof mine, &mine) != 0) return;
+    CPU_AND(&d.cpus, &mine, &want);
+    // (never trade threads for placement: the node must offer a CPU per thread of this device)
+    if (CPU_COUNT(&d.cpus) < d.helpers) { CPU_ZERO(&d.cpus); return; }
+    d.numaNode = node;
 }
 
 int device_init(Device &d) {
@@ -1253,7 +1297,12 @@ int for_each_device(yb_ctx *ctx, F &&fn) {
     if (ndev == 1) rcs[0] = fn(0);
     else {
         std::vector<std::thread> th;
-        for (int d = 0; d < ndev; ++d) th.emplace_back([&, d] { rcs[(size_t)d] = fn(d); });
+        for (int d = 0; d < ndev; ++d)
+            th.emplace_back([&, d] {
+                const Device &dv = ctx->devs[(size_t)d];          // (a thread of ours: it may sit next to its device)
+                if (CPU_COUNT(&dv.cpus) > 0) pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), &dv.cpus);
+                rcs[(size_t)d] = fn(d);
+            });
         for (auto &t : th) t.join();
     }
     for (int d = 0; d < ndev; ++d)
@@ -1325,7 +1374,8 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_WAVE_PAIRS")) ctx->wavePairs = std::max<int64_t>(1, atoll(e));
     for (auto &d : ctx->devs) {
         d.helpers = std::max(1, ctx->nThreads / (int)ctx->devs.size());
-        d.pool.reset(new Pool(d.helpers - 1));
+        device_cpus(d);
+        d.pool.reset(new Pool(d.helpers - 1, &d.cpus));
     }
     *out = ctx;
     return YB_OK;
