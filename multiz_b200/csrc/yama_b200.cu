@@ -274,6 +274,7 @@ struct yb_ctx {
     size_t waveMinBytes = (size_t)16 << 20; // first waves of a batch (the device idles while the first wave is packed)
     size_t waveTailBytes = (size_t)16 << 20; // last waves of a batch (a short last wave shortens the traceback + unpack tail)
     size_t batchBlobBytes = 0;              // input bytes of the current batch (dimension-only estimate)
+    bool waveEnv = false;                   // wave sizes were given in the environment: no adaptation to the batch
     size_t waveTbBytes = (size_t)12 << 30;  // traceback bytes per wave (device memory per slot)
     int64_t wavePairs = 1 << 20;
     int tbLong = TB_LONG;                   // paths of at least this many moves: warp-per-path traceback (YB_TB_LONG)
@@ -1349,6 +1350,7 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (hw < 1) hw = 1;
     ctx->nThreads = std::min(hw, 32);
     if (const char *e = getenv("YB_THREADS")) ctx->nThreads = std::max(1, atoi(e));
+    ctx->waveEnv = getenv("YB_WAVE_MB") || getenv("YB_WAVE_MIN_MB") || getenv("YB_WAVE_TAIL_MB");
     if (const char *e = getenv("YB_WAVE_MB")) ctx->waveInBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_MIN_MB")) ctx->waveMinBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
     if (const char *e = getenv("YB_WAVE_TAIL_MB")) ctx->waveTailBytes = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)) << 20;
@@ -1533,6 +1535,17 @@ int yb_run_batch(yb_ctx *ctx, int64_t n, const yb_job *jobs, yb_result *results,
     disp.maxPairs = ctx->wavePairs;
     disp.minBytes = std::min(ctx->waveInBytes, ctx->waveMinBytes);
     disp.tailBytes = std::min(ctx->waveInBytes, ctx->waveTailBytes);
+    // A small batch (one merge step of a 10 Mb pipeline is 50-80 MB) is one trip through the pipeline, not a stream of waves:
+    // cut it finer, so that the copy of one piece overlaps the kernels of the one before (measured on the real merge's
+    // batches, profiles/r2_ab_waves.txt: 5.5 -> 4.6 ms per call with 4 / 16 MB waves; 8 MB waves lose it again to launches)
+    if (!ctx->waveEnv) {
+        const size_t perDev = ctx->batchBlobBytes / std::max<size_t>(1, ctx->devs.size());
+        const size_t steady = std::min(ctx->waveInBytes, std::max<size_t>((size_t)16 << 20, perDev / 8));
+        if (steady < disp.maxBytes) {
+            disp.maxBytes = steady;
+            disp.minBytes = disp.tailBytes = std::min(disp.minBytes, std::max<size_t>((size_t)4 << 20, steady / 4));
+        }
+    }
     disp.ndev = (int)ctx->devs.size();
     disp.remaining = ctx->batchBlobBytes;
     int rc = for_each_device(ctx, [&](int d) { return device_run(ctx, ctx->devs[(size_t)d], disp, results); });
