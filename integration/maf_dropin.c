@@ -44,6 +44,8 @@ static int use_ref(void) {
 struct reader {
     struct reader *next;
     struct mafFile *mf;
+    FILE *fp;               /* the stream the buffered bytes came from: a mafFile freed before its end and another one
+                               allocated at the same address must not inherit them */
     char *buf;              /* cap + 1 bytes: a line is NUL-terminated in place */
     size_t cap, lo, hi;     /* unread bytes: buf[lo, hi) */
     char saved;             /* the byte the last line's terminator replaced */
@@ -54,9 +56,13 @@ static struct reader *readers = NULL;
 static struct reader *reader_of(struct mafFile *mf) {
     struct reader *r;
     for (r = readers; r != NULL; r = r->next)
-        if (r->mf == mf) return r;
+        if (r->mf == mf) {
+            if (r->fp == mf->fp) return r;
+            r->fp = mf->fp; r->lo = r->hi = 0; r->have_saved = 0; r->eof = 0;      /* a new file behind an old address */
+            return r;
+        }
     r = ckalloc(sizeof *r);
-    r->mf = mf; r->cap = (size_t)1 << 20; r->buf = ckalloc(r->cap + 1);
+    r->mf = mf; r->fp = mf->fp; r->cap = (size_t)1 << 20; r->buf = ckalloc(r->cap + 1);
     r->lo = r->hi = 0; r->have_saved = 0; r->eof = 0; r->saved = 0;
     r->next = readers; readers = r;
     return r;
