@@ -236,6 +236,9 @@ struct Device {
     int fillSplit = 2;                     // a wave's fill takes 1/fillSplit of the machine, so that consecutive waves' fills overlap
     int maxCls = 2, keyedMaxK = 0;         // kernel classes on offer; deepest first profile the KEYED class takes (yb_set_scores)
     int fillBlocks[NBINS] = {};
+    unsigned fillReady[NBINS] = {};        // fill kernels of the bin whose attributes are set (bit 0: Y16 = false / bulk, bit 1: Y16 = true)
+    int prioLo = 0;
+    double tContext = 0, tStreams = 0;     // start-up times (YB_PROFILE)
     int helpers = 1;
     cpu_set_t cpus;                        // CPUs of the device's NUMA node that this process may use (empty: unknown / YB_NUMA=0)
     int numaNode = -1;
@@ -492,44 +495,43 @@ void device_cpus(Device &d) {
 }
 
 int device_init(Device &d) {
+    const double t0 = now_ms();
     CUDA_TRY(d, cudaSetDevice(d.id));
+    CUDA_TRY(d, cudaFree(nullptr));                          // (the context is created here)
     cudaDeviceProp prop;
     CUDA_TRY(d, cudaGetDeviceProperties(&prop, d.id));
     d.sms = prop.multiProcessorCount;
+    d.tContext = now_ms() - t0;
     // A wave's copies, K0, K1, K3 run on its main stream, the fill kernels on the bin streams.  The fill kernels are persistent
     // and fill the machine; the short kernels of the NEXT waves must get the CTA slots that free up first, or every wave's
     // K0 / K1 / K3 waits behind a whole fill: the main streams get the higher priority (YB_PRIO=0: all equal).
     int prioLo = 0, prioHi = 0;
     CUDA_TRY(d, cudaDeviceGetStreamPriorityRange(&prioLo, &prioHi));
     if (const char *e = getenv("YB_PRIO")) if (atoi(e) == 0) prioHi = prioLo;
+    d.prioLo = prioLo;
     for (auto &s : d.slots) {
         CUDA_TRY(d, cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prioHi));
         for (auto &e : s.ev) CUDA_TRY(d, cudaEventCreate(&e));
-        for (int b = 0; b < NBINS; ++b) {
-            CUDA_TRY(d, cudaStreamCreateWithPriority(&s.binStream[b], cudaStreamNonBlocking, prioLo));
-            CUDA_TRY(d, cudaEventCreateWithFlags(&s.binDone[b], cudaEventDisableTiming));
-        }
     }
-    for (int b = 0; b < BULK_BIN0; ++b) {
-        FillFn fn = fill_fn(b, true);
-        size_t sm = fill_smem(b);
-        CUDA_TRY(d, cudaFuncSetAttribute(fill_fn(b, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        if (fill_fn(b, true, true) != fn)
-            CUDA_TRY(d, cudaFuncSetAttribute(fill_fn(b, true, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        int occ = 0;
-        CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBin[b].G * kBin[b].P * 32, sm));
-        if (occ < 1) occ = 1;
-        d.fillBlocks[b] = occ * d.sms;
-    }
-    for (int b = BULK_BIN0; b < NBINS; ++b) {
-        FillFn fn = fill_fn2(b);
-        const size_t sm = fill2_smem(b);
-        CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        int occ = 0;
-        CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, F2_WARPS * 32, sm));
-        d.fillBlocks[b] = std::max(occ, 1) * d.sms;
-    }
+    d.tStreams = now_ms() - t0 - d.tContext;
+    // (the bins' streams, and the fill kernels' attributes -- which make the driver load the kernel -- are set up at a bin's
+    //  first launch: a tool invocation uses two or three of the twenty fill kernels, and its start-up is its wall clock)
+    return YB_OK;
+}
+
+// First launch of a fill kernel on this device: dynamic shared memory limit, grid size from the occupancy.
+int ensure_fill(Device &d, int b, bool y16) {
+    const bool bulk = b >= BULK_BIN0;
+    const unsigned bit = (!bulk && y16) ? 2u : 1u;
+    if (d.fillReady[b] & bit) return YB_OK;
+    FillFn fn = bulk ? fill_fn2(b) : fill_fn(b, y16, false);
+    const size_t sm = bulk ? fill2_smem(b) : fill_smem(b);
+    const int threads = bulk ? F2_WARPS * 32 : kBin[b].G * kBin[b].P * 32;
+    CUDA_TRY(d, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int occ = 0;
+    CUDA_TRY(d, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, sm));
+    d.fillBlocks[b] = std::max(occ, 1) * d.sms;
+    d.fillReady[b] |= bit;
     return YB_OK;
 }
 
@@ -928,6 +930,11 @@ int slot_launch(Device &d, Slot &s, bool d2h, int fillSplit = 1) {
         s.binOnSide[b] = false;
         if (!((s.launchMask >> b) & 1u)) continue;
         const BinCfg &bc = kBin[b];
+        if (!s.binStream[b]) {
+            CUDA_TRY(d, cudaStreamCreateWithPriority(&s.binStream[b], cudaStreamNonBlocking, d.prioLo));
+            CUDA_TRY(d, cudaEventCreateWithFlags(&s.binDone[b], cudaEventDisableTiming));
+        }
+        if (int rc = ensure_fill(d, b, s.y16)) return rc;
         cudaStream_t bs = s.binStream[b];
         CUDA_TRY(d, cudaStreamWaitEvent(bs, s.ev[3], 0));
         const bool bulk = b >= BULK_BIN0;
@@ -949,6 +956,10 @@ int slot_launch(Device &d, Slot &s, bool d2h, int fillSplit = 1) {
     s.tTbLaunch = now_ms();
     CUDA_TRY(d, cudaEventRecord(s.ev[6], st));
     if (s.nLongMax > 0) {
+        if (!s.binStream[1]) {
+            CUDA_TRY(d, cudaStreamCreateWithPriority(&s.binStream[1], cudaStreamNonBlocking, d.prioLo));
+            CUDA_TRY(d, cudaEventCreateWithFlags(&s.binDone[1], cudaEventDisableTiming));
+        }
         cudaStream_t ls = s.binStream[1];
         CUDA_TRY(d, cudaStreamWaitEvent(ls, s.ev[6], 0));
         yb_traceback_long_kernel<<<(unsigned)((s.nLongMax + 3) / 4), 128, 0, ls>>>(
@@ -1347,7 +1358,8 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     for (auto &d : ctx->devs)
         if (device_init(d) != YB_OK) { fprintf(stderr, "yama_b200: %s\n", d.err.c_str()); yb_destroy(ctx); return YB_ERR_CUDA; }
     if (getenv("YB_PROFILE"))
-        fprintf(stderr, "yama_b200[profile] start-up: driver %.0f ms, contexts + streams + kernel attributes %.0f ms\n", tc1 - tc0, now_ms() - tc1);
+        fprintf(stderr, "yama_b200[profile] start-up: driver %.0f ms, devices %.0f ms (device 0: context %.0f ms, streams + events %.0f ms)\n", tc1 - tc0,
+                now_ms() - tc1, ctx->devs[0].tContext, ctx->devs[0].tStreams);
     int hw = (int)std::thread::hardware_concurrency();
     if (hw < 1) hw = 1;
     ctx->nThreads = std::min(hw, 32);
