@@ -427,10 +427,8 @@ namespace {
 
 typedef void (*FillFn)(const PairMeta *, const int *, const int *, int *, const RowRec *, const ColRec *,
                        unsigned char *, const unsigned long long *, PairOut *, int, int);
-// ungated: the variant without existence multipliers (bulk bins only), for waves of small enough pairs (Slot::ungated)
-FillFn fill_fn(int bin, bool y16, bool ungated = false) {
-    if (ungated && y16 && bin == 0) return yb_fill_kernel_w<128, 1, 8, true, false>;
-    if (ungated && y16 && bin == 1) return yb_fill_kernel_w<512, 1, 8, true, false>;
+// (the form without existence multipliers is fill_body2, the bulk bins: fill_fn2)
+FillFn fill_fn(int bin, bool y16, bool = false) {
     switch (bin) {
         case 0: return y16 ? yb_fill_kernel_w<128, 1, 8, true> : yb_fill_kernel_w<128, 1, 8, false>;
         case 1: return y16 ? yb_fill_kernel_w<512, 1, 8, true> : yb_fill_kernel_w<512, 1, 8, false>;
@@ -1384,6 +1382,7 @@ int yb_create(const int *devices, int ndev, yb_ctx **out) {
     if (const char *e = getenv("YB_FILL_SPLIT")) for (auto &d : ctx->devs) d.fillSplit = std::max(1, atoi(e));
     if (const char *e = getenv("YB_SLACK")) ctx->slackBulk = std::max(1, atoi(e));
     if (const char *e = getenv("YB_UNGATED")) ctx->ungatedOk = atoi(e) != 0;
+    if (!ctx->ungatedOk) ctx->maxCls = 0;   // every pair through the kernels that carry the existence multipliers (fill_body)
     if (const char *e = getenv("YB_KEYED")) if (atoi(e) == 0) ctx->maxCls = std::min(ctx->maxCls, 1);
     if (const char *e = getenv("YB_FILL2")) if (atoi(e) == 0) ctx->maxCls = 0;
     if (const char *e = getenv("YB_TB_LONG")) ctx->tbLong = std::max(1, atoi(e));
