@@ -282,7 +282,7 @@ struct yb_ctx {
     int64_t wavePairs = 1 << 20;
     int tbLong = TB_LONG;                   // paths of at least this many moves: warp-per-path traceback (YB_TB_LONG)
     bool directCopy = true;                 // inputs inside yb_host_alloc memory are copied from where they are (YB_DIRECT=0: always staged)
-    int bandPack = -1;                      // delta-coded bands over PCIe: -1 when the device has >= 12 host threads, YB_BAND_PACK=0/1
+    int bandPack = -1;                      // delta-coded bands over PCIe: -1 when the device has >= 8 host threads, YB_BAND_PACK=0/1
     std::vector<HostBlock> hostBlocks;      // yb_host_alloc
     // results of the last batch
     uint8_t *scriptStore = nullptr;         // pinned (portable): the D2H copies of the waves land here directly
@@ -602,9 +602,9 @@ int slot_prepare(yb_ctx *ctx, Device &d, Slot &s, const yb_job *jobs, int64_t fi
     const double t0 = now_ms();
     // delta-coded bands (yb_band_expand): worth it when the host has threads to spare -- it reads every band row once so
     // that PCIe carries a quarter of it; with few threads per device the copy of the raw rows is the faster way (measured
-    // with 16 threads: cfg3 +21 %, cfg2 +3 % end to end; the coding pass takes 0.5 ms per 16 000 pairs there and would pace
-    // the waves with half the threads)
-    const bool pack = !rawBands && count > 0 && (ctx->bandPack > 0 || (ctx->bandPack < 0 && d.helpers >= 12));
+    // on cfg2, end to end: 16 threads 12.7 -> 12.2 ms, 8 threads 12.7 -> 11.6 ms, 4 threads 15.3 ms with it -- the coding pass
+    // then paces the waves; cfg3 with 16 threads +21 %)
+    const bool pack = !rawBands && count > 0 && (ctx->bandPack > 0 || (ctx->bandPack < 0 && d.helpers >= 8));
     s.tPack0 = t0;
     s.first = first;
     s.off.resize((size_t)count + 1);
