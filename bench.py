@@ -387,6 +387,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if args.workload == "cfg2real":
+            emit({"impl": "reference", "unavailable": "cfg2real replays jobs recorded by the GPU tool; the reference arm runs the synthetic workloads (cfg2, cfg3, cfg5)"})
+            return
         procs = os.cpu_count() or 1
         vals = []
         for s in range(args.warmup + args.steps):
