@@ -3,6 +3,7 @@
 O=gpurun_out
 mkdir -p $O
 L=$PWD/multiz_b200
+[ -f $L/libyama_b200_sync.so ] || make -C multiz_b200/csrc sanitize > $O/r2z_make_sanitize.log 2>&1      # (same image on the box: nvcc is there)
 timeout 600 python -m pytest tests -m gpu -x -q > $O/r2z_pytest_gpu.txt 2>&1
 tail -4 $O/r2z_pytest_gpu.txt
 timeout 300 python bench.py > $O/r2z_bench.json 2> $O/r2z_bench.err
@@ -17,12 +18,6 @@ $NCU -k 'regex:yb_fill_kernel_w<.int.1024' -s 3 -c 1 -f -o $O/r2z_fill_cta pytho
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2z_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/r2z_ncu_bench.log 2>&1
 YAMA_B200_LIB=$L/libyama_b200_sync.so timeout 400 compute-sanitizer --tool racecheck --print-limit 100 python tools/sanitize_probe.py > $O/r2z_racecheck_sync.log 2>&1
 tail -3 $O/r2z_racecheck_sync.log
-YAMA_B200_LIB=$L/libyama_b200_c5.so timeout 200 python bench.py --workload cfg5 --steps 5 --no-cpu-baseline > $O/r2z_bench_cfg5_c5.json 2>> $O/r2z_bench.err
-python -c "import json
-for f in ('r2z_bench_cfg5.json','r2z_bench_cfg5_c5.json'):
-    try:
-        d=json.load(open('$O/'+f)); print(f, d['value'], d['kernel_split_ms'], d['e2e']['value'])
-    except Exception as e: print(f, e)"
 timeout 300 compute-sanitizer --tool racecheck --print-limit 100 python tools/sanitize_probe.py > $O/r2z_racecheck_shipped.log 2>&1
 tail -3 $O/r2z_racecheck_shipped.log
 timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_probe.py > $O/r2z_memcheck.log 2>&1
